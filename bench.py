@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRF++ ray-marching hot path on B200 (BASELINE.json metric: rays/sec, 4096 rays x
+(64 coarse + 128 importance) samples, 8x256 MLP, depth_loss=mse -- configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole path over one batch of 4096 rays per GPU: intersect_sphere ->
+stratified coarse depths -> NerfNet.forward (level 0, 64+64 samples) -> sample_pdf + merge (fg, bg)
+-> NerfNet.forward (level 1, 192+192 samples) -> rgb MSE + depth loss per level; for N > 1 each rank
+renders its contiguous band of the 4096*N-ray batch and one NCCL all-gather collects the rendered
+(rgb, depth) tiles.  `value` times that with inputs resident in HBM; `e2e` times the same through
+the public API from pinned host buffers with the H2D/D2H copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "outdoor-nerf-depth_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+N_RAYS = 4096
+CASCADE = (64, 128)
+LAMBDA_DEPTH = 0.1          # scripts/train.sh:5
+DEPTH_SIGMA, DEPTH_SCALE = 0.01, 0.05
+MACS_FG, MACS_BG = 593408, 604160      # per sample, SURVEY.md section 8(d)
+METRIC = "rays/sec (4096 rays x 128 samples, 8x256 MLP)"
+WORKLOAD = ("NeRF++ configs[1]: 4096 rays/GPU, cascade 64 -> +128 (192 fine) fg and bg, depth_loss=mse lambda=0.1, "
+            "forward of both levels + sampling + composite + losses")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def make_rays(n, seed):
+    import nerfpp_oracle as O   # synthetic workload generator only (inputs, not results)
+    return O.synthetic_rays(n, seed=seed, depth_scale=DEPTH_SCALE)
+
+
+def make_models(device):
+    from types import SimpleNamespace
+    import ddp_model
+    args = SimpleNamespace(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True)
+    torch.manual_seed(777)   # ddp_train_nerf.py:308
+    nets = [ddp_model.NerfNetWithAutoExpo(args) for _ in CASCADE]
+    with torch.no_grad():
+        for n in nets:        # non-degenerate density
+            n.nerf_net.fg_net.sigma_layers[0].bias += 5.0
+            n.nerf_net.bg_net.sigma_layers[0].bias += 5.0
+    return [n.to(device) for n in nets]
+
+
+def run_ours(args):
+    import nerfpp_b200
+    from nerfpp_b200 import _lib, ops, render_rays
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    models = make_models(dev)
+    host = make_rays(N_RAYS, seed=rank)                 # this rank's band of the global 4096*world batch
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    gathered = torch.empty(world * N_RAYS, 4, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(b):
+        with torch.no_grad():
+            res = render_rays(models, b, CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH,
+                              depth_sigma=DEPTH_SIGMA)
+            ret = res["levels"][-1][0]
+            if world > 1:
+                tile = torch.cat((ret["rgb"], ret["depth"][:, None]), -1)
+                dist.all_gather_into_tensor(gathered, tile)
+        return res, ret
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(batch)
+    barrier()
+    # ---- timed: K steps, device time per step by CUDA events, L2 flushed between steps ----
+    ops.LAUNCHES[0] = 0
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            step(batch)
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    launches = ops.LAUNCHES[0]
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * N_RAYS / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host buffers -> H2D -> path -> D2H of rgb/depth/loss, wall clock ----
+    def e2e_step():
+        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        res, ret = step(b)
+        out = torch.cat((ret["rgb"], ret["depth"][:, None]), -1) if world == 1 else gathered
+        h = out.cpu()
+        loss = [l.cpu() for l in res["losses"]]
+        return h, loss
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e2e_step()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_RAYS * args.steps / float(t_e2e.item())
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    d2h = (world * N_RAYS * 4 * 4 if world > 1 else N_RAYS * 4 * 4) + 2 * 4 * 4
+
+    # ---- roofline of the dominant kernel (field_tc_kernel), timed alone with CUDA events ----
+    roof = field_roofline(models, batch, dev)
+    cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "global_rays": world * N_RAYS,
+                       "cascade_samples": list(CASCADE), "unit_of_work": "U2 forward (SURVEY 8(d)): 2.512 TFLOP algorithmic per 4096 rays",
+                       "l2": "flushed between timed steps (256 MiB write)", "field": "tcgen05" if ops.default_field_impl() == 0 else "simt",
+                       "parallelism": "rays sharded in contiguous bands, %d rank(s), 1 NCCL all-gather/step" % world if world > 1 else "single GPU",
+                       "wall_s_timed_region": t_wall},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def field_roofline(models, batch, dev, reps=10):
+    """Average duration of the field kernel's four launches in a step (coarse/fine x fg/bg), each
+    timed alone with CUDA events on the launching stream; achieved = algorithmic FLOPs / time."""
+    from nerfpp_b200 import cascade_forward, ops
+    burst, sustained, hbm, how = peaks()
+    with torch.no_grad():
+        out, far = cascade_forward(models, batch["ray_o"], batch["ray_d"], batch["min_depth"], CASCADE, train=True)
+    impl = ops.default_field_impl()
+    flops = tot_ms = 0.0
+    n_launch = 0
+    with torch.no_grad():
+        for m, (ret, fg_z, bg_z) in enumerate(out):
+            net = models[m].nerf_net
+            for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), MACS_FG), (1, bg_z, net.bg_net.tensors(), MACS_BG)):
+                packed = net._packed[is_bg].get(tensors, impl)
+                for _ in range(3):
+                    ops.field_forward(packed, is_bg, batch["ray_o"], batch["ray_d"], z, impl)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    ops.field_forward(packed, is_bg, batch["ray_o"], batch["ray_d"], z, impl)
+                b.record()
+                torch.cuda.synchronize()
+                tot_ms += a.elapsed_time(b) / reps
+                flops += 2.0 * macs * z.numel()
+                n_launch += 1
+    achieved = flops / (tot_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "field_tc_kernel" if impl == 0 else "field_simt_kernel", "achieved": achieved, "peak": burst,
+            "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
+            "launches_per_step": n_launch, "avg_launch_ms": tot_ms / n_launch, "algorithmic_flops_per_step": flops}
+
+
+def reference_step(levels, rays, O):
+    """The reference's cascade loop (ddp_train_nerf.py:432-493) restated by the oracle port, no_grad forward + losses."""
+    with torch.no_grad():
+        out, far = O.cascade_forward(levels, rays["ray_o"], rays["ray_d"], rays["min_depth"], CASCADE,
+                                     O.synthetic_rand(rays["ray_o"].shape[0], CASCADE, seed=1))
+        for ret, fg_z, _ in out:
+            O.level_loss(ret, rays["rgb"], rays["depth_sup"], fg_z, far, True, "mse", LAMBDA_DEPTH, DEPTH_SIGMA * DEPTH_SCALE)
+
+
+def cpu_baseline(sample=1024):
+    import nerfpp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    reference_step(levels, make_rays(64, 5), O)     # warm-up
+    rays = make_rays(sample, 6)
+    t0 = time.perf_counter()
+    reference_step(levels, rays, O)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d rays of the same workload (oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference, "
+                      "all host threads), %.1f s" % (sample, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm for the path on the host cores (the oracle port;
+    /root/reference is Python+torch and does not travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import nerfpp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 512
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    rays = make_rays(sample, 6)
+    for _ in range(max(min(args.warmup, 1), 1)):
+        reference_step(levels, make_rays(64, 5), O)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        reference_step(levels, rays, O)
+    dt = (time.perf_counter() - t0) / steps
+    v = sample / dt
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": 1,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_rays_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d rays/step of the same workload, torch-CPU fp32, %d threads" % (sample, cores)},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+/*
+ * nerfpp_b200.h -- C ABI of the B200-native NeRF++ ray-marching hot path.
+ *
+ * Drop-in boundary for the one path BASELINE.json names: hierarchical
+ * sampling -> positional-encoded 8x256 MLP -> transmittance composite -> rgb + depth-prior loss.
+ * The reference (cwchenwang/outdoor-nerf-depth) has no FFI for this path -- it is plain PyTorch
+ * modules -- so every entry point cites the reference Python symbol it replaces
+ * (paths relative to nerf-methods/nerfplusplus/).  The reference-side binding is the ctypes stub in
+ * outdoor-nerf-depth_b200/nerfpp_b200/_lib.py, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless stated otherwise.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises unless stated.
+ *   - the library owns nothing past a call: outputs and workspaces are caller-allocated.
+ *   - return value: 0 on success, >0 a cudaError_t, <0 an argument error; never throws.
+ *     nerfpp_last_error() returns a static, thread-local text for the last non-zero return.
+ *   - compiled for sm_100a only; there is no CPU path.
+ */
+#ifndef NERFPP_B200_H_
+#define NERFPP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFPP_ABI_VERSION 1
+
+/* Network shape: the only one the reference scripts use (configs/kitti.txt:36-40):
+ * netdepth 8, netwidth 256, skips [4], max_freq_log2 10, max_freq_log2_viewdirs 4. */
+#define NERFPP_WIDTH 256
+#define NERFPP_DEPTH 8
+#define NERFPP_NFREQ_POS 10
+#define NERFPP_NFREQ_VIEW 4
+#define NERFPP_NLAYERS 12 /* base 0..7, sigma, base_remap, rgb.0, rgb.2 */
+
+/* Parameters of one MLPNet (nerf_network.py:70-118) as the torch state_dict holds them:
+ * w[i] is nn.Linear.weight [out,in] row-major, b[i] is nn.Linear.bias [out].
+ * order: base_layers.0..7.0, sigma_layers.0, base_remap_layers.0, rgb_layers.0, rgb_layers.2 */
+typedef struct NerfppNetParams {
+  const float* w[NERFPP_NLAYERS];
+  const float* b[NERFPP_NLAYERS];
+} NerfppNetParams;
+
+/* Gradients wrt the same tensors (same shapes). Accumulated INTO (+=), caller zero-fills. */
+typedef struct NerfppNetGrads {
+  float* w[NERFPP_NLAYERS];
+  float* b[NERFPP_NLAYERS];
+} NerfppNetGrads;
+
+/* Field evaluators. TC = tcgen05 tensor-core path (fp16 operands, fp32 accumulate in TMEM);
+ * SIMT = plain fp32 FFMA path (bit-for-bit fp32 arithmetic, ~20x slower; the cross-check). */
+enum { NERFPP_FIELD_TC = 0, NERFPP_FIELD_SIMT = 1 };
+
+int nerfpp_abi_version(void);
+const char* nerfpp_last_error(void);
+
+/* ---- A1: intersect_sphere (ddp_train_nerf.py:51-66) -------------------------------------- */
+/* out_far[n]; *out_unbounded (int32, device) is set non-zero when any ||p||^2 >= 1, the
+ * condition on which the reference raises (ddp_train_nerf.py:62-63).  Caller zero-fills it. */
+int nerfpp_intersect_sphere(const float* ray_o, const float* ray_d, int n_rays, float* out_far,
+                            int32_t* out_unbounded, void* stream);
+
+/* ---- A2+A3: coarse depths (ddp_train_nerf.py:441-449 train / 168-175 test) ---------------- */
+/* fg: z[i] = near + i*((far-near)/(S-1)).  bg: z[i] = bg_base[i] (the reference's
+ * torch.linspace(0,1,S), supplied by the caller so its rounding is the framework's).
+ * t_rand_fg / t_rand_bg [n,S]: the torch.rand_like draw of perturb_samples
+ * (ddp_train_nerf.py:69-78); NULL = no perturbation (test-time path). */
+int nerfpp_coarse_depths(const float* near, const float* far, const float* bg_base, int n_rays,
+                         int n_samples, const float* t_rand_fg, const float* t_rand_bg,
+                         float* out_fg_z, float* out_bg_z, void* stream);
+
+/* perturb_samples (ddp_train_nerf.py:69-78) on caller-supplied depths z [n,S]; out_z must not alias z. */
+int nerfpp_perturb_samples(const float* z, const float* t_rand, int n_rays, int n_samples, float* out_z,
+                           void* stream);
+
+/* ---- A4: sample_pdf (ddp_train_nerf.py:81-130) ------------------------------------------- */
+/* bins [n, M+1] (row stride bins_ld), weights [n, M] (row stride w_ld, so the trainer's
+ * weights[..., 1:-1] slice needs no copy), u [n, Ns] with row stride u_ld (0 = one shared row:
+ * the det=True linspace).  out_samples [n,Ns]; out_above (int32 [n,Ns]) and out_cdf
+ * ([n,M+1]) optional (NULL to skip).  Index contract: above = #{j<M : u >= cdf[j]}. */
+int nerfpp_sample_pdf(const float* bins, int bins_ld, const float* weights, int w_ld,
+                      const float* u, int u_ld, int n_rays, int M, int n_new,
+                      float* out_samples, int32_t* out_above, float* out_cdf, void* stream);
+/* Same search + interpolation on a caller-supplied cdf [n, M+1]: given identical (cdf,u) the
+ * indices and samples are bit-identical to the reference's. */
+int nerfpp_sample_cdf(const float* bins, int bins_ld, const float* cdf, int cdf_ld,
+                      const float* u, int u_ld, int n_rays, int M, int n_new,
+                      float* out_samples, int32_t* out_above, void* stream);
+
+/* ---- A4+A5 fused: one cascade refinement (ddp_train_nerf.py:452-457 / 460-465) ------------ */
+/* mids of z_prev -> sample_pdf(weights_prev[1:-1]) -> sort(cat(z_prev, new)).
+ * z_prev, w_prev [n,Sp]; u [n,Ns] (u_ld 0 = shared row); out_z [n, Sp+Ns] ascending. */
+int nerfpp_resample_merge(const float* z_prev, const float* w_prev, const float* u, int u_ld,
+                          int n_rays, int n_prev, int n_new, float* out_z, void* stream);
+
+/* ---- packed weights ---------------------------------------------------------------------- */
+/* The field kernels read a repacked copy of one net's parameters (transposed / padded fp32
+ * for SIMT, fp16 UMMA-swizzled K-major tiles + fp32 tails for TC). Size query then pack;
+ * re-pack whenever the parameters change (the Python shim keys it on tensor._version). */
+int64_t nerfpp_packed_bytes(int is_bg, int field_impl);
+int nerfpp_pack_weights(const NerfppNetParams* params, int is_bg, int field_impl, void* out_packed,
+                        void* stream);
+
+/* ---- A6+A7+A8: embed + MLP per sample (nerf_network.py:42-60,120-142; ddp_model.py:16-45) -- */
+/* Evaluates one net on every sample of every ray.
+ *   fg (is_bg=0): pts = ray_o + z*ray_d, sample order as given.
+ *   bg (is_bg=1): pts = depth2pts_outside(ray_o, ray_d, z) = (x',y',z',1/r); outputs are written
+ *                 in the reference's FLIPPED order (ddp_model.py:116-117): out[., j] belongs to
+ *                 z[., S-1-j]; out_depth_real [n,S] likewise (may be NULL for fg).
+ * out_sigma [n,S] (after abs), out_rgb [n,S,3] (after sigmoid). */
+int nerfpp_field_forward(const void* packed, int is_bg, int field_impl, const float* ray_o,
+                         const float* ray_d, const float* z, int n_rays, int n_samples,
+                         float* out_sigma, float* out_rgb, float* out_depth_real, void* stream);
+
+/* depth2pts_outside (ddp_model.py:16-45) as a standalone op: ray_o, ray_d [n,3] and depth [n]
+ * already expanded per sample -> out_pts [n,4] = (x',y',z',1/r), out_depth_real [n]. */
+int nerfpp_depth2pts_outside(const float* ray_o, const float* ray_d, const float* depth, int64_t n,
+                             float* out_pts, float* out_depth_real, void* stream);
+
+/* ---- A9+A10: composite ("raw2outputs", ddp_model.py:95-134) ------------------------------- */
+typedef struct NerfppRenderOut { /* the 10 keys of NerfNet.forward's OrderedDict */
+  float* rgb;        /* [n,3] */
+  float* fg_weights; /* [n,S_fg] */
+  float* bg_weights; /* [n,S_bg] flipped order, as the reference returns it */
+  float* fg_dists;   /* [n,S_fg] */
+  float* fg_rgb;     /* [n,3] */
+  float* fg_depth;   /* [n] */
+  float* bg_rgb;     /* [n,3]  already scaled by bg_lambda */
+  float* bg_depth;   /* [n]    already scaled by bg_lambda */
+  float* bg_lambda;  /* [n] */
+  float* depth;      /* [n] */
+} NerfppRenderOut;
+
+int nerfpp_composite(const float* ray_d, const float* fg_z_max, const float* fg_z,
+                     const float* bg_z, const float* fg_sigma, const float* fg_rgb,
+                     const float* bg_sigma, const float* bg_rgb, const float* bg_depth_real,
+                     int n_rays, int s_fg, int s_bg, const NerfppRenderOut* out, void* stream);
+
+/* ---- A11: NerfNet.forward (ddp_model.py:74-147) in one call -------------------------------- */
+/* workspace: nerfpp_forward_workspace_bytes(n, s_fg, s_bg) bytes of device memory; holds the
+ * per-sample sigma/rgb/depth_real (kept for backward). */
+int64_t nerfpp_forward_workspace_bytes(int n_rays, int s_fg, int s_bg);
+int nerfpp_forward(const void* packed_fg, const void* packed_bg, int field_impl,
+                   const float* ray_o, const float* ray_d, const float* fg_z_max,
+                   const float* fg_z, const float* bg_z, int n_rays, int s_fg, int s_bg,
+                   const NerfppRenderOut* out, void* workspace, void* stream);
+
+/* ---- A12-A14: losses (utils.py:12-16, depth_loss.py:4-44, ddp_train_nerf.py:481-493) ------- */
+enum { NERFPP_DEPTH_NONE = 0, NERFPP_DEPTH_MSE = 1, NERFPP_DEPTH_L1 = 2, NERFPP_DEPTH_KL = 3 };
+/* out_loss[4] (device) = { img2mse(rgb, rgb_gt), depth loss, rgb + lambda*depth, #valid rays }.
+ * mse/l1: mean over rays with depth_sup > 0 (NaN when none, like the reference);
+ * kl: depth_kl(fg_weights, depth_sup, fg_z, fg_dists, kl_sigma, fg_z_max): sum over rays with
+ * 0 < depth_sup < fg_z_max, divided by S.  workspace: nerfpp_loss_workspace_bytes(). */
+int64_t nerfpp_loss_workspace_bytes(void);
+int nerfpp_loss(const float* rgb, const float* rgb_gt, const float* depth, const float* depth_sup,
+                const float* fg_weights, const float* fg_z, const float* fg_dists,
+                const float* fg_z_max, int n_rays, int s_fg, int depth_loss_type,
+                float lambda_depth, float kl_sigma, float* out_loss, void* workspace,
+                void* stream);
+
+/* The depth term alone (the drop-in depth_loss.depth_mse/l1/kl entry points): same out_loss[4]
+ * layout with out_loss[0] = 0; and its backward: out_grad = d(loss)/d(depth) [n] for mse/l1,
+ * d(loss)/d(fg_weights) [n,S] for kl, times the upstream scalar *grad_out (device). fwd_out is
+ * the forward's out_loss (supplies the valid-ray count). */
+int nerfpp_depth_loss(const float* depth, const float* depth_sup, const float* fg_weights,
+                      const float* fg_z, const float* fg_dists, const float* fg_z_max, int n_rays,
+                      int s_fg, int depth_loss_type, float kl_sigma, float* out_loss, void* workspace,
+                      void* stream);
+int nerfpp_depth_loss_backward(const float* depth, const float* depth_sup, const float* fg_weights,
+                               const float* fg_z, const float* fg_dists, const float* fg_z_max,
+                               int n_rays, int s_fg, int depth_loss_type, float kl_sigma,
+                               const float* fwd_out, const float* grad_out, float* out_grad,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFPP_B200_H_ */

@@ -1,0 +1,90 @@
+// extern "C" entry points that tie the kernels together (include/nerfpp_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+// defined in field_simt.cu / field_tc.cu
+size_t npp_simt_packed_bytes(bool bg);
+int npp_pack_simt(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
+int npp_field_simt(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
+                   float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st);
+size_t npp_tc_packed_bytes(bool bg);
+int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
+int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
+                 float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void npp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int nerfpp_abi_version(void) { return NERFPP_ABI_VERSION; }
+extern "C" const char* nerfpp_last_error(void) { return g_err; }
+
+extern "C" int64_t nerfpp_packed_bytes(int is_bg, int field_impl) {
+  if (field_impl == NERFPP_FIELD_SIMT) return (int64_t)npp_simt_packed_bytes(is_bg != 0);
+  if (field_impl == NERFPP_FIELD_TC) return (int64_t)npp_tc_packed_bytes(is_bg != 0);
+  return -1;
+}
+
+extern "C" int nerfpp_pack_weights(const NerfppNetParams* params, int is_bg, int field_impl, void* out_packed, void* stream) {
+  NPP_CHECK_ARG(params && out_packed, "null argument");
+  for (int l = 0; l < NERFPP_NLAYERS; ++l) NPP_CHECK_ARG(params->w[l] && params->b[l], "null parameter tensor");
+  if (field_impl == NERFPP_FIELD_SIMT) return npp_pack_simt(params, is_bg != 0, out_packed, (cudaStream_t)stream);
+  if (field_impl == NERFPP_FIELD_TC) return npp_pack_tc(params, is_bg != 0, out_packed, (cudaStream_t)stream);
+  NPP_CHECK_ARG(false, "unknown field_impl");
+}
+
+extern "C" int nerfpp_field_forward(const void* packed, int is_bg, int field_impl, const float* ray_o, const float* ray_d,
+                                    const float* z, int n_rays, int n_samples, float* out_sigma, float* out_rgb,
+                                    float* out_depth_real, void* stream) {
+  NPP_CHECK_ARG(packed && ray_o && ray_d && z && out_sigma && out_rgb, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "bad shape");
+  NPP_CHECK_ARG(!is_bg || out_depth_real, "background needs out_depth_real");
+  if (n_rays == 0) return 0;
+  if (field_impl == NERFPP_FIELD_SIMT)
+    return npp_field_simt(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, (cudaStream_t)stream);
+  if (field_impl == NERFPP_FIELD_TC)
+    return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, (cudaStream_t)stream);
+  NPP_CHECK_ARG(false, "unknown field_impl");
+}
+
+// workspace of nerfpp_forward: fg sigma [n,Sf], fg rgb [n,Sf,3], bg sigma [n,Sb], bg rgb [n,Sb,3], bg depth_real [n,Sb]
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct FwdWs { float *fg_sigma, *fg_rgb, *bg_sigma, *bg_rgb, *bg_dr; size_t bytes; };
+static FwdWs carve(void* base, int n, int sf, int sb) {
+  FwdWs w;
+  char* p = (char*)base;
+  size_t o = 0;
+  w.fg_sigma = (float*)(p + o); o += align256((size_t)n * sf * 4);
+  w.fg_rgb = (float*)(p + o); o += align256((size_t)n * sf * 12);
+  w.bg_sigma = (float*)(p + o); o += align256((size_t)n * sb * 4);
+  w.bg_rgb = (float*)(p + o); o += align256((size_t)n * sb * 12);
+  w.bg_dr = (float*)(p + o); o += align256((size_t)n * sb * 4);
+  w.bytes = o;
+  return w;
+}
+
+extern "C" int64_t nerfpp_forward_workspace_bytes(int n_rays, int s_fg, int s_bg) {
+  if (n_rays < 0 || s_fg < 1 || s_bg < 1) return -1;
+  return (int64_t)carve(nullptr, n_rays, s_fg, s_bg).bytes;
+}
+
+extern "C" int nerfpp_forward(const void* packed_fg, const void* packed_bg, int field_impl, const float* ray_o,
+                              const float* ray_d, const float* fg_z_max, const float* fg_z, const float* bg_z, int n_rays,
+                              int s_fg, int s_bg, const NerfppRenderOut* out, void* workspace, void* stream) {
+  NPP_CHECK_ARG(packed_fg && packed_bg && workspace && out, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && s_fg >= 1 && s_bg >= 1, "bad shape");
+  if (n_rays == 0) return 0;
+  FwdWs w = carve(workspace, n_rays, s_fg, s_bg);
+  int rc = nerfpp_field_forward(packed_fg, 0, field_impl, ray_o, ray_d, fg_z, n_rays, s_fg, w.fg_sigma, w.fg_rgb, nullptr, stream);
+  if (rc) return rc;
+  rc = nerfpp_field_forward(packed_bg, 1, field_impl, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr, stream);
+  if (rc) return rc;
+  return nerfpp_composite(ray_d, fg_z_max, fg_z, bg_z, w.fg_sigma, w.fg_rgb, w.bg_sigma, w.bg_rgb, w.bg_dr, n_rays, s_fg,
+                          s_bg, out, stream);
+}

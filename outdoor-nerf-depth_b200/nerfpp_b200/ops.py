@@ -1,0 +1,352 @@
+"""Torch-facing wrappers over the C ABI (include/nerfpp_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping.
+All arithmetic of the hot path happens in libnerfpp_b200.so; nothing in this module computes a
+result with torch ops (the only torch maths is the RNG draw and the linspace constants whose
+rounding has to be the framework's own).  No CPU fallback: CPU tensors raise.
+"""
+import ctypes
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._lib import DEPTH_KL, DEPTH_L1, DEPTH_MSE, DEPTH_NONE, FIELD_SIMT, FIELD_TC, NerfppError, check
+
+LAYER_NAMES = (["base_layers.%d.0" % i for i in range(8)]
+               + ["sigma_layers.0", "base_remap_layers.0", "rgb_layers.0", "rgb_layers.2"])
+RET_KEYS = ("rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth",
+            "bg_lambda", "depth")
+LAUNCHES = [0]   # kernels of libnerfpp_b200.so launched through this module (bench.py reads it)
+_KERNELS_PER_CALL = {"intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
+                     "resample_merge": 1, "pack_weights": 1, "field_forward": 1, "forward": 3, "loss": 2}
+
+
+def check(rc, what):   # noqa: F811  (wraps _lib.check to count launches)
+    _lib.check(rc, what)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
+
+
+UNBOUNDED_MSG = ("Not all your cameras are bounded by the unit sphere; please make sure the cameras are "
+                 "normalized properly!")   # ddp_train_nerf.py:63
+
+
+def default_field_impl():
+    """NERFPP_FIELD=simt selects the plain-fp32 evaluator (cross-check); default is tcgen05."""
+    return FIELD_SIMT if os.environ.get("NERFPP_FIELD", "tc").lower() == "simt" else FIELD_TC
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise NerfppError("%s is on %s: this path only exists as CUDA kernels (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def _c(t, name, ndim=None):
+    return _chk(t, name, ndim).detach().contiguous()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _rows(t):
+    """Flattens leading dims: [..., S] -> ([n, S] contiguous, leading shape)."""
+    lead = tuple(t.shape[:-1])
+    return t.reshape(-1, t.shape[-1]).contiguous(), lead
+
+
+# ------------------------------------------------------------------------------------------------
+# A1-A5 sampling
+# ------------------------------------------------------------------------------------------------
+def intersect_sphere(ray_o, ray_d):
+    """ddp_train_nerf.py:51-66. ray_o, ray_d [..., 3] -> [...]. Raises like the reference when a
+    camera is outside the unit sphere (same data-dependent host sync as its ``.any()``)."""
+    o, lead = _rows(_c(ray_o, "ray_o"))
+    d, _ = _rows(_c(ray_d, "ray_d"))
+    if o.shape[-1] != 3 or d.shape != o.shape:
+        raise ValueError("ray_o/ray_d must be [..., 3] of equal shape")
+    n = o.shape[0]
+    far = torch.empty(n, device=o.device, dtype=torch.float32)
+    flag = torch.zeros(1, device=o.device, dtype=torch.int32)
+    with torch.cuda.device(o.device):
+        check(_lib.lib().nerfpp_intersect_sphere(_p(o), _p(d), n, _p(far), _p(flag), _stream()), "intersect_sphere")
+    if int(flag.item()) != 0:
+        raise Exception(UNBOUNDED_MSG)
+    return far.reshape(lead)
+
+
+_LINSPACE = {}
+
+
+def linspace01(n, device):
+    """torch.linspace(0,1,n) computed on the CPU exactly as the reference does
+    (ddp_train_nerf.py:447 builds it on the host and moves it), cached per device."""
+    key = (n, str(device))
+    if key not in _LINSPACE:
+        _LINSPACE[key] = torch.linspace(0., 1., n).to(device)
+    return _LINSPACE[key]
+
+
+def coarse_depths(near, far, n_samples, t_rand_fg=None, t_rand_bg=None):
+    """ddp_train_nerf.py:441-449 / 168-175 fused with perturb_samples. near, far [n] -> fg_z, bg_z [n,S]."""
+    near, far = _c(near, "near", 1), _c(far, "far", 1)
+    n = near.shape[0]
+    fg = torch.empty(n, n_samples, device=near.device, dtype=torch.float32)
+    bg = torch.empty_like(fg)
+    tf = _c(t_rand_fg, "t_rand_fg", 2) if t_rand_fg is not None else None
+    tb = _c(t_rand_bg, "t_rand_bg", 2) if t_rand_bg is not None else None
+    for t in (tf, tb):
+        if t is not None and tuple(t.shape) != (n, n_samples):
+            raise ValueError("t_rand must be [n, S]")
+    with torch.cuda.device(near.device):
+        check(_lib.lib().nerfpp_coarse_depths(_p(near), _p(far), _p(linspace01(n_samples, near.device)), n, n_samples,
+                                              _p(tf), _p(tb), _p(fg), _p(bg), _stream()), "coarse_depths")
+    return fg, bg
+
+
+def perturb_samples(z_vals, t_rand=None):
+    """ddp_train_nerf.py:69-78; the torch.rand_like draw (:75) stays in torch (H3) unless supplied."""
+    z, lead = _rows(_c(z_vals, "z_vals"))
+    if t_rand is None:
+        t_rand = torch.rand_like(z)
+    t, _ = _rows(_c(t_rand, "t_rand"))
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        check(_lib.lib().nerfpp_perturb_samples(_p(z), _p(t), z.shape[0], z.shape[1], _p(out), _stream()), "perturb_samples")
+    return out.reshape(lead + (z.shape[1],))
+
+
+def _u_rows(u, n, n_new, device):
+    if u.dim() == 1:
+        u = _c(u, "u")
+        return u, 0
+    u, _ = _rows(_c(u, "u"))
+    if u.shape != (n, n_new):
+        raise ValueError("u must be [n, N_samples]")
+    return u, n_new
+
+
+def sample_pdf(bins, weights, N_samples, det=False, u=None, return_aux=False):
+    """ddp_train_nerf.py:81-130. bins [..., M+1], weights [..., M] -> [..., N_samples].
+    ``u`` overrides the draw (tests); otherwise linspace (det) or torch.rand (:102-107)."""
+    b, lead = _rows(_c(bins, "bins"))
+    w = _chk(weights, "weights").detach()
+    M = w.shape[-1]
+    w = w.reshape(-1, M)
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    n = b.shape[0]
+    if b.shape[1] != M + 1 or w.shape[0] != n:
+        raise ValueError("bins must be [..., M+1] for weights [..., M]")
+    if u is None:
+        u = linspace01(N_samples, b.device) if det else torch.rand(n, N_samples, device=b.device)
+    uu, u_ld = _u_rows(u, n, N_samples, b.device)
+    out = torch.empty(n, N_samples, device=b.device, dtype=torch.float32)
+    above = torch.empty(n, N_samples, device=b.device, dtype=torch.int32) if return_aux else None
+    cdf = torch.empty(n, M + 1, device=b.device, dtype=torch.float32) if return_aux else None
+    with torch.cuda.device(b.device):
+        check(_lib.lib().nerfpp_sample_pdf(_p(b), M + 1, _p(w), w.stride(0) if n > 1 else M, _p(uu), u_ld, n, M,
+                                           N_samples, _p(out), _p(above), _p(cdf), _stream()), "sample_pdf")
+    out = out.reshape(lead + (N_samples,))
+    return (out, cdf, above) if return_aux else out
+
+
+def sample_cdf(bins, cdf, u):
+    """Search + interpolation on a supplied cdf [n, M+1] (bit-exact contract). Returns (samples, above)."""
+    b, c = _c(bins, "bins", 2), _c(cdf, "cdf", 2)
+    n, M = c.shape[0], c.shape[1] - 1
+    n_new = u.shape[-1]
+    uu, u_ld = _u_rows(u, n, n_new, b.device)
+    out = torch.empty(n, n_new, device=b.device, dtype=torch.float32)
+    above = torch.empty(n, n_new, device=b.device, dtype=torch.int32)
+    with torch.cuda.device(b.device):
+        check(_lib.lib().nerfpp_sample_cdf(_p(b), M + 1, _p(c), M + 1, _p(uu), u_ld, n, M, n_new, _p(out), _p(above),
+                                           _stream()), "sample_cdf")
+    return out, above
+
+
+def resample_merge(z_prev, w_prev, N_samples, det=False, u=None):
+    """One cascade refinement, ddp_train_nerf.py:452-457: mids -> sample_pdf(w[1:-1]) -> sort(cat)."""
+    z, w = _c(z_prev, "z_prev", 2), _c(w_prev, "w_prev", 2)
+    n, sp = z.shape
+    if w.shape != z.shape:
+        raise ValueError("weights must match depths")
+    if u is None:
+        u = linspace01(N_samples, z.device) if det else torch.rand(n, N_samples, device=z.device)
+    uu, u_ld = _u_rows(u, n, N_samples, z.device)
+    out = torch.empty(n, sp + N_samples, device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        check(_lib.lib().nerfpp_resample_merge(_p(z), _p(w), _p(uu), u_ld, n, sp, N_samples, _p(out), _stream()),
+              "resample_merge")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# packed weights
+# ------------------------------------------------------------------------------------------------
+class PackedNet:
+    """Cache of one MLPNet's repacked parameters, re-packed when any parameter's version or
+    storage changes (optimizer steps bump ``_version``)."""
+
+    def __init__(self, is_bg):
+        self.is_bg = int(is_bg)
+        self._buf = {}
+        self._key = {}
+
+    def get(self, tensors, impl):
+        """tensors: 24 parameter tensors in LAYER_NAMES order (weight, bias interleaved per layer)."""
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        dev = tensors[0].device
+        if self._key.get(impl) != key or self._buf[impl].device != dev:
+            nbytes = _lib.lib().nerfpp_packed_bytes(self.is_bg, impl)
+            buf = self._buf.get(impl)
+            if buf is None or buf.numel() != nbytes or buf.device != dev:
+                buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            ps = net_params_struct(tensors)
+            with torch.cuda.device(dev):
+                check(_lib.lib().nerfpp_pack_weights(ctypes.byref(ps), self.is_bg, impl, _p(buf), _stream()), "pack_weights")
+            self._buf[impl], self._key[impl] = buf, key
+        return self._buf[impl]
+
+
+def net_params_struct(tensors):
+    ps = _lib.NetParams()
+    for l in range(_lib.NLAYERS):
+        w, b = tensors[2 * l], tensors[2 * l + 1]
+        for t in (w, b):
+            _chk(t, "parameter")
+            if not t.is_contiguous():
+                raise ValueError("parameters must be contiguous")
+        ps.w[l], ps.b[l] = w.data_ptr(), b.data_ptr()
+    return ps
+
+
+def check_param_shapes(tensors, is_bg):
+    emb = 84 if is_bg else 63
+    want = [(256, emb)] + [(256, 256)] * 4 + [(256, 256 + emb)] + [(256, 256)] * 2 + [(1, 256), (256, 256), (128, 283), (3, 128)]
+    for l, shp in enumerate(want):
+        if tuple(tensors[2 * l].shape) != shp or tuple(tensors[2 * l + 1].shape) != (shp[0],):
+            raise ValueError("layer %s: expected weight %s, got %s -- only the reference's netdepth=8, netwidth=256, "
+                             "max_freq_log2=10, max_freq_log2_viewdirs=4 shape is built (configs/kitti.txt:36-40)"
+                             % (LAYER_NAMES[l], shp, tuple(tensors[2 * l].shape)))
+
+
+# ------------------------------------------------------------------------------------------------
+# A6-A11 forward (+ backward)
+# ------------------------------------------------------------------------------------------------
+def field_forward(packed, is_bg, ray_o, ray_d, z, impl=None):
+    """Per-sample sigma/rgb of one net (embed + MLP). Returns sigma [n,S], rgb [n,S,3], depth_real [n,S] or None."""
+    impl = default_field_impl() if impl is None else impl
+    o, d, zz = _c(ray_o, "ray_o", 2), _c(ray_d, "ray_d", 2), _c(z, "z", 2)
+    n, S = zz.shape
+    sigma = torch.empty(n, S, device=zz.device, dtype=torch.float32)
+    rgb = torch.empty(n, S, 3, device=zz.device, dtype=torch.float32)
+    dr = torch.empty(n, S, device=zz.device, dtype=torch.float32) if is_bg else None
+    with torch.cuda.device(zz.device):
+        check(_lib.lib().nerfpp_field_forward(_p(packed), int(is_bg), impl, _p(o), _p(d), _p(zz), n, S, _p(sigma), _p(rgb),
+                                              _p(dr), _stream()), "field_forward")
+    return sigma, rgb, dr
+
+
+def _alloc_outputs(n, sf, sb, device):
+    shapes = dict(rgb=(n, 3), fg_weights=(n, sf), bg_weights=(n, sb), fg_dists=(n, sf), fg_rgb=(n, 3), fg_depth=(n,),
+                  bg_rgb=(n, 3), bg_depth=(n,), bg_lambda=(n,), depth=(n,))
+    outs = OrderedDict((k, torch.empty(shapes[k], device=device, dtype=torch.float32)) for k in RET_KEYS)
+    st = _lib.RenderOut()
+    for k in RET_KEYS:
+        setattr(st, k, outs[k].data_ptr())
+    return outs, st
+
+
+def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl=None, keep_workspace=False):
+    """NerfNet.forward (ddp_model.py:74-147) without autograd. Returns OrderedDict of the 10 keys
+    (+ the per-sample workspace when keep_workspace)."""
+    impl = default_field_impl() if impl is None else impl
+    o, d = _c(ray_o, "ray_o", 2), _c(ray_d, "ray_d", 2)
+    zmax, fz, bz = _c(fg_z_max, "fg_z_max", 1), _c(fg_z, "fg_z_vals", 2), _c(bg_z, "bg_z_vals", 2)
+    n, sf = fz.shape
+    sb = bz.shape[1]
+    if o.shape != (n, 3) or d.shape != (n, 3) or zmax.shape != (n,) or bz.shape[0] != n:
+        raise ValueError("inconsistent ray batch shapes")
+    L = _lib.lib()
+    ws = torch.empty(max(int(L.nerfpp_forward_workspace_bytes(n, sf, sb)), 1), device=fz.device, dtype=torch.uint8)
+    outs, st = _alloc_outputs(n, sf, sb, fz.device)
+    with torch.cuda.device(fz.device):
+        check(L.nerfpp_forward(_p(packed_fg), _p(packed_bg), impl, _p(o), _p(d), _p(zmax), _p(fz), _p(bz), n, sf, sb,
+                               ctypes.byref(st), _p(ws), _stream()), "forward")
+    if keep_workspace:
+        return outs, ws, (o, d, zmax, fz, bz)
+    return outs
+
+
+class _NerfppFunction(torch.autograd.Function):
+    """Autograd node for NerfNet.forward: forward = nerfpp_forward, backward = nerfpp_backward."""
+
+    @staticmethod
+    def forward(ctx, model_cache, impl, ray_o, ray_d, fg_z_max, fg_z, bg_z, *params):
+        fg_t, bg_t = params[:24], params[24:]
+        packed_fg = model_cache[0].get(fg_t, impl)
+        packed_bg = model_cache[1].get(bg_t, impl)
+        outs, ws, inputs = render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl, keep_workspace=True)
+        ctx.impl, ctx.ws, ctx.inputs, ctx.outs = impl, ws, inputs, outs
+        ctx.save_for_backward(*params)
+        vals = tuple(outs.values())
+        ctx.mark_non_differentiable(outs["fg_dists"])
+        return vals
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from . import backward as B   # CUDA backward (nerfpp_backward); raises if the library lacks it
+        params = ctx.saved_tensors
+        pg = B.render_backward(ctx.impl, params, ctx.inputs, ctx.outs, ctx.ws, grads)
+        return (None, None, None, None, None, None, None) + tuple(pg)
+
+
+def nerfpp_forward(model_cache, fg_tensors, bg_tensors, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl=None):
+    """Autograd-connected NerfNet.forward. Returns the reference's 10-key OrderedDict."""
+    impl = default_field_impl() if impl is None else impl
+    params = tuple(fg_tensors) + tuple(bg_tensors)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        vals = _NerfppFunction.apply(model_cache, impl, ray_o, ray_d, fg_z_max, fg_z, bg_z, *params)
+        return OrderedDict(zip(RET_KEYS, vals))
+    packed_fg = model_cache[0].get(tuple(fg_tensors), impl)
+    packed_bg = model_cache[1].get(tuple(bg_tensors), impl)
+    return render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl)
+
+
+# ------------------------------------------------------------------------------------------------
+# A12-A14 losses
+# ------------------------------------------------------------------------------------------------
+_LOSS_TYPES = {None: DEPTH_NONE, "none": DEPTH_NONE, "mse": DEPTH_MSE, "l1": DEPTH_L1, "kl": DEPTH_KL}
+
+
+def fused_loss(rgb, rgb_gt, depth=None, depth_sup=None, depth_loss_type=None, lambda_depth=0.0, fg_weights=None,
+               fg_z=None, fg_dists=None, fg_z_max=None, kl_sigma=1.0):
+    """img2mse + depth prior loss + total in one pass (ddp_train_nerf.py:481-493), no autograd.
+    Returns a [4] device tensor: rgb_loss, depth_loss, rgb + lambda*depth, #valid rays."""
+    typ = _LOSS_TYPES[depth_loss_type]
+    r, g = _c(rgb, "rgb", 2), _c(rgb_gt, "rgb_gt", 2)
+    n = r.shape[0]
+    S = fg_z.shape[-1] if fg_z is not None else 1
+    args = [(_c(t, nm) if t is not None else None) for t, nm in
+            ((depth, "depth"), (depth_sup, "depth_sup"), (fg_weights, "fg_weights"), (fg_z, "fg_z"),
+             (fg_dists, "fg_dists"), (fg_z_max, "fg_z_max"))]
+    L = _lib.lib()
+    out = torch.empty(4, device=r.device, dtype=torch.float32)
+    ws = torch.empty(int(L.nerfpp_loss_workspace_bytes()), device=r.device, dtype=torch.uint8)
+    with torch.cuda.device(r.device):
+        check(L.nerfpp_loss(_p(r), _p(g), _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(args[5]),
+                            n, S, typ, float(lambda_depth), float(kl_sigma), _p(out), _p(ws), _stream()), "loss")
+    return out

@@ -1,0 +1,127 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
+header declares, the shim modules mirror the reference's import surface / state dict / RNG
+stream, and the product path refuses to run without CUDA (no fallback)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import nerfpp_oracle as O
+from conftest import ROOT, reference_args
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "nerfpp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nerfpp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nerfpp_b200 import _lib
+    L = _lib.lib()
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), "libnerfpp_b200.so lacks %s" % n
+    bound = set(_lib.SIGNATURES) | set(_lib.OPTIONAL)
+    assert set(names) <= bound, "ctypes binding lacks %s" % (set(names) - bound)
+    assert L.nerfpp_abi_version() == 1
+    assert L.nerfpp_packed_bytes(0, _lib.FIELD_SIMT) > 4 * 590000
+    assert L.nerfpp_packed_bytes(1, _lib.FIELD_TC) > 2 * 590000
+    assert L.nerfpp_forward_workspace_bytes(4096, 192, 192) >= 4096 * 192 * 4 * 9
+
+
+def test_argument_errors_return_codes_not_exceptions():
+    from nerfpp_b200 import _lib
+    L = _lib.lib()
+    rc = L.nerfpp_intersect_sphere(None, None, 4, None, None, None)
+    assert rc < 0 and b"intersect_sphere" in L.nerfpp_last_error()
+    assert L.nerfpp_packed_bytes(0, 7) == -1
+
+
+def test_library_is_sm100a_tcgen05():
+    """The shipped binary holds sm_100a SASS with tensor-core MMA (UTCHMMA) and bulk-copy (UBLKCP) ops."""
+    import shutil
+    import subprocess
+    from nerfpp_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "field_tc_kernel", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if "UTCHMMA" not in sass:
+        sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+
+
+def test_shim_surface_and_state_dict_match_reference_layout():
+    import ddp_model
+    import depth_loss
+    for name in ("NerfNetWithAutoExpo", "NerfNet", "depth2pts_outside", "remap_name"):
+        assert hasattr(ddp_model, name)
+    for name in ("depth_mse", "depth_l1", "depth_kl", "depth_light_of_sight", "depth_gaussian_log_likelihood"):
+        assert hasattr(depth_loss, name)
+    torch.manual_seed(777)
+    nets = [ddp_model.NerfNetWithAutoExpo(reference_args()) for _ in range(2)]
+    ref_levels = O.make_params_levels(2)
+    for net, ref in zip(nets, ref_levels):
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(ref.keys())
+        for k in ref:
+            assert sd[k].shape == ref[k].shape
+            assert torch.equal(sd[k], ref[k]), k     # same RNG stream as the reference's create_nerf
+    assert sum(p.numel() for p in nets[0].parameters()) == 1202440
+    # golden digest of the unmodified reference's parameters
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nerfpp_c2_train_dense.npz"))
+    h = hashlib.sha256()
+    sd = nets[0].state_dict()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].numpy().astype(np.float32).tobytes())
+    assert h.hexdigest() == str(g["meta_param_digest"][0])
+    # a reference-style checkpoint (DDP 'module.' prefix stripped by the loader) loads strictly
+    nets[1].load_state_dict({k: v.clone() for k, v in ref_levels[0].items()}, strict=True)
+
+
+def test_autoexpo_and_remap_name():
+    import ddp_model
+    assert ddp_model.remap_name("/data/kitti/seq00/train/rgb/000001.png") == "train/rgb/000001-png"
+    net = ddp_model.NerfNetWithAutoExpo(reference_args(), optim_autoexpo=True, img_names=["a/b/c/d.png"])
+    assert list(net.autoexpo_params.keys()) == ["b/c/d-png"]
+
+
+def test_unsupported_network_shape_is_refused():
+    import ddp_model
+    a = reference_args()
+    a.netwidth = 128
+    with pytest.raises(ValueError):
+        ddp_model.NerfNetWithAutoExpo(a)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly: the path exists only as CUDA kernels."""
+    from nerfpp_b200 import NerfppError, ops
+    import ddp_model
+    import depth_loss
+    with pytest.raises(NerfppError):
+        ops.intersect_sphere(torch.zeros(4, 3), torch.ones(4, 3))
+    net = ddp_model.NerfNetWithAutoExpo(reference_args())
+    n, S = 4, 8
+    with pytest.raises(NerfppError):
+        with torch.no_grad():
+            net(torch.zeros(n, 3), torch.ones(n, 3), torch.ones(n), torch.rand(n, S), torch.rand(n, S))
+    with pytest.raises(NerfppError):
+        depth_loss.depth_mse(torch.ones(4), torch.ones(4))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "outdoor-nerf-depth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "nerfpp_oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f

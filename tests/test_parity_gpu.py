@@ -1,0 +1,358 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the unmodified
+reference and against the CPU oracle on seeded inputs.  Needs a B200: run with -m gpu.
+
+Tolerances (north_star: 1e-4 relative fp32, inverse-CDF indices bit-exact):
+  * sampling arithmetic given identical inputs: bit-exact (integer compare / array_equal);
+  * SIMT (fp32 FFMA) field:   max|a-b| <= 1e-5 * max|b|  per output tensor;
+  * tcgen05 (fp16 operand) field: max|a-b| <= 1e-4 * max|b| for rgb / depth / losses.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nerfpp_oracle as O
+from conftest import reference_args
+
+pytestmark = pytest.mark.gpu
+
+TOL_SIMT = 1e-5
+TOL_TC = 1e-4
+KEYS = ["rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth", "bg_lambda", "depth"]
+CASES = ["c1_coarse_det", "c2_train_dense", "c2_train_init", "c2_det_dense"]
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    return torch.device("cuda:0")
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "nerfpp_%s.npz" % name))
+    return {k: z[k] for k in z.files}
+
+
+def G(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if b.size else 0.0
+
+
+def make_models(levels):
+    """Shim modules loaded with the oracle's (== the reference's) parameters via state_dict."""
+    import ddp_model
+    nets = []
+    for p in levels:
+        net = ddp_model.NerfNetWithAutoExpo(reference_args())
+        net.load_state_dict(p, strict=True)
+        nets.append(net.to(dev()))
+    return nets
+
+
+def golden_levels(g):
+    cascade = tuple(int(x) for x in g["meta_cascade"])
+    levels = O.make_params_levels(len(cascade))
+    if float(g["meta_sigma_bias"]):
+        levels = [O.densify(p, float(g["meta_sigma_bias"])) for p in levels]
+    return cascade, levels
+
+
+def impl_id(name):
+    from nerfpp_b200 import FIELD_SIMT, FIELD_TC
+    return {"simt": FIELD_SIMT, "tc": FIELD_TC}[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# A1-A5: sampling is bit-exact given identical inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_intersect_and_coarse_depths_bit_exact(golden_dir, name):
+    from nerfpp_b200 import ops
+    g = load(golden_dir, name)
+    far = ops.intersect_sphere(G(g["ray_o"]), G(g["ray_d"]))
+    assert np.array_equal(far.cpu().numpy(), g["fg_far"])
+    S = int(g["meta_cascade"][0])
+    train = bool(g["meta_train"])
+    fg, bg = ops.coarse_depths(G(g["min_depth"]), far, S, G(g["rand_t_fg"]) if train else None,
+                               G(g["rand_t_bg"]) if train else None)
+    assert np.array_equal(fg.cpu().numpy(), g["fg_z_0"])
+    assert np.array_equal(bg.cpu().numpy(), g["bg_z_0"])
+    if train:   # generic perturb_samples on the unperturbed grid
+        pz = ops.perturb_samples(G(g["fg_z_grid"]), G(g["rand_t_fg"]))
+        assert np.array_equal(pz.cpu().numpy(), g["fg_z_0"])
+
+
+def test_intersect_sphere_raises_like_reference():
+    from nerfpp_b200 import ops
+    o = torch.tensor([[0.0, 0.0, 2.0]], device=dev())
+    d = torch.tensor([[1.0, 0.0, 0.0]], device=dev())
+    with pytest.raises(Exception, match="bounded by the unit sphere"):
+        ops.intersect_sphere(o, d)
+
+
+@pytest.mark.parametrize("name", ["c2_train_dense", "c2_train_init", "c2_det_dense"])
+def test_inverse_cdf_bit_exact_given_cdf(golden_dir, name):
+    """Given the reference's own cdf and u, indices (ddp_train_nerf.py:111) and samples (:128) are identical."""
+    from nerfpp_b200 import ops
+    g = load(golden_dir, name)
+    train = bool(g["meta_train"])
+    for side in ("fg", "bg"):
+        z = G(g["%s_z_0" % side])
+        mids = (0.5 * (z[..., 1:] + z[..., :-1])).contiguous()
+        u = G(g["rand_u_%s_1" % side]) if train else O.det_u(1, 128)[0].to(dev())
+        samples, above = ops.sample_cdf(mids, G(g["%s_cdf_1" % side]), u)
+        assert np.array_equal(above.cpu().numpy(), g["%s_inds_1" % side])
+        assert np.array_equal(samples.cpu().numpy(), g["%s_new_1" % side])
+
+
+@pytest.mark.parametrize("name", ["c2_train_dense", "c2_train_init", "c2_det_dense"])
+def test_sample_pdf_and_merge_from_weights(golden_dir, name):
+    """Fused path from weights: the device builds its own cdf (fp64-carried sum/scan). torch's CPU
+    ``sum`` is not correctly rounded so a cdf entry may differ by 1 ulp; indices then
+    flip only where u sits within that ulp of a cdf edge: report and bound the flip count."""
+    from nerfpp_b200 import ops
+    g = load(golden_dir, name)
+    train = bool(g["meta_train"])
+    for side in ("fg", "bg"):
+        z0 = G(g["%s_z_0" % side])
+        w0 = G(g["ret0_%s_weights" % side])
+        mids = (0.5 * (z0[..., 1:] + z0[..., :-1])).contiguous()
+        u = G(g["rand_u_%s_1" % side]) if train else None
+        out, cdf, above = ops.sample_pdf(mids, w0[..., 1:-1], 128, det=not train, u=u, return_aux=True)
+        ref_cdf = g["%s_cdf_1" % side]
+        assert np.abs(cdf.cpu().numpy() - ref_cdf).max() <= 1.2e-7
+        flips = int((above.cpu().numpy() != g["%s_inds_1" % side]).sum())
+        assert flips <= 2, "%d index flips of %d" % (flips, above.numel())
+        np.testing.assert_allclose(out.cpu().numpy(), g["%s_new_1" % side], rtol=0, atol=2e-6)
+        merged = ops.resample_merge(z0, w0, 128, det=not train, u=u)
+        m = merged.cpu().numpy()
+        assert m.shape == g["%s_z_1" % side].shape
+        assert np.all(np.diff(m, axis=-1) >= 0)
+        np.testing.assert_allclose(m, g["%s_z_1" % side], rtol=0, atol=2e-6)
+        assert (m == g["%s_z_1" % side]).mean() > 0.99
+
+
+def test_merge_is_exact_sort_of_union():
+    """sortedness + multiset equality with torch.sort(cat) on random data incl. ties and ragged ray counts."""
+    from nerfpp_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    for n in (1, 3, 37, 1000):
+        z = torch.sort(torch.rand(n, 64, generator=gen), -1)[0]
+        z[:, 10] = z[:, 9]                         # ties
+        w = torch.rand(n, 64, generator=gen)
+        u = torch.rand(n, 128, generator=gen)
+        ref = O.resample_level(z, w, u)
+        got = ops.resample_merge(z.to(dev()), w.to(dev()), 128, u=u.to(dev())).cpu()
+        assert torch.all(got[:, 1:] >= got[:, :-1])
+        assert torch.allclose(got, ref, rtol=0, atol=2e-6)
+        # the 64 old depths are carried over exactly
+        both = torch.sort(torch.cat([got, z], -1), -1)[0]
+        assert both.shape[-1] == 256
+
+
+# ------------------------------------------------------------------------------------------------
+# A6-A11: NerfNet.forward on the reference's own depths
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(golden_dir, name, impl):
+    g = load(golden_dir, name)
+    cascade, levels = golden_levels(g)
+    nets = make_models(levels)
+    tol = TOL_SIMT if impl == "simt" else TOL_TC
+    for m in range(len(cascade)):
+        with torch.no_grad():
+            ret = nets[m](G(g["ray_o"]), G(g["ray_d"]), G(g["fg_far"]), G(g["fg_z_%d" % m]), G(g["bg_z_%d" % m]),
+                          impl=impl_id(impl))
+        assert list(ret.keys()) == KEYS
+        errs = {k: relerr(ret[k].cpu().numpy(), g["ret%d_%s" % (m, k)]) for k in KEYS}
+        # the quantities north_star names (pixel colour, expected depth) and everything feeding them
+        for k in ("rgb", "depth", "fg_rgb", "bg_rgb", "bg_depth", "bg_lambda", "fg_dists"):
+            assert errs[k] <= tol, (impl, name, m, k, errs)
+        # per-sample weights / fg_depth of an untrained net are sums of ~1e-3 terms dominated by
+        # sigma's cancellation error; they get the same bound relative to the tensor's own scale
+        for k in ("fg_weights", "bg_weights", "fg_depth"):
+            assert errs[k] <= (tol if impl == "simt" else 5e-4), (impl, name, m, k, errs)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_field_outputs_match_oracle_per_sample(impl):
+    """sigma / rgb per sample (before compositing) against the oracle's MLP on ragged shapes."""
+    from nerfpp_b200 import ops
+    params = O.densify(O.make_params(), 3.0)
+    nets = make_models([params])
+    for n, S in ((1, 64), (5, 192), (3, 77)):
+        rays = O.synthetic_rays(n, seed=n)
+        far = O.intersect_sphere(rays["ray_o"], rays["ray_d"])
+        gen = torch.Generator().manual_seed(n)
+        fg_z = torch.sort(torch.rand(n, S, generator=gen), -1)[0] * far[:, None]
+        bg_z = torch.sort(torch.rand(n, S, generator=gen), -1)[0]
+        with torch.no_grad():
+            ref = O.nerfpp_forward(params, rays["ray_o"], rays["ray_d"], far, fg_z, bg_z, return_raw=True)
+        net = nets[0].nerf_net
+        for is_bg, zz, tensors in ((0, fg_z, net.fg_net.tensors()), (1, bg_z, net.bg_net.tensors())):
+            packed = net._packed[is_bg].get(tensors, impl_id(impl))
+            sigma, rgb, dr = ops.field_forward(packed, is_bg, rays["ray_o"].to(dev()), rays["ray_d"].to(dev()), zz.to(dev()),
+                                               impl_id(impl))
+            side = "bg" if is_bg else "fg"
+            tol = 2e-5 if impl == "simt" else 3e-4
+            assert relerr(sigma.cpu().numpy(), ref["_%s_sigma" % side].numpy()) <= tol
+            assert relerr(rgb.cpu().numpy(), ref["_%s_rgb_raw" % side].numpy()) <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# A12-A14 losses
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_losses_match_reference_golden(golden_dir, name):
+    from nerfpp_b200 import ops
+    import depth_loss
+    g = load(golden_dir, name)
+    cascade = [int(x) for x in g["meta_cascade"]]
+    sig = float(g["meta_depth_sigma"]) * float(g["meta_depth_scale"])
+    for m in range(len(cascade)):
+        rgb, depth = G(g["ret%d_rgb" % m]), G(g["ret%d_depth" % m])
+        w, fz, dl = G(g["ret%d_fg_weights" % m]), G(g["fg_z_%d" % m]), G(g["ret%d_fg_dists" % m])
+        sup, far, gt = G(g["depth_sup"]), G(g["fg_far"]), G(g["rgb_gt"])
+        for lt in ("mse", "l1", "kl"):
+            out = ops.fused_loss(rgb, gt, depth, sup, lt, 0.1, w, fz, dl, far, sig).cpu().numpy()
+            ref_rgb, ref_d = float(g["loss%d_rgb" % m]), float(g["loss%d_%s" % (m, lt)])
+            assert abs(out[0] - ref_rgb) <= 2e-6 * abs(ref_rgb)
+            assert abs(out[1] - ref_d) <= 5e-6 * abs(ref_d) + 1e-12
+            assert abs(out[2] - (ref_rgb + 0.1 * ref_d)) <= 5e-6 * abs(ref_rgb + 0.1 * ref_d)
+        # drop-in entry points (autograd nodes)
+        assert abs(float(depth_loss.depth_mse(sup, depth)) - float(g["loss%d_mse" % m])) <= 5e-6 * float(g["loss%d_mse" % m])
+        assert abs(float(depth_loss.depth_l1(sup, depth)) - float(g["loss%d_l1" % m])) <= 5e-6 * float(g["loss%d_l1" % m])
+        assert abs(float(depth_loss.depth_kl(w, sup, fz, dl, sig, far)) - float(g["loss%d_kl" % m])) <= 5e-6 * abs(float(g["loss%d_kl" % m])) + 1e-12
+
+
+def test_depth_loss_edge_cases_and_gradients():
+    import depth_loss
+    d = dev()
+    gt = torch.zeros(7, device=d)
+    pred = torch.rand(7, device=d)
+    assert torch.isnan(depth_loss.depth_mse(gt, pred)) and torch.isnan(depth_loss.depth_l1(gt, pred))
+    w = torch.rand(7, 5, device=d)
+    assert float(depth_loss.depth_kl(w, gt, torch.rand(7, 5, device=d), torch.rand(7, 5, device=d), 0.01, torch.ones(7, device=d))) == 0.0
+    # gradients against the oracle's autograd
+    gen = torch.Generator().manual_seed(3)
+    n, S = 33, 20
+    gt = torch.rand(n, generator=gen); gt[::4] = 0
+    pred = torch.rand(n, generator=gen)
+    w = torch.rand(n, S, generator=gen) * 0.1
+    z = torch.sort(torch.rand(n, S, generator=gen), -1)[0]
+    dl = torch.rand(n, S, generator=gen) * 0.05
+    far = torch.full((n,), 0.9)
+    for fn, ofn in ((depth_loss.depth_mse, O.depth_mse), (depth_loss.depth_l1, O.depth_l1)):
+        p_ref = pred.clone().requires_grad_(True)
+        ofn(gt, p_ref).backward()
+        p_gpu = pred.to(d).requires_grad_(True)
+        (fn(gt.to(d), p_gpu) * 1.0).backward()
+        assert torch.allclose(p_gpu.grad.cpu(), p_ref.grad, rtol=1e-5, atol=1e-8)
+    w_ref = w.clone().requires_grad_(True)
+    O.depth_kl(w_ref, gt, z, dl, 0.05, far).backward()
+    w_gpu = w.to(d).requires_grad_(True)
+    depth_loss.depth_kl(w_gpu, gt.to(d), z.to(d), dl.to(d), 0.05, far.to(d)).backward()
+    assert torch.allclose(w_gpu.grad.cpu(), w_ref.grad, rtol=2e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole cascade ("render_rays") against the oracle, and size-independent properties at full size
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("train", [False, True])
+def test_cascade_matches_oracle(impl, train):
+    from nerfpp_b200 import cascade_forward
+    n = 96
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    rays = O.synthetic_rays(n, seed=31)
+    rand = O.synthetic_rand(n, (64, 128), seed=32) if train else None
+    with torch.no_grad():
+        ref, far = O.cascade_forward(levels, rays["ray_o"], rays["ray_d"], rays["min_depth"], (64, 128), rand)
+        rg = {k: v.to(dev()) for k, v in rand.items()} if train else None
+        got, gfar = cascade_forward(nets, rays["ray_o"].to(dev()), rays["ray_d"].to(dev()), rays["min_depth"].to(dev()),
+                                    (64, 128), train=train, rand=rg, impl=impl_id(impl))
+    assert torch.equal(gfar.cpu(), far)
+    tol = 2e-5 if impl == "simt" else TOL_TC
+    for m in range(2):
+        for k in ("rgb", "depth"):
+            assert relerr(got[m][0][k].cpu().numpy(), ref[m][0][k].numpy()) <= tol, (m, k)
+    assert torch.equal(got[0][1].cpu(), ref[0][1]) and torch.equal(got[0][2].cpu(), ref[0][2])
+    assert torch.allclose(got[1][1].cpu(), ref[1][1], rtol=0, atol=(1e-5 if impl == "simt" else 2e-4))
+
+
+def test_full_size_properties_and_tc_vs_simt():
+    """BASELINE config 2 size (4096 rays, 64 -> 192 samples): properties the domain offers, and the
+    tensor-core evaluator against the fp32 evaluator on identical depths."""
+    from nerfpp_b200 import FIELD_SIMT, FIELD_TC, cascade_forward, ops
+    n = 4096
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    rays = {k: (v.to(dev()) if torch.is_tensor(v) else v) for k, v in O.synthetic_rays(n, seed=0).items()}
+    with torch.no_grad():
+        out, far = cascade_forward(nets, rays["ray_o"], rays["ray_d"], rays["min_depth"], (64, 128), train=True, impl=FIELD_TC)
+        ret, fg_z, bg_z = out[1]
+        assert fg_z.shape == (n, 192) and bg_z.shape == (n, 192)
+        assert bool(torch.all(fg_z[:, 1:] >= fg_z[:, :-1])) and bool(torch.all(bg_z[:, 1:] >= bg_z[:, :-1]))
+        assert bool(torch.all(fg_z[:, -1] <= far * (1 + 1e-5) + 1e-6)) and bool(torch.all(bg_z <= 1.0 + 1e-5))
+        for k in KEYS:
+            assert bool(torch.isfinite(ret[k]).all()), k
+        # weights are a sub-partition of unity; fg and bg mass adds to ~1 (last bg interval is 1e10 long)
+        assert bool(torch.all(ret["fg_weights"] >= 0)) and bool(torch.all(ret["bg_weights"] >= 0))
+        total = ret["fg_weights"].sum(-1) + ret["bg_lambda"] * ret["bg_weights"].sum(-1)
+        assert float((total - 1).abs().max()) < 1e-3
+        assert float(ret["rgb"].min()) >= 0 and float(ret["rgb"].max()) <= 1 + 1e-5
+        # merge identity (ddp_model.py:131-134)
+        assert torch.allclose(ret["rgb"], ret["fg_rgb"] + ret["bg_rgb"], rtol=0, atol=1e-6)
+        assert torch.allclose(ret["depth"], ret["fg_depth"] + ret["bg_depth"], rtol=1e-6, atol=1e-6)
+        # same depths through the fp32 evaluator
+        ref = nets[1](rays["ray_o"], rays["ray_d"], far, fg_z, bg_z, impl=FIELD_SIMT)
+        for k in ("rgb", "depth", "bg_lambda"):
+            assert relerr(ret[k].cpu().numpy(), ref[k].cpu().numpy()) <= TOL_TC, k
+        # losses agree too
+        for lt in ("mse", "l1", "kl"):
+            a = ops.fused_loss(ret["rgb"], rays["rgb"], ret["depth"], rays["depth_sup"], lt, 0.1, ret["fg_weights"], fg_z,
+                               ret["fg_dists"], far, 0.01 * 0.05).cpu().numpy()
+            b = ops.fused_loss(ref["rgb"], rays["rgb"], ref["depth"], rays["depth_sup"], lt, 0.1, ref["fg_weights"], fg_z,
+                               ref["fg_dists"], far, 0.01 * 0.05).cpu().numpy()
+            assert abs(a[2] - b[2]) <= 2e-4 * abs(b[2]), (lt, a, b)
+
+
+def test_empty_and_ragged_batches():
+    from nerfpp_b200 import FIELD_TC, cascade_forward, ops
+    nets = make_models([O.densify(p, 5.0) for p in O.make_params_levels(2)])
+    d = dev()
+    with torch.no_grad():
+        ret = nets[0](torch.zeros(0, 3, device=d), torch.zeros(0, 3, device=d), torch.zeros(0, device=d),
+                      torch.zeros(0, 64, device=d), torch.zeros(0, 64, device=d))
+        assert ret["rgb"].shape == (0, 3) and ret["fg_weights"].shape == (0, 64)
+        for n in (1, 2, 3, 129):      # tiles that end mid-ray and partial last tiles
+            rays = O.synthetic_rays(n, seed=100 + n)
+            ref, far = O.cascade_forward([O.densify(p, 5.0) for p in O.make_params_levels(2)], rays["ray_o"], rays["ray_d"],
+                                         rays["min_depth"], (64, 128), None)
+            got, _ = cascade_forward(nets, rays["ray_o"].to(d), rays["ray_d"].to(d), rays["min_depth"].to(d), (64, 128),
+                                     train=False, impl=FIELD_TC)
+            for m in range(2):
+                for k in ("rgb", "depth"):
+                    assert relerr(got[m][0][k].cpu().numpy(), ref[m][0][k].numpy()) <= TOL_TC, (n, m, k)
+        # leading batch dims like the reference's [..., 3] convention
+        rays = O.synthetic_rays(6, seed=9)
+        far = ops.intersect_sphere(rays["ray_o"].to(d).reshape(2, 3, 3), rays["ray_d"].to(d).reshape(2, 3, 3))
+        assert far.shape == (2, 3)
+
+
+def test_depth2pts_outside_matches_oracle():
+    import ddp_model
+    rays = O.synthetic_rays(50, seed=77)
+    depth = torch.rand(50, 9)
+    o = rays["ray_o"][:, None, :].expand(50, 9, 3)
+    dd = rays["ray_d"][:, None, :].expand(50, 9, 3)
+    pts_ref, real_ref = O.inverted_sphere_points(o, dd, depth)
+    pts, real = ddp_model.depth2pts_outside(o.to(dev()), dd.to(dev()), depth.to(dev()))
+    assert torch.allclose(pts.cpu(), pts_ref, rtol=0, atol=2e-6)
+    assert relerr(real.cpu().numpy(), real_ref.numpy()) <= 1e-5
