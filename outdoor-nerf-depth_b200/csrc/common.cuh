@@ -80,19 +80,23 @@ struct BgRay {
   float ax_dot_ps;  // sum(axis * p_sphere)
   float p_mid_norm, phi, d1, inv_len;
 };
+// torch.norm over 3 components as the CPU kernel rounds it: sqrt(fma(z,z,fma(y,y,x*x)))
+__device__ __forceinline__ float norm3(float x, float y, float z) {
+  return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
 __device__ __forceinline__ BgRay bg_ray_setup(const float o[3], const float d[3]) {
   BgRay r;
   float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   float dO = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
   r.d1 = -dO / dd;
   float pm[3] = {o[0] + r.d1 * d[0], o[1] + r.d1 * d[1], o[2] + r.d1 * d[2]};
-  r.p_mid_norm = sqrtf(pm[0] * pm[0] + pm[1] * pm[1] + pm[2] * pm[2]);
-  r.inv_len = 1.f / sqrtf(dd);
+  r.p_mid_norm = norm3(pm[0], pm[1], pm[2]);
+  r.inv_len = 1.f / norm3(d[0], d[1], d[2]);
   float d2 = sqrtf(1.f - r.p_mid_norm * r.p_mid_norm) * r.inv_len;
   float t = r.d1 + d2;
   r.ps[0] = o[0] + t * d[0]; r.ps[1] = o[1] + t * d[1]; r.ps[2] = o[2] + t * d[2];
   float ax[3] = {o[1] * r.ps[2] - o[2] * r.ps[1], o[2] * r.ps[0] - o[0] * r.ps[2], o[0] * r.ps[1] - o[1] * r.ps[0]};
-  float an = sqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  float an = norm3(ax[0], ax[1], ax[2]);
   r.ax[0] = ax[0] / an; r.ax[1] = ax[1] / an; r.ax[2] = ax[2] / an;
   r.axps[0] = r.ax[1] * r.ps[2] - r.ax[2] * r.ps[1];
   r.axps[1] = r.ax[2] * r.ps[0] - r.ax[0] * r.ps[2];
@@ -110,7 +114,7 @@ __device__ __forceinline__ float bg_point(const BgRay& r, float depth, float pts
   float q[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) q[i] = r.ps[i] * c + r.axps[i] * s + r.ax[i] * r.ax_dot_ps * (1.f - c);
-  float qn = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  float qn = norm3(q[0], q[1], q[2]);
   pts[0] = q[0] / qn; pts[1] = q[1] / qn; pts[2] = q[2] / qn; pts[3] = depth;
   return 1.f / (depth + NPP_TINY) * cosf(theta) * r.inv_len + r.d1;
 }

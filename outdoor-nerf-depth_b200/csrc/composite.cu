@@ -59,7 +59,7 @@ composite_kernel(const float* __restrict__ ray_d, const float* __restrict__ fg_z
   int r = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
   if (r >= n) return;
   float d0 = ray_d[3 * r], d1 = ray_d[3 * r + 1], d2 = ray_d[3 * r + 2];
-  float dnorm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+  float dnorm = norm3(d0, d1, d2);
   float zmax = fg_z_max[r];
   const float* zf = fg_z + (size_t)r * Sf;
   const float* zb = bg_z + (size_t)r * Sb;

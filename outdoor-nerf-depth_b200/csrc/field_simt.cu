@@ -144,7 +144,7 @@ field_simt_kernel(const float* __restrict__ packed, const float* __restrict__ ra
         for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(zv, d[c]));   // ddp_model.py:91
       }
       embed_part<D>(x, NF_POS, q, erow);
-      float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float dn = norm3(d[0], d[1], d[2]);
       float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
       embed_part<3>(vd, NF_VIEW, q, vrow);
     } else {

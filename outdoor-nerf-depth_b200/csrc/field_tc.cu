@@ -271,7 +271,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
           embed_rows<D>(x, 0, 5, true, sE, row, 0);
         } else {
           embed_rows<D>(x, 5, NF_POS, false, sE, row, 0);
-          float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          float dn = norm3(d[0], d[1], d[2]);
           float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};
           embed_rows<3>(vd, 0, NF_VIEW, true, sE, row, VIEW_COL);
         }

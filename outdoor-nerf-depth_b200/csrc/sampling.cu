@@ -21,7 +21,8 @@ __global__ void intersect_sphere_kernel(const float* __restrict__ ray_o, const f
   float dd = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1_, d1_)), __fmul_rn(d2_, d2_));
   float d1 = __fdiv_rn(-dO, dd);
   float p0 = __fadd_rn(o0, __fmul_rn(d1, d0)), p1 = __fadd_rn(o1, __fmul_rn(d1, d1_)), p2 = __fadd_rn(o2, __fmul_rn(d1, d2_));
-  float inv_len = __fdiv_rn(1.f, __fsqrt_rn(dd));
+  // torch.norm (CPU) accumulates x*x with an FMA chain: sqrt(fma(z,z,fma(y,y,x*x)))
+  float inv_len = __fdiv_rn(1.f, __fsqrt_rn(__fmaf_rn(d2_, d2_, __fmaf_rn(d1_, d1_, __fmul_rn(d0, d0)))));
   float psq = __fadd_rn(__fadd_rn(__fmul_rn(p0, p0), __fmul_rn(p1, p1)), __fmul_rn(p2, p2));
   if (psq >= 1.f) atomicOr(out_unbounded, 1);
   float d2 = __fmul_rn(__fsqrt_rn(__fsub_rn(1.f, psq)), inv_len);
