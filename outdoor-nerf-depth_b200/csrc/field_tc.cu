@@ -17,6 +17,7 @@
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
 // against the fp32 reference: rgb/depth within 3e-5 relative (tests/test_parity_gpu.py).
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace npp {
@@ -117,6 +118,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one L2 read delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -170,11 +184,14 @@ __device__ __forceinline__ void embed_rows(const float* x, int k_lo, int k_hi, b
   }
 }
 
-template <bool BG>
+// CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
+// CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings, so L2->SM
+// traffic (the binding resource of the unshared version, profiles/r1_notes.md) drops CLUSTER-fold.
+template <bool BG, int CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
-                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles) {
+                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
   const StepTable& tab = c_tab[BG ? 1 : 0];
@@ -184,9 +201,15 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   auto bar = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * B_COUNT);
   if ((s_base & 1023u) != 0) __trap();
+  const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1u);
+  // tiles: cluster c takes groups of CLUSTER consecutive tiles; every CTA of a cluster runs the same
+  // number of (possibly empty) tiles so the shared weight ring stays in step
+  const int n_groups = (num_tiles + CLUSTER - 1) / CLUSTER;
+  const int group0 = blockIdx.x / CLUSTER, group_step = gridDim.x / CLUSTER;
 
   if (warp == MMA_WARP && lane == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
     mbar_init(bar(B_EREADY), NUM_EPI_WARPS);
     mbar_init(bar(B_ACC), 1); mbar_init(bar(B_ACC + 1), 1);
@@ -201,6 +224,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long total = (long long)n * S;
@@ -209,12 +233,18 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     // ================= weight loader =================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int grp = group0; grp < n_groups; grp += group_step) {
         for (int i = 0; i < tab.n; ++i, ++it) {
           const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          mbar_wait(bar(B_WEMPTY + st), ph ^ 1);
-          mbar_expect_tx(bar(B_WFULL + st), (uint32_t)tab.s[i].blob_bytes);
-          bulk_g2s(s_base + OFF_W + st * STAGE_BYTES, blobs + tab.s[i].blob_off, (uint32_t)tab.s[i].blob_bytes, bar(B_WFULL + st));
+          const uint32_t bytes = (uint32_t)tab.s[i].blob_bytes;
+          mbar_wait(bar(B_WEMPTY + st), ph ^ 1);          // every CTA of the cluster has consumed this stage
+          mbar_expect_tx(bar(B_WFULL + st), bytes);
+          if (CLUSTER == 1) {
+            bulk_g2s(s_base + OFF_W + st * STAGE_BYTES, blobs + tab.s[i].blob_off, bytes, bar(B_WFULL + st));
+          } else {
+            const uint32_t part = bytes / CLUSTER, o = cta_rank * part;
+            bulk_g2s_mcast(s_base + OFF_W + st * STAGE_BYTES + o, blobs + tab.s[i].blob_off + o, part, bar(B_WFULL + st), kMask);
+          }
         }
       }
     }
@@ -222,14 +252,22 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     // ================= MMA issuer =================
     if (lane == 0) {
       uint32_t it = 0, a_cnt[4] = {0, 0, 0, 0}, e_cnt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      long long t_e = 0, t_a = 0, t_w = 0, t_i = 0, t0 = clock64(), tt;
+      for (int grp = group0; grp < n_groups; grp += group_step) {
+        tt = clock64();
         mbar_wait(bar(B_EREADY), e_cnt & 1);
+        t_e += clock64() - tt;
         ++e_cnt;
         for (int i = 0; i < tab.n; ++i, ++it) {
           const Step s = tab.s[i];
+          tt = clock64();
           if (s.src == 1) { mbar_wait(bar(B_AREADY + s.chunk), a_cnt[s.chunk] & 1); ++a_cnt[s.chunk]; }
+          t_a += clock64() - tt;
           const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          tt = clock64();
           mbar_wait(bar(B_WFULL + st), ph);
+          t_w += clock64() - tt;
+          tt = clock64();
           tc_fence_after();
           const uint32_t a_addr = s_base + (s.src ? OFF_A : OFF_E) + s.chunk * CHUNK_BYTES;
           const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
@@ -237,10 +275,12 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
           const uint32_t idesc = idesc_f16(s.n);
           for (int k = s.k0; k < s.k0 + s.nk; ++k)
             umma_f16(d_tmem, sw128_desc(a_addr + k * 32), sw128_desc(b_addr + k * 32), idesc, (s.first && k == s.k0) ? 0u : 1u);
-          tc_commit(bar(B_WEMPTY + st));
+          if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
           if (s.last) tc_commit(bar(B_ACC + (s.layer & 1)));
+          t_i += clock64() - tt;
         }
       }
+      if (dbg) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; dbg[8 * blockIdx.x + 4] = t_i; }
     }
   } else {
     // ================= epilogue warps =================
@@ -250,7 +290,10 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     uint8_t* sE = smem + OFF_E;
     uint8_t* sA = smem + OFF_A;
     uint32_t acc_cnt[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long e_wait = 0, e_emb = 0, e_t0 = clock64(), ett;
+    for (int grp = group0; grp < n_groups; grp += group_step) {
+      ett = clock64();
+      const int tile = grp * CLUSTER + (int)cta_rank;
       long long g = (long long)tile * TILE + row;
       const bool valid = g < total;
       if (!valid) g = total - 1;
@@ -278,11 +321,14 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_EREADY));
+        e_emb += clock64() - ett;
       }
       float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
       for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
         const int ab = m & 1;
+        ett = clock64();
         mbar_wait(bar(B_ACC + ab), acc_cnt[ab] & 1);
+        e_wait += clock64() - ett;
         ++acc_cnt[ab];
         tc_fence_after();
         const float* bias = tail + T_BIAS + m * 256;
@@ -356,9 +402,11 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (dbg && threadIdx.x == 0) { dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait; dbg[8 * blockIdx.x + 7] = e_emb; }
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // no peer may still multicast into / arrive on this CTA
   if (warp == LOAD_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -414,6 +462,42 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
   return 0;
 }
 
+static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1, 2 or 4)
+static long long* g_dbg = nullptr;
+
+template <bool BG, int CLUSTER>
+static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
+                     int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, cudaStream_t st) {
+  auto kern = tc::field_tc_kernel<BG, CLUSTER>;
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(max_ctas / CLUSTER * CLUSTER); q.blockDim = dim3(tc::THREADS); q.dynamicSmemBytes = tc::SMEM_BYTES;
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CLUSTER; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+    q.attrs = a; q.numAttrs = 1;
+    if (CLUSTER == 1 || cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q) != cudaSuccess || max_clusters <= 0) max_clusters = max_ctas / CLUSTER;
+    cudaGetLastError();
+    configured = true;
+  }
+  const int n_groups = (num_tiles + CLUSTER - 1) / CLUSTER;
+  const int clusters = n_groups < max_clusters ? n_groups : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CLUSTER); cfg.blockDim = dim3(tc::THREADS); cfg.dynamicSmemBytes = tc::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_dr, num_tiles, g_dbg);
+  if (e != cudaSuccess) { npp_set_error("field_tc launch (cluster %d): %s", CLUSTER, cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+// debug hook (tests/diag only): device buffer of 4 x gridDim.x int64 receiving the MMA thread's cycle counters
+extern "C" void nerfpp_debug_set_tc_timers(long long* dev_buf) { g_dbg = dev_buf; }
+extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = c; }
+
 int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
                  float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st) {
   static int num_sms = 0;
@@ -421,18 +505,18 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(tc::field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    cudaFuncSetAttribute(tc::field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+  }
+  if (g_cluster < 0) {
+    const char* e = getenv("NERFPP_TC_CLUSTER");
+    g_cluster = e ? atoi(e) : 2;
+    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 2;
   }
   const long long total = (long long)n * S;
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   const uint8_t* blobs = (const uint8_t*)packed;
   const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
-  if (bg)
-    tc::field_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles);
-  else
-    tc::field_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles);
-  NPP_CHECK_LAUNCH();
-  return 0;
+#define NPP_TC_LAUNCH(BG, C) launch_tc<BG, C>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, st)
+  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1) : g_cluster == 2 ? NPP_TC_LAUNCH(true, 2) : NPP_TC_LAUNCH(true, 4);
+  return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1) : g_cluster == 2 ? NPP_TC_LAUNCH(false, 2) : NPP_TC_LAUNCH(false, 4);
+#undef NPP_TC_LAUNCH
 }

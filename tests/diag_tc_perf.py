@@ -1,0 +1,52 @@
+"""Diagnostic (not a test): times the tcgen05 field kernel for each weight-sharing cluster size and prints the
+MMA-issuer cycle counters (total / waiting for E / waiting for A / waiting for weights). Run on the GPU box."""
+import ctypes, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import conftest  # noqa
+import nerfpp_oracle as O
+from nerfpp_b200 import _lib, ops, FIELD_TC, FIELD_SIMT
+from test_parity_gpu import make_models, relerr
+
+dev = torch.device("cuda:0")
+L = _lib.lib()
+L.nerfpp_debug_set_tc_timers.argtypes = [ctypes.c_void_p]
+L.nerfpp_debug_set_tc_cluster.argtypes = [ctypes.c_int]
+nets = make_models([O.densify(O.make_params(), 5.0)])
+net = nets[0].nerf_net
+n, S = 4096, 192
+rays = O.synthetic_rays(n, seed=0)
+o, d = rays["ray_o"].to(dev), rays["ray_d"].to(dev)
+far = ops.intersect_sphere(o, d)
+g = torch.Generator().manual_seed(0)
+fg_z = (torch.sort(torch.rand(n, S, generator=g), -1)[0]).to(dev) * far[:, None]
+bg_z = torch.sort(torch.rand(n, S, generator=g), -1)[0].to(dev)
+ref = {}
+for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_z, net.bg_net.tensors(), 604160)):
+    packed = net._packed[is_bg].get(tensors, FIELD_TC)
+    for cl in [int(x) for x in os.environ.get("CLUSTERS", "1,2,4").split(",")]:
+        L.nerfpp_debug_set_tc_cluster(cl)
+        dbg = torch.zeros(8 * 148, dtype=torch.int64, device=dev)
+        L.nerfpp_debug_set_tc_timers(ctypes.c_void_p(dbg.data_ptr()))
+        try:
+            for _ in range(3):
+                sig, rgb, dr = ops.field_forward(packed, is_bg, o, d, z, FIELD_TC)
+            torch.cuda.synchronize()
+        except Exception as e:
+            print("cluster", cl, "FAILED", e); continue
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 10
+        for _ in range(reps):
+            sig, rgb, dr = ops.field_forward(packed, is_bg, o, d, z, FIELD_TC)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        t = dbg.cpu().numpy().reshape(-1, 8)
+        t = t[t[:, 0] > 0]
+        key = (is_bg,)
+        if key not in ref:
+            ref[key] = (sig.clone(), rgb.clone())
+        es, er = relerr(sig.cpu().numpy(), ref[key][0].cpu().numpy()), relerr(rgb.cpu().numpy(), ref[key][1].cpu().numpy())
+        print("bg=%d cluster=%d  %.3f ms  %.0f TFLOP/s  ctas=%d  mma-thread cycles: total %.0f  wait_E %.0f  wait_A %.0f  wait_W %.0f issue %.0f | epi warp0: total %.0f wait_acc %.0f embed %.0f  (vs cluster1: sigma %.1e rgb %.1e)"
+              % (is_bg, cl, ms, 2 * macs * n * S / ms / 1e9, len(t), t[:, 0].mean(), t[:, 1].mean(), t[:, 2].mean(), t[:, 3].mean(), t[:, 4].mean(), t[:, 5].mean(), t[:, 6].mean(), t[:, 7].mean(), es, er))
+    L.nerfpp_debug_set_tc_timers(None)
