@@ -5,15 +5,16 @@
 // (M=128, N=256|128, K=16, fp16 operands, fp32 accumulators in TMEM); sigma (256->1) and rgb.2
 // (128->3) are fp32 dot products in the epilogue on the fp32 accumulators.
 //
-//   warp 0-7  epilogue: positional encoding -> E operand; per layer TMEM -> regs, +bias, ReLU,
-//             fp16 pack -> A operand of the next layer (K-major, 128B swizzle), 64 columns at a time
-//   warp 8    one lane issues every tcgen05.mma; layer l+1's K-chunk j starts as soon as the
-//             epilogue of layer l has produced columns [64j,64j+64) (two TMEM accumulators
-//             ping-pong between consecutive layers)
-//   warp 9    one lane streams the pre-swizzled weight tiles (32 KB each, in MMA issue order)
-//             from L2 into a 4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx
+//   warp 0-7   epilogue: per layer TMEM -> regs, +bias, ReLU, fp16 pack -> written back to TMEM in
+//              place as the A operand of the next layer, 64 columns at a time
+//   warp 8     one lane issues every tcgen05.mma (A from TMEM, B from shared memory); layer l+1's
+//              K-chunk j starts as soon as the epilogue of layer l has produced columns [64j,64j+64)
+//              (two TMEM accumulators ping-pong between consecutive layers)
+//   warp 9     one lane streams the pre-swizzled weight tiles (32 KB each, in MMA issue order) from L2
+//              into a 5-deep shared-memory ring with cp.async.bulk (+cluster multicast) and mbarriers
+//   warp 10-11 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128)
 //
-// Shared memory (bytes): E 32K | A 64K | ring 4x32K | barriers.  TMEM: 2 x 256 columns.
+// Shared memory (bytes): E 2x32K | ring 5x32K | barriers.  TMEM: 2 x 256 columns.
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
 // against the fp32 reference: rgb/depth within 3e-5 relative (tests/test_parity_gpu.py).
 #include <cuda_fp16.h>
@@ -24,19 +25,19 @@ namespace npp {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 5;
 constexpr int STAGE_BYTES = 32768;
 constexpr int CHUNK_BYTES = 16384;          // 128 rows x 64 fp16
-constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir
-constexpr int A_BYTES = 4 * CHUNK_BYTES;    // 256 columns
-constexpr int OFF_E = 0, OFF_A = E_BYTES, OFF_W = E_BYTES + A_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir; double-buffered
+constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_SCRATCH = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_SCRATCH + 128 * 16;
 constexpr int VIEW_COL = 96;
-constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, THREADS = 320;
+constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, EMB_WARP0 = 10, NUM_EMB_WARPS = 2, THREADS = 384;
 constexpr int NUM_MMA_LAYERS = 10;          // base 0..7, remap, rgb0
 
 // barrier slots
-enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EREADY = 2 * NSTAGE + 4, B_ACC = 2 * NSTAGE + 5, B_COUNT = 2 * NSTAGE + 7 };
+enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = 2 * NSTAGE + 4, B_EEMPTY = 2 * NSTAGE + 6,
+       B_ACC = 2 * NSTAGE + 8, B_COUNT = 2 * NSTAGE + 10 };
 
 // fp32 tail of the packed buffer (float offsets)
 constexpr int T_BIAS = 0;                    // 10 x 256
@@ -144,6 +145,21 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = fp16 pairs packed in 32-bit TMEM columns, row = lane
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -169,24 +185,25 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((c >> 6) * CHUNK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
 }
 
-template <int D>
-__device__ __forceinline__ void embed_rows(const float* x, int k_lo, int k_hi, bool raw, uint8_t* region, int row, int col_base) {
-  if (raw)
-    for (int c = 0; c < D; ++c) *reinterpret_cast<__half*>(region + sw128_off(row, col_base + c)) = __float2half_rn(x[c]);
-  for (int k = k_lo; k < k_hi; ++k) {
-    float f = (float)(1 << k);
-    for (int c = 0; c < D; ++c) {
-      float s, co;
-      sincosf(x[c] * f, &s, &co);
-      *reinterpret_cast<__half*>(region + sw128_off(row, col_base + D + 2 * k * D + c)) = __float2half_rn(s);
-      *reinterpret_cast<__half*>(region + sw128_off(row, col_base + D + (2 * k + 1) * D + c)) = __float2half_rn(co);
-    }
+// Encodes one row (sample) of the E operand: columns [0,emb) = Embedder(pts) (nerf_network.py:42-60),
+// columns [96,123) = Embedder(viewdir); fp16, 128B-swizzled.  Deliberately a compact loop around ONE
+// sincosf call site: this runs on the two producer warps, off the critical path, and the kernel's
+// instruction footprint matters more (I-cache) than its speed.
+__device__ __noinline__ void embed_vec(const float* x, int dim, int nfreq, uint8_t* region, int row, int col_base) {
+  for (int c = 0; c < dim; ++c) *reinterpret_cast<__half*>(region + sw128_off(row, col_base + c)) = __float2half_rn(x[c]);
+#pragma unroll 1
+  for (int i = 0; i < nfreq * dim; ++i) {
+    const int k = i / dim, c = i - k * dim;
+    float sn, cs;
+    sincosf(x[c] * (float)(1 << k), &sn, &cs);
+    const int col = col_base + dim + 2 * k * dim + c;
+    *reinterpret_cast<__half*>(region + sw128_off(row, col)) = __float2half_rn(sn);
+    *reinterpret_cast<__half*>(region + sw128_off(row, col + dim)) = __float2half_rn(cs);
   }
 }
 
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
-// CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings, so L2->SM
-// traffic (the binding resource of the unshared version, profiles/r1_notes.md) drops CLUSTER-fold.
+// CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
 template <bool BG, int CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
@@ -194,6 +211,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                 float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
+  constexpr int E_CHUNKS = BG ? 2 : 1;
   const StepTable& tab = c_tab[BG ? 1 : 0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
@@ -207,11 +225,12 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   // number of (possibly empty) tiles so the shared weight ring stays in step
   const int n_groups = (num_tiles + CLUSTER - 1) / CLUSTER;
   const int group0 = blockIdx.x / CLUSTER, group_step = gridDim.x / CLUSTER;
+  const bool timing = dbg != nullptr;
 
   if (warp == MMA_WARP && lane == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
-    mbar_init(bar(B_EREADY), NUM_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_EFULL + i), NUM_EMB_WARPS); mbar_init(bar(B_EEMPTY + i), 1); }
     mbar_init(bar(B_ACC), 1); mbar_init(bar(B_ACC + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,8 +238,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < NUM_EPI_WARPS) {   // zero E once: padding columns are never written again
-    for (int i = threadIdx.x; i < E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
+  if (warp < NUM_EPI_WARPS) {   // zero both E buffers once: padding columns are never written again
+    for (int i = threadIdx.x; i < 2 * E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -250,146 +270,195 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer =================
+    // Issue is the critical resource: UTCHMMA issue blocks for about the execution time of the MMAs
+    // ahead of it, so everything this thread does between two MMAs is tensor-pipe idle time.
     if (lane == 0) {
-      uint32_t it = 0, a_cnt[4] = {0, 0, 0, 0}, e_cnt = 0;
-      long long t_e = 0, t_a = 0, t_w = 0, t_i = 0, t0 = clock64(), tt;
-      for (int grp = group0; grp < n_groups; grp += group_step) {
-        tt = clock64();
-        mbar_wait(bar(B_EREADY), e_cnt & 1);
-        t_e += clock64() - tt;
-        ++e_cnt;
-        for (int i = 0; i < tab.n; ++i, ++it) {
-          const Step s = tab.s[i];
-          tt = clock64();
-          if (s.src == 1) { mbar_wait(bar(B_AREADY + s.chunk), a_cnt[s.chunk] & 1); ++a_cnt[s.chunk]; }
-          t_a += clock64() - tt;
-          const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-          tt = clock64();
-          mbar_wait(bar(B_WFULL + st), ph);
-          t_w += clock64() - tt;
-          tt = clock64();
-          tc_fence_after();
-          const uint32_t a_addr = s_base + (s.src ? OFF_A : OFF_E) + s.chunk * CHUNK_BYTES;
-          const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(s.layer & 1) * 256u;
-          const uint32_t idesc = idesc_f16(s.n);
-          for (int k = s.k0; k < s.k0 + s.nk; ++k)
-            umma_f16(d_tmem, sw128_desc(a_addr + k * 32), sw128_desc(b_addr + k * 32), idesc, (s.first && k == s.k0) ? 0u : 1u);
-          if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
-          if (s.last) tc_commit(bar(B_ACC + (s.layer & 1)));
-          t_i += clock64() - tt;
+      uint32_t it = 0, a_par = 0, tile_i = 0;
+      long long t_e = 0, t_a = 0, t_w = 0, t0 = clock64(), tt = 0;
+      constexpr uint32_t ID256 = idesc_f16(256), ID128 = idesc_f16(128);
+      // one ring stage of weights against an operand in shared memory (E region)
+      auto step_ss = [&](uint32_t a_smem, int k0, int nk, uint32_t d_tmem, uint32_t idesc, bool first) {
+        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        if (timing) tt = clock64();
+        mbar_wait(bar(B_WFULL + st), ph);
+        if (timing) t_w += clock64() - tt;
+        tc_fence_after();
+        const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k >= k0 && k < k0 + nk)
+            umma_f16(d_tmem, sw128_desc(a_smem + k * 32), sw128_desc(b_addr + k * 32), idesc, (first && k == k0) ? 0u : 1u);
+        if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
+        ++it;
+      };
+      // one ring stage against operand chunk c held in TMEM (the previous layer's accumulator, fp16 in place)
+      auto step_ts = [&](uint32_t a_tmem, int c, uint32_t d_tmem, uint32_t idesc, bool first) {
+        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+        if (timing) tt = clock64();
+        mbar_wait(bar(B_AREADY + c), a_par);
+        if (timing) { long long t1 = clock64(); t_a += t1 - tt; tt = t1; }
+        mbar_wait(bar(B_WFULL + st), ph);
+        if (timing) t_w += clock64() - tt;
+        tc_fence_after();
+        const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(d_tmem, a_tmem + 64u * c + 32u * (k >> 1) + 8u * (k & 1), sw128_desc(b_addr + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+        if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
+        ++it;
+      };
+      for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
+        const uint32_t eb = tile_i & 1;
+        const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
+        if (timing) tt = clock64();
+        mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
+        if (timing) t_e += clock64() - tt;
+#pragma unroll 1
+        for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
+          const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
+          const uint32_t idesc = (m == 9) ? ID128 : ID256;
+          bool first = true;
+          if (m == 0 || m == 5) {
+#pragma unroll 1
+            for (int c = 0; c < E_CHUNKS; ++c) { step_ss(e_addr + c * CHUNK_BYTES, 0, (BG && c == 1) ? 2 : 4, d_tmem, idesc, first); first = false; }
+          }
+          if (m == 9) {   // view-direction columns; last reader of this tile's E buffer
+            step_ss(e_addr + CHUNK_BYTES, 2, 2, d_tmem, idesc, first); first = false;
+            tc_commit(bar(B_EEMPTY + eb));
+          }
+          if (m != 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) { step_ts(a_tmem, c, d_tmem, idesc, first); first = false; }
+            a_par ^= 1;
+          }
+          tc_commit(bar(B_ACC + (m & 1)));
         }
       }
-      if (dbg) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; dbg[8 * blockIdx.x + 4] = t_i; }
+      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; }
     }
-  } else {
-    // ================= epilogue warps =================
-    const int q = warp & 3, hh = warp >> 2;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint8_t* sE = smem + OFF_E;
-    uint8_t* sA = smem + OFF_A;
-    uint32_t acc_cnt[2] = {0, 0};
-    long long e_wait = 0, e_emb = 0, e_t0 = clock64(), ett;
-    for (int grp = group0; grp < n_groups; grp += group_step) {
-      ett = clock64();
+  } else if (warp >= EMB_WARP0) {
+    // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
+    const int et = threadIdx.x - EMB_WARP0 * 32;    // 0..63, two rows each
+    uint32_t tile_i = 0;
+    for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
+      const uint32_t eb = tile_i & 1;
       const int tile = grp * CLUSTER + (int)cta_rank;
-      long long g = (long long)tile * TILE + row;
-      const bool valid = g < total;
-      if (!valid) g = total - 1;
-      {  // ---- positions + encodings -> E (fp16). half 0: raw + freqs 0..4, half 1: freqs 5..9 + view dir
+      mbar_wait(bar(B_EEMPTY + eb), ((tile_i >> 1) & 1) ^ 1);
+      uint8_t* sE = smem + OFF_E + eb * E_BYTES;
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = et + 64 * rr;
+        long long g = (long long)tile * TILE + row;
+        const bool valid = g < total;
+        if (!valid) g = total - 1;
         const int r = (int)(g / S), j = (int)(g % S);
         float o[3] = {ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2]};
         float d[3] = {ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]};
         float x[4];
         if (BG) {
           BgRay br = bg_ray_setup(o, d);
-          float dr = bg_point(br, z[(size_t)r * S + (S - 1 - j)], x);
-          if (hh == 0 && valid) out_depth_real[g] = dr;
+          float dr = bg_point(br, z[(size_t)r * S + (S - 1 - j)], x);   // flipped order, ddp_model.py:116-117
+          if (valid) out_depth_real[g] = dr;
         } else {
           float zv = z[g];
-          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(zv, d[c]));
+          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(zv, d[c]));   // ddp_model.py:91
         }
-        if (hh == 0) {
-          embed_rows<D>(x, 0, 5, true, sE, row, 0);
-        } else {
-          embed_rows<D>(x, 5, NF_POS, false, sE, row, 0);
-          float dn = norm3(d[0], d[1], d[2]);
-          float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};
-          embed_rows<3>(vd, 0, NF_VIEW, true, sE, row, VIEW_COL);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_EREADY));
-        e_emb += clock64() - ett;
+        float dn = norm3(d[0], d[1], d[2]);
+        float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
+        embed_vec(x, D, NF_POS, sE, row, 0);
+        embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_EFULL + eb));
+    }
+  } else {
+    // ================= epilogue warps =================
+    // Thread = one accumulator row (TMEM lane); warps w and w+4 split each 64-column chunk.  The fp16
+    // activations are written back IN PLACE over the first half of the fp32 columns just read
+    // (chunk j, half hh: K values [32hh,32hh+32) -> TMEM columns [64j+32hh, 64j+32hh+16)), where the
+    // next layer's MMAs read them as the A operand: no shared-memory round trip.
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_par[2] = {0, 0};
+    long long e_wait = 0, e_t0 = clock64(), ett = 0;
+    for (int grp = group0; grp < n_groups; grp += group_step) {
+      const int tile = grp * CLUSTER + (int)cta_rank;
+      const long long g = (long long)tile * TILE + row;
+      const bool valid = g < total;
       float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
       for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
         const int ab = m & 1;
-        ett = clock64();
-        mbar_wait(bar(B_ACC + ab), acc_cnt[ab] & 1);
-        e_wait += clock64() - ett;
-        ++acc_cnt[ab];
+        if (timing) ett = clock64();
+        mbar_wait(bar(B_ACC + ab), acc_par[ab]);
+        if (timing) e_wait += clock64() - ett;
+        acc_par[ab] ^= 1;
         tc_fence_after();
-        const float* bias = tail + T_BIAS + m * 256;
+        const float* bias = tail + T_BIAS + m * 256 + 32 * hh;
+        const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
         const int nchunk = (m == 9) ? 2 : 4;
-        for (int jc = 0; jc < nchunk; ++jc) {
-          const int col = 64 * jc + 32 * hh;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_addr + (uint32_t)(ab * 256 + col), v);
-          float4 b4[8];
+        uint32_t v[2][32];
+        tmem_ld32(acc_addr, v[0]);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) b4[t] = __ldg(reinterpret_cast<const float4*>(bias + col) + t);
-          tmem_ld_wait();
-          float f[32];
+        for (int jc = 0; jc < 4; ++jc) {
+          if (jc < nchunk) {
+            uint32_t (&cur)[32] = v[jc & 1];
+            float4 b4[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            f[4 * t + 0] = __uint_as_float(v[4 * t + 0]) + b4[t].x;
-            f[4 * t + 1] = __uint_as_float(v[4 * t + 1]) + b4[t].y;
-            f[4 * t + 2] = __uint_as_float(v[4 * t + 2]) + b4[t].z;
-            f[4 * t + 3] = __uint_as_float(v[4 * t + 3]) + b4[t].w;
-          }
-          if (m != 8) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) f[t] = fmaxf(f[t], 0.f);
-          }
-          if (m == 7) {   // sigma head on the fp32 activations, nerf_network.py:133
+            for (int t = 0; t < 8; ++t) b4[t] = __ldg(reinterpret_cast<const float4*>(bias + 64 * jc) + t);
+            tmem_ld_wait();
+            if (jc + 1 < nchunk) tmem_ld32(acc_addr + 64u * (jc + 1), v[(jc + 1) & 1]);   // overlaps the maths below
+            float f[32];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + col) + t);
-              sig_part = fmaf(f[4 * t], w4.x, sig_part); sig_part = fmaf(f[4 * t + 1], w4.y, sig_part);
-              sig_part = fmaf(f[4 * t + 2], w4.z, sig_part); sig_part = fmaf(f[4 * t + 3], w4.w, sig_part);
+              f[4 * t + 0] = __uint_as_float(cur[4 * t + 0]) + b4[t].x;
+              f[4 * t + 1] = __uint_as_float(cur[4 * t + 1]) + b4[t].y;
+              f[4 * t + 2] = __uint_as_float(cur[4 * t + 2]) + b4[t].z;
+              f[4 * t + 3] = __uint_as_float(cur[4 * t + 3]) + b4[t].w;
             }
-          }
-          if (m == 9) {   // rgb.2 on the fp32 hidden colour features, nerf_network.py:114-117
+            if (m != 8) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+              for (int t = 0; t < 32; ++t) f[t] = fmaxf(f[t], 0.f);
+            }
+            if (m == 7) {   // sigma head on the fp32 activations, nerf_network.py:133
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
-                float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + col) + t);
-                rgb_part[c] = fmaf(f[4 * t], w4.x, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 1], w4.y, rgb_part[c]);
-                rgb_part[c] = fmaf(f[4 * t + 2], w4.z, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 3], w4.w, rgb_part[c]);
+                float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * jc + 32 * hh) + t);
+                sig_part = fmaf(f[4 * t], w4.x, sig_part); sig_part = fmaf(f[4 * t + 1], w4.y, sig_part);
+                sig_part = fmaf(f[4 * t + 2], w4.z, sig_part); sig_part = fmaf(f[4 * t + 3], w4.w, sig_part);
               }
             }
-          } else {        // next layer's A operand, columns [col, col+32) of this row
+            if (m == 9) {   // rgb.2 on the fp32 hidden colour features, nerf_network.py:114-117
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __half2 h0 = __floats2half2_rn(f[8 * t + 0], f[8 * t + 1]), h1 = __floats2half2_rn(f[8 * t + 2], f[8 * t + 3]);
-              __half2 h2 = __floats2half2_rn(f[8 * t + 4], f[8 * t + 5]), h3 = __floats2half2_rn(f[8 * t + 6], f[8 * t + 7]);
-              uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                    *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-              *reinterpret_cast<uint4*>(sA + sw128_off(row, col + 8 * t)) = pk;
+              for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * jc + 32 * hh) + t);
+                  rgb_part[c] = fmaf(f[4 * t], w4.x, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 1], w4.y, rgb_part[c]);
+                  rgb_part[c] = fmaf(f[4 * t + 2], w4.z, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 3], w4.w, rgb_part[c]);
+                }
+              }
+            } else {        // next layer's A operand: 32 fp16 = 16 packed columns, in place
+              uint32_t pk[16];
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                __half2 h = __floats2half2_rn(f[2 * t], f[2 * t + 1]);
+                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              tmem_st16(acc_addr + 64u * jc, pk);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(B_AREADY + jc));
             }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_AREADY + jc));
           }
         }
       }
       // ---- combine the two column halves of each row, write sigma / rgb -------------------------------
-      tc_fence_before();
-      float4* scratch = reinterpret_cast<float4*>(sA);   // A is idle: every MMA of this tile has completed
+      float4* scratch = reinterpret_cast<float4*>(smem + OFF_SCRATCH);
       if (hh == 1) scratch[row] = make_float4(sig_part, rgb_part[0], rgb_part[1], rgb_part[2]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (hh == 0 && valid) {
@@ -402,7 +471,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    if (dbg && threadIdx.x == 0) { dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait; dbg[8 * blockIdx.x + 7] = e_emb; }
+    if (timing && threadIdx.x == 0) { dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait; }
   }
   tc_fence_before();
   __syncthreads();
