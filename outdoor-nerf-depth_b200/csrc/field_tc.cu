@@ -4,17 +4,24 @@
 // axis).  Per tile the ten dense layers (base 0..7, base_remap, rgb.0) run as tcgen05.mma
 // (M=128, N=256|128, K=16, fp16 operands, fp32 accumulators in TMEM); sigma (256->1) and rgb.2
 // (128->3) are fp32 dot products in the epilogue on the fp32 accumulators.
+// (N=128 halves would let the epilogue of one half hide under the MMAs of the other, but at M=128 an
+// N=128 MMA is operand-bandwidth bound -- measured 2x slower per FLOP -- so layers stay N=256.)
 //
-//   warp 0-7   epilogue: per layer TMEM -> regs, +bias, ReLU, fp16 pack -> written back to TMEM in
-//              place as the A operand of the next layer, 64 columns at a time
-//   warp 8     one lane issues every tcgen05.mma (A from TMEM, B from shared memory); layer l+1's
-//              K-chunk j starts as soon as the epilogue of layer l has produced columns [64j,64j+64)
-//              (two TMEM accumulators ping-pong between consecutive layers)
-//   warp 9     one lane streams the pre-swizzled weight tiles (32 KB each, in MMA issue order) from L2
-//              into a 5-deep shared-memory ring with cp.async.bulk (+cluster multicast) and mbarriers
-//   warp 10-11 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128)
+// The bias is part of the contraction: the E operand carries two constant-one columns and every
+// layer starts with a K=16 MMA against a [N x 16] tile holding the bias split into fp16 hi + lo,
+// so the epilogue is TMEM load -> cvt.rn.relu.f16x2 -> TMEM store and nothing else; the bias and
+// embedding steps of layer l+1 do not depend on layer l and run under its epilogue latency.
 //
-// Shared memory (bytes): E 2x32K | ring 5x32K | barriers.  TMEM: 2 x 256 columns.
+//   warp 0-7   epilogue: per layer TMEM -> regs, ReLU + fp16 pack -> written back to TMEM in place as
+//              the A operand of the next layer, 64 columns at a time
+//   warp 8     one lane issues every tcgen05.mma (A from TMEM or the E tile, B from shared memory);
+//              layer l+1's K-chunk j starts as soon as the epilogue of layer l has produced columns
+//              [64j,64j+64) (two TMEM accumulators ping-pong between consecutive layers)
+//   warp 9     one lane streams the pre-swizzled weight tiles (in MMA issue order) from L2 into a
+//              4 x 40 KB shared-memory ring with cp.async.bulk (+cluster multicast) and mbarriers
+//   warp 10-13 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128)
+//
+// Shared memory (bytes): E 2x32K | ring 4x40K | barriers | scratch.  TMEM: 2 x 256 columns.
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
 // against the fp32 reference: rgb/depth within 3e-5 relative (tests/test_parity_gpu.py).
 #include <cuda_fp16.h>
@@ -25,39 +32,42 @@ namespace npp {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int NSTAGE = 5;
-constexpr int STAGE_BYTES = 32768;
+constexpr int NSTAGE = 4;
+constexpr int AUX_BYTES = 8192;             // head of a ring slot: the layer's bias tile (first stage of a layer only)
+constexpr int STAGE_BYTES = AUX_BYTES + 32768;   // + one [256 N x 64 K] SW128 weight tile
 constexpr int CHUNK_BYTES = 16384;          // 128 rows x 64 fp16
-constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir; double-buffered
-constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_SCRATCH = OFF_BAR + 256;
+constexpr int BIAS_ROW_BYTES = 32;          // bias tile: [N x 16 K] fp16, unswizzled 8x8 core matrices
+constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir, 123/124 = 1; double-buffered
+constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_SCRATCH = OFF_BAR + 512;
 constexpr int SMEM_BYTES = OFF_SCRATCH + 128 * 16;
-constexpr int VIEW_COL = 96;
-constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, EMB_WARP0 = 10, NUM_EMB_WARPS = 2, THREADS = 384;
+constexpr int VIEW_COL = 96, ONE_COL = 123;  // ONE_COL, ONE_COL+1 hold 1.0 (bias hi / lo)
+constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, EMB_WARP0 = 10, NUM_EMB_WARPS = 4, THREADS = 448;
 constexpr int NUM_MMA_LAYERS = 10;          // base 0..7, remap, rgb0
 
 // barrier slots
-enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = 2 * NSTAGE + 4, B_EEMPTY = 2 * NSTAGE + 6,
-       B_ACC = 2 * NSTAGE + 8, B_COUNT = 2 * NSTAGE + 10 };
+enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = B_AREADY + 4, B_EEMPTY = B_EFULL + 2,
+       B_ACC = B_EEMPTY + 2, B_COUNT = B_ACC + 2 };
+static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 
 // fp32 tail of the packed buffer (float offsets)
-constexpr int T_BIAS = 0;                    // 10 x 256
-constexpr int T_WSIG = 10 * 256;             // 256
-constexpr int T_WRGB2 = 11 * 256;            // 3 x 128
-constexpr int T_BSIG = 11 * 256 + 384;
+constexpr int T_WSIG = 0;                    // 256
+constexpr int T_WRGB2 = 256;                 // 3 x 128
+constexpr int T_BSIG = 256 + 384;
 constexpr int T_BRGB2 = T_BSIG + 1;
 constexpr int T_TOTAL = T_BRGB2 + 3;
 
 __host__ __device__ constexpr int param_layer(int m) { return m < 8 ? m : m == 8 ? L_REMAP : L_RGB0; }
 
-// One MMA step = one weight tile in the ring x one 64-column operand chunk.
+// One ring stage = one weight tile x one operand chunk (+ the layer's bias tile ahead of its first stage).
+// The loader and the packer walk this table; the MMA issuer hard-codes the same order.
+enum { SRC_E = 0, SRC_A = 1 };
 struct Step {
   short layer;     // MMA layer 0..9
-  short src;       // 0 = E region, 1 = A region
-  short chunk;     // 64-column chunk within the region
-  short k0, nk;    // K=16 sub-steps [k0, k0+nk) of the chunk
+  short src;       // SRC_*
+  short chunk;     // 64-column chunk within the E / A region
   short n;         // MMA N (256 or 128)
-  short first, last;
-  int col0;        // first input feature (state-dict column) this tile maps, -1 = zero tile part
+  short bias;      // 1: [N x 16] bias tile at the head of the slot (blob: bias tile then weight tile)
+  int col0;        // first input feature (state-dict column) the tile maps; -2 = view dir + bias columns
   int blob_off, blob_bytes;
 };
 struct StepTable { Step s[48]; int n; int total; };
@@ -65,30 +75,17 @@ struct StepTable { Step s[48]; int n; int total; };
 __host__ __device__ constexpr StepTable make_table(bool bg) {
   StepTable t{};
   int i = 0, off = 0;
-  const int e_chunks = bg ? 2 : 1;
   for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-    const int n = (m == 9) ? 128 : 256;
-    const int bytes = n * 128;
-    int first = 1;
-    if (m == 0 || m == 5) {
-      for (int c = 0; c < e_chunks; ++c) {
-        t.s[i] = Step{(short)m, 0, (short)c, 0, (short)((bg && c == 1) ? 2 : 4), (short)n, (short)first, 0, c * 64, off, bytes};
-        first = 0; off += bytes; ++i;
-      }
-    }
-    if (m == 9) {   // view-direction columns [96,128) of E -> rgb.0 inputs 256..282
-      t.s[i] = Step{(short)m, 0, 1, 2, 2, (short)n, (short)first, 0, -2, off, bytes};
-      first = 0; off += bytes; ++i;
-    }
-    if (m != 0) {
-      for (int c = 0; c < 4; ++c) {
-        const int base = (m == 5) ? emb_dim(bg) : 0;
-        t.s[i] = Step{(short)m, 1, (short)c, 0, 4, (short)n, (short)first, (short)(c == 3), base + c * 64, off, bytes};
-        first = 0; off += bytes; ++i;
-      }
-    } else {
-      t.s[i - 1].last = 1;
-    }
+    const short n = (m == 9) ? 128 : 256;
+    short bias = (m != 9);
+    auto push = [&](short src, short chunk, int col0) {
+      const int bytes = n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
+      t.s[i] = Step{(short)m, src, chunk, n, bias, col0, off, bytes};
+      off += bytes; ++i; bias = 0;
+    };
+    if (m == 0 || m == 5) for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 64 * c);
+    if (m == 9) push(SRC_E, 1, -2);      // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
+    if (m != 0) for (int c = 0; c < 4; ++c) push(SRC_A, (short)c, ((m == 5) ? emb_dim(bg) : 0) + 64 * c);
   }
   t.n = i;
   t.total = off;
@@ -114,6 +111,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n.reg .pred p;\nWAIT_LOOP:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+// waits on two barriers at once (their try_wait latencies overlap)
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nWAIT2_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n"
+      "and.pred p, p, q;\n"
+      "@p bra WAIT2_DONE;\nbra WAIT2_LOOP;\nWAIT2_DONE:\n}" ::"r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -171,13 +177,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are only valid after wait::ld.  Binding them to the
+// wait as in/out operands keeps the compiler from reading or moving them across it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
+}
+// two fp32 -> packed fp16x2 (lo in the low half), optionally through ReLU, one instruction
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_f16x2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
 
 // K-major, 128-byte-swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 | LBO=1<<16 | SBO=64<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major unswizzled [N x 16] tile: 8x8 core matrices of 128 B; N/8 along N (SBO = 128 B), 2 along K (LBO = 16 N B)
+__device__ __forceinline__ uint64_t bias_desc(uint32_t saddr, int n) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)n << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr int bias_tile_off(int n_total, int n, int k) { return (k >> 3) * 16 * n_total + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128
 __host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 // byte offset of element (row r, column c) of a [128 x 64k] region made of 64-column SW128 chunks
@@ -185,20 +213,31 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((c >> 6) * CHUNK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
 }
 
-// Encodes one row (sample) of the E operand: columns [0,emb) = Embedder(pts) (nerf_network.py:42-60),
-// columns [96,123) = Embedder(viewdir); fp16, 128B-swizzled.  Deliberately a compact loop around ONE
-// sincosf call site: this runs on the two producer warps, off the critical path, and the kernel's
-// instruction footprint matters more (I-cache) than its speed.
-__device__ __noinline__ void embed_vec(const float* x, int dim, int nfreq, uint8_t* region, int row, int col_base) {
+// sin/cos of x * 2^k for the fp16 operand: two-constant Cody-Waite reduction to [-pi, pi] (exact to
+// ~3e-7 for |arg| < 2^10), then the SFU approximations (abs error ~5e-7, far below the fp16 rounding
+// of the operand, 2.4e-4).
+__device__ __forceinline__ void fast_sincos(float arg, float* sn, float* cs) {
+  const float n = rintf(arg * 0.15915494309189535f);
+  float r = fmaf(-n, 6.2831854820251465f, arg);
+  r = fmaf(-n, -1.7484555e-7f, r);
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
+// Encodes one row (sample) of the E operand: columns [col_base, +dim(1+2 nfreq)) = Embedder(x)
+// (nerf_network.py:42-60); fp16, 128B-swizzled.
+__device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, uint8_t* region, int row, int col_base) {
   for (int c = 0; c < dim; ++c) *reinterpret_cast<__half*>(region + sw128_off(row, col_base + c)) = __float2half_rn(x[c]);
 #pragma unroll 1
-  for (int i = 0; i < nfreq * dim; ++i) {
-    const int k = i / dim, c = i - k * dim;
-    float sn, cs;
-    sincosf(x[c] * (float)(1 << k), &sn, &cs);
-    const int col = col_base + dim + 2 * k * dim + c;
-    *reinterpret_cast<__half*>(region + sw128_off(row, col)) = __float2half_rn(sn);
-    *reinterpret_cast<__half*>(region + sw128_off(row, col + dim)) = __float2half_rn(cs);
+  for (int k = 0; k < nfreq; ++k) {
+    const float f = (float)(1 << k);
+    for (int c = 0; c < dim; ++c) {
+      float sn, cs;
+      fast_sincos(x[c] * f, &sn, &cs);
+      const int col = col_base + dim + 2 * k * dim + c;
+      *reinterpret_cast<__half*>(region + sw128_off(row, col)) = __float2half_rn(sn);
+      *reinterpret_cast<__half*>(region + sw128_off(row, col + dim)) = __float2half_rn(cs);
+    }
   }
 }
 
@@ -208,10 +247,9 @@ template <bool BG, int CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
-                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg) {
+                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
-  constexpr int E_CHUNKS = BG ? 2 : 1;
   const StepTable& tab = c_tab[BG ? 1 : 0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
@@ -231,15 +269,19 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(B_EFULL + i), NUM_EMB_WARPS); mbar_init(bar(B_EEMPTY + i), 1); }
-    mbar_init(bar(B_ACC), 1); mbar_init(bar(B_ACC + 1), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == LOAD_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < NUM_EPI_WARPS) {   // zero both E buffers once: padding columns are never written again
+  if (warp < NUM_EPI_WARPS) {   // zero both E buffers once (padding columns are never written again), then the two ones
     for (int i = threadIdx.x; i < 2 * E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int eb = threadIdx.x >> 7, row = threadIdx.x & 127;
+    *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL)) = __float2half_rn(1.f);
+    *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL + 1)) = __float2half_rn(1.f);
     fence_proxy_async();
   }
   tc_fence_before();
@@ -257,122 +299,156 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         for (int i = 0; i < tab.n; ++i, ++it) {
           const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
           const uint32_t bytes = (uint32_t)tab.s[i].blob_bytes;
+          // a stage without bias tile lands straight on the weight area of the slot
+          const uint32_t dst = s_base + OFF_W + st * STAGE_BYTES + (tab.s[i].bias ? (uint32_t)(AUX_BYTES - tab.s[i].n * BIAS_ROW_BYTES) : (uint32_t)AUX_BYTES);
           mbar_wait(bar(B_WEMPTY + st), ph ^ 1);          // every CTA of the cluster has consumed this stage
           mbar_expect_tx(bar(B_WFULL + st), bytes);
           if (CLUSTER == 1) {
-            bulk_g2s(s_base + OFF_W + st * STAGE_BYTES, blobs + tab.s[i].blob_off, bytes, bar(B_WFULL + st));
+            bulk_g2s(dst, blobs + tab.s[i].blob_off, bytes, bar(B_WFULL + st));
           } else {
             const uint32_t part = bytes / CLUSTER, o = cta_rank * part;
-            bulk_g2s_mcast(s_base + OFF_W + st * STAGE_BYTES + o, blobs + tab.s[i].blob_off + o, part, bar(B_WFULL + st), kMask);
+            bulk_g2s_mcast(dst + o, blobs + tab.s[i].blob_off + o, part, bar(B_WFULL + st), kMask);
           }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer =================
-    // Issue is the critical resource: UTCHMMA issue blocks for about the execution time of the MMAs
-    // ahead of it, so everything this thread does between two MMAs is tensor-pipe idle time.
     if (lane == 0) {
-      uint32_t it = 0, a_par = 0, tile_i = 0;
-      long long t_e = 0, t_a = 0, t_w = 0, t0 = clock64(), tt = 0;
+      uint32_t st = 0, ph = 0, a_par = 0, tile_i = 0;
+      long long t_e = 0, t_a = 0, t_w = 0, t_i = 0, t_c = 0, t0 = clock64(), tt = 0;
       constexpr uint32_t ID256 = idesc_f16(256), ID128 = idesc_f16(128);
-      // one ring stage of weights against an operand in shared memory (E region)
-      auto step_ss = [&](uint32_t a_smem, int k0, int nk, uint32_t d_tmem, uint32_t idesc, bool first) {
-        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-        if (timing) tt = clock64();
-        mbar_wait(bar(B_WFULL + st), ph);
-        if (timing) t_w += clock64() - tt;
-        tc_fence_after();
-        const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k >= k0 && k < k0 + nk)
-            umma_f16(d_tmem, sw128_desc(a_smem + k * 32), sw128_desc(b_addr + k * 32), idesc, (first && k == k0) ? 0u : 1u);
+      constexpr int E_CHUNKS = BG ? 2 : 1;
+      auto commit_stage = [&]() {
         if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
-        ++it;
-      };
-      // one ring stage against operand chunk c held in TMEM (the previous layer's accumulator, fp16 in place)
-      auto step_ts = [&](uint32_t a_tmem, int c, uint32_t d_tmem, uint32_t idesc, bool first) {
-        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
-        if (timing) tt = clock64();
-        mbar_wait(bar(B_AREADY + c), a_par);
-        if (timing) { long long t1 = clock64(); t_a += t1 - tt; tt = t1; }
-        mbar_wait(bar(B_WFULL + st), ph);
-        if (timing) t_w += clock64() - tt;
-        tc_fence_after();
-        const uint32_t b_addr = s_base + OFF_W + st * STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ts(d_tmem, a_tmem + 64u * c + 32u * (k >> 1) + 8u * (k & 1), sw128_desc(b_addr + k * 32), idesc, (first && k == 0) ? 0u : 1u);
-        if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
-        ++it;
+        if (++st == NSTAGE) { st = 0; ph ^= 1; }
       };
       for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
         const uint32_t eb = tile_i & 1;
         const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
+        const uint64_t one_desc = sw128_desc(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
         if (timing) tt = clock64();
         mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
+        // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
+        // overwrite: wait until those MMAs have completed (ACC[1] completes 5 times per tile; layer 9 is the 5th)
+        if (tile_i > 0) mbar_wait(bar(B_ACC + 1), (tile_i - 1) & 1);
         if (timing) t_e += clock64() - tt;
 #pragma unroll 1
         for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
           const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
           const uint32_t idesc = (m == 9) ? ID128 : ID256;
-          bool first = true;
-          if (m == 0 || m == 5) {
-#pragma unroll 1
-            for (int c = 0; c < E_CHUNKS; ++c) { step_ss(e_addr + c * CHUNK_BYTES, 0, (BG && c == 1) ? 2 : 4, d_tmem, idesc, first); first = false; }
+          uint32_t acc = 0u;
+          if (m == 0 || m == 5) {      // embedding chunks (+ the bias tile with the first)
+#pragma unroll
+            for (int c = 0; c < E_CHUNKS; ++c) {
+              const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
+              if (timing) tt = clock64();
+              mbar_wait(bar(B_WFULL + st), ph);
+              if (timing) t_w += clock64() - tt;
+              tc_fence_after();
+              if (c == 0) { umma_f16(d_tmem, one_desc, bias_desc(slot, 256), idesc, 0u); acc = 1u; }
+              const uint64_t ad = sw128_desc(e_addr + c * CHUNK_BYTES), bd = sw128_desc(slot + AUX_BYTES);
+#pragma unroll
+              for (int k = 0; k < (c == 1 ? 2 : 4); ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, 1u);
+              commit_stage();
+            }
           }
-          if (m == 9) {   // view-direction columns; last reader of this tile's E buffer
-            step_ss(e_addr + CHUNK_BYTES, 2, 2, d_tmem, idesc, first); first = false;
-            tc_commit(bar(B_EEMPTY + eb));
+          if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
+            const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
+            if (timing) tt = clock64();
+            mbar_wait(bar(B_WFULL + st), ph);
+            if (timing) t_w += clock64() - tt;
+            tc_fence_after();
+            const uint64_t ad = sw128_desc(e_addr + CHUNK_BYTES), bd = sw128_desc(slot + AUX_BYTES);
+            umma_f16(d_tmem, ad + 4u, bd + 4u, idesc, 0u);
+            umma_f16(d_tmem, ad + 6u, bd + 6u, idesc, 1u);
+            acc = 1u;
+            commit_stage();
+            tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
           }
           if (m != 0) {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) { step_ts(a_tmem, c, d_tmem, idesc, first); first = false; }
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
+              const uint64_t bd = sw128_desc(slot + AUX_BYTES);
+              const uint32_t a0 = a_tmem + 64u * c;
+              long long ti0 = 0;
+              // (The bias MMA must not be hoisted above the AREADY wait: it overwrites the accumulator buffer the
+              //  previous layer's last MMAs still read their A operand from, and consecutive tcgen05.mma are not
+              //  interlocked on TMEM A-read vs D-write.)
+              if (timing) {
+                tt = clock64();
+                mbar_wait(bar(B_WFULL + st), ph);
+                long long t1 = clock64(); t_w += t1 - tt;
+                mbar_wait(bar(B_AREADY + c), a_par);
+                t_a += clock64() - t1;
+              } else {
+                mbar_wait2(bar(B_AREADY + c), a_par, bar(B_WFULL + st), ph);
+              }
+              tc_fence_after();
+              if (timing) ti0 = clock64();
+              if (acc == 0u) { umma_f16(d_tmem, one_desc, bias_desc(slot, 256), idesc, 0u); acc = 1u; }
+              if ((flags & 2) && m != 9) {   // experiment: every N=256 MMA as two N=128 halves
+                for (int hN = 0; hN < 2; ++hN) {
+                  umma_f16_ts(d_tmem + 128u * hN, a0, bd + 1024u * hN, ID128, 1u);
+                  umma_f16_ts(d_tmem + 128u * hN, a0 + 8u, bd + 1024u * hN + 2u, ID128, 1u);
+                  umma_f16_ts(d_tmem + 128u * hN, a0 + 32u, bd + 1024u * hN + 4u, ID128, 1u);
+                  umma_f16_ts(d_tmem + 128u * hN, a0 + 40u, bd + 1024u * hN + 6u, ID128, 1u);
+                }
+              } else {
+              umma_f16_ts(d_tmem, a0, bd, idesc, 1u);
+              umma_f16_ts(d_tmem, a0 + 8u, bd + 2u, idesc, 1u);
+              umma_f16_ts(d_tmem, a0 + 32u, bd + 4u, idesc, 1u);
+              umma_f16_ts(d_tmem, a0 + 40u, bd + 6u, idesc, 1u);
+              }
+              if (timing) { long long t1 = clock64(); t_i += t1 - ti0; ti0 = t1; }
+              commit_stage();
+              if (timing) t_c += clock64() - ti0;
+            }
             a_par ^= 1;
           }
           tc_commit(bar(B_ACC + (m & 1)));
         }
       }
-      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; }
+      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; dbg[8 * 148 + 2 * blockIdx.x] = t_i; dbg[8 * 148 + 2 * blockIdx.x + 1] = t_c; }
     }
   } else if (warp >= EMB_WARP0) {
     // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
-    const int et = threadIdx.x - EMB_WARP0 * 32;    // 0..63, two rows each
+    const int row = threadIdx.x - EMB_WARP0 * 32;    // 0..127
     uint32_t tile_i = 0;
+    long long m_t0 = clock64(), m_wait = 0, mtt = 0;
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
       const uint32_t eb = tile_i & 1;
       const int tile = grp * CLUSTER + (int)cta_rank;
+      if (timing) mtt = clock64();
       mbar_wait(bar(B_EEMPTY + eb), ((tile_i >> 1) & 1) ^ 1);
+      if (timing) m_wait += clock64() - mtt;
       uint8_t* sE = smem + OFF_E + eb * E_BYTES;
-#pragma unroll 1
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = et + 64 * rr;
-        long long g = (long long)tile * TILE + row;
-        const bool valid = g < total;
-        if (!valid) g = total - 1;
-        const int r = (int)(g / S), j = (int)(g % S);
-        float o[3] = {ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2]};
-        float d[3] = {ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]};
-        float x[4];
-        if (BG) {
-          BgRay br = bg_ray_setup(o, d);
-          float dr = bg_point(br, z[(size_t)r * S + (S - 1 - j)], x);   // flipped order, ddp_model.py:116-117
-          if (valid) out_depth_real[g] = dr;
-        } else {
-          float zv = z[g];
-          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(zv, d[c]));   // ddp_model.py:91
-        }
-        float dn = norm3(d[0], d[1], d[2]);
-        float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
-        embed_vec(x, D, NF_POS, sE, row, 0);
-        embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
+      long long g = (long long)tile * TILE + row;
+      const bool valid = g < total;
+      if (!valid) g = total - 1;
+      const int r = (int)(g / S), j = (int)(g % S);
+      float o[3] = {ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2]};
+      float d[3] = {ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]};
+      float x[4];
+      if (BG) {
+        BgRay br = bg_ray_setup(o, d);
+        float dr = bg_point(br, z[(size_t)r * S + (S - 1 - j)], x);   // flipped order, ddp_model.py:116-117
+        if (valid) out_depth_real[g] = dr;
+      } else {
+        float zv = z[g];
+        for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(o[c], __fmul_rn(zv, d[c]));   // ddp_model.py:91
       }
+      float dn = norm3(d[0], d[1], d[2]);
+      float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
+      embed_vec(x, D, NF_POS, sE, row, 0);
+      embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EFULL + eb));
     }
+    if (timing && threadIdx.x == EMB_WARP0 * 32) { dbg[8 * blockIdx.x + 4] = clock64() - m_t0; dbg[8 * blockIdx.x + 7] = m_wait; }
   } else {
     // ================= epilogue warps =================
     // Thread = one accumulator row (TMEM lane); warps w and w+4 split each 64-column chunk.  The fp16
@@ -382,8 +458,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_par[2] = {0, 0};
-    long long e_wait = 0, e_t0 = clock64(), ett = 0;
+    uint32_t acc_par = 0;
+    long long e_wait = 0, e_t0 = clock64(), ett = 0, e_ld = 0, e_cvt = 0, e_st = 0, e_arr = 0;
     for (int grp = group0; grp < n_groups; grp += group_step) {
       const int tile = grp * CLUSTER + (int)cta_rank;
       const long long g = (long long)tile * TILE + row;
@@ -393,66 +469,63 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
         const int ab = m & 1;
         if (timing) ett = clock64();
-        mbar_wait(bar(B_ACC + ab), acc_par[ab]);
+        mbar_wait(bar(B_ACC + ab), (acc_par >> ab) & 1u);
         if (timing) e_wait += clock64() - ett;
-        acc_par[ab] ^= 1;
+        acc_par ^= 1u << ab;
         tc_fence_after();
-        const float* bias = tail + T_BIAS + m * 256 + 32 * hh;
         const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
         const int nchunk = (m == 9) ? 2 : 4;
         uint32_t v[2][32];
         tmem_ld32(acc_addr, v[0]);
 #pragma unroll
-        for (int jc = 0; jc < 4; ++jc) {
-          if (jc < nchunk) {
-            uint32_t (&cur)[32] = v[jc & 1];
-            float4 b4[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) b4[t] = __ldg(reinterpret_cast<const float4*>(bias + 64 * jc) + t);
-            tmem_ld_wait();
-            if (jc + 1 < nchunk) tmem_ld32(acc_addr + 64u * (jc + 1), v[(jc + 1) & 1]);   // overlaps the maths below
-            float f[32];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              f[4 * t + 0] = __uint_as_float(cur[4 * t + 0]) + b4[t].x;
-              f[4 * t + 1] = __uint_as_float(cur[4 * t + 1]) + b4[t].y;
-              f[4 * t + 2] = __uint_as_float(cur[4 * t + 2]) + b4[t].z;
-              f[4 * t + 3] = __uint_as_float(cur[4 * t + 3]) + b4[t].w;
-            }
-            if (m != 8) {
-#pragma unroll
-              for (int t = 0; t < 32; ++t) f[t] = fmaxf(f[t], 0.f);
-            }
+        for (int j = 0; j < 4; ++j) {
+          if (j < nchunk) {
+            uint32_t (&cur)[32] = v[j & 1];
+            if (timing) ett = clock64();
+            tmem_ld_wait(cur);
+            if (timing) { long long t1 = clock64(); e_ld += t1 - ett; ett = t1; }
+            if (j + 1 < nchunk) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
             if (m == 7) {   // sigma head on the fp32 activations, nerf_network.py:133
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
-                float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * jc + 32 * hh) + t);
-                sig_part = fmaf(f[4 * t], w4.x, sig_part); sig_part = fmaf(f[4 * t + 1], w4.y, sig_part);
-                sig_part = fmaf(f[4 * t + 2], w4.z, sig_part); sig_part = fmaf(f[4 * t + 3], w4.w, sig_part);
+                float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh) + t);
+                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t]), 0.f), w4.x, sig_part);
+                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f), w4.y, sig_part);
+                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), w4.z, sig_part);
+                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f), w4.w, sig_part);
               }
             }
             if (m == 9) {   // rgb.2 on the fp32 hidden colour features, nerf_network.py:114-117
 #pragma unroll
+              for (int t = 0; t < 32; ++t) cur[t] = __float_as_uint(fmaxf(__uint_as_float(cur[t]), 0.f));
+#pragma unroll
               for (int c = 0; c < 3; ++c) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                  float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * jc + 32 * hh) + t);
-                  rgb_part[c] = fmaf(f[4 * t], w4.x, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 1], w4.y, rgb_part[c]);
-                  rgb_part[c] = fmaf(f[4 * t + 2], w4.z, rgb_part[c]); rgb_part[c] = fmaf(f[4 * t + 3], w4.w, rgb_part[c]);
+                  float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * j + 32 * hh) + t);
+                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t]), w4.x, rgb_part[c]);
+                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 1]), w4.y, rgb_part[c]);
+                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 2]), w4.z, rgb_part[c]);
+                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 3]), w4.w, rgb_part[c]);
                 }
               }
             } else {        // next layer's A operand: 32 fp16 = 16 packed columns, in place
               uint32_t pk[16];
+              if (m == 8) {
 #pragma unroll
-              for (int t = 0; t < 16; ++t) {
-                __half2 h = __floats2half2_rn(f[2 * t], f[2 * t + 1]);
-                pk[t] = *reinterpret_cast<uint32_t*>(&h);
+                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<false>(cur[2 * t], cur[2 * t + 1]);
+              } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
               }
-              tmem_st16(acc_addr + 64u * jc, pk);
+              if (timing) { long long t1 = clock64(); e_cvt += t1 - ett; ett = t1; }
+              tmem_st16(acc_addr + 64u * j, pk);
               tmem_st_wait();
+              if (timing) { long long t1 = clock64(); e_st += t1 - ett; ett = t1; }
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_AREADY + jc));
+              if (lane == 0) mbar_arrive(bar(B_AREADY + j));
+              if (timing) { long long t1 = clock64(); e_arr += t1 - ett; ett = t1; }
             }
           }
         }
@@ -471,7 +544,11 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    if (timing && threadIdx.x == 0) { dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait; }
+    if (timing && threadIdx.x == 0) {
+      dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait;
+      long long* x = dbg + 10 * 148 + 4 * blockIdx.x;
+      x[0] = e_ld; x[1] = e_cvt; x[2] = e_st; x[3] = e_arr;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -482,7 +559,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   }
 }
 
-// ---- packer: state-dict tensors -> swizzled fp16 tiles in MMA issue order + fp32 tail ---------------
+// ---- packer: state-dict tensors -> fp16 tiles in MMA issue order + fp32 tail ------------------------
 __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__ out, int blob_total) {
   const StepTable& tab = c_tab[bg ? 1 : 0];
   const int i = blockIdx.y;
@@ -490,25 +567,47 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
     const Step s = tab.s[i];
     const int pl = param_layer(s.layer), nin = layer_in(pl, bg);
     const float* Wl = p.w[pl];
-    __half* blob = reinterpret_cast<__half*>(out + s.blob_off);
+    const float* Bl = p.b[pl];
+    const int bias_bytes = s.bias ? s.n * BIAS_ROW_BYTES : 0;
+    if (s.bias) {
+      __half* bt = reinterpret_cast<__half*>(out + s.blob_off);
+      for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 16; idx += gridDim.x * blockDim.x) {
+        const int nn = idx >> 4, kk = idx & 15;
+        const float b = Bl[nn];
+        const __half hi = __float2half_rn(b);
+        __half v = __float2half_rn(0.f);
+        if (kk == ONE_COL - 112) v = hi;
+        if (kk == ONE_COL + 1 - 112) v = __float2half_rn(b - __half2float(hi));
+        bt[bias_tile_off(s.n, nn, kk) / 2] = v;
+      }
+    }
+    __half* blob = reinterpret_cast<__half*>(out + s.blob_off + bias_bytes);
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 64; idx += gridDim.x * blockDim.x) {
       const int nn = idx >> 6, kk = idx & 63;
-      int src = -1;
-      if (s.src == 0) {
-        if (s.col0 == -2) { int vc = kk - (VIEW_COL - 64); if (vc >= 0 && vc < VIEW_DIM) src = W + vc; }   // rgb.0 view part
-        else { int c = s.col0 + kk; if (c < emb_dim(bg)) src = c; }                                       // embedding part
+      float v = 0.f;
+      if (s.src == SRC_E) {
+        if (s.col0 == -2) {           // rgb.0: view part + bias columns
+          const int c = 64 + kk;
+          if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)nn * nin + W + (c - VIEW_COL)];
+          else if (c == ONE_COL || c == ONE_COL + 1) {
+            const float b = Bl[nn];
+            const float hi = __half2float(__float2half_rn(b));
+            v = (c == ONE_COL) ? hi : b - hi;
+          }
+        } else {
+          const int c = s.col0 + kk;
+          if (c < emb_dim(bg)) v = Wl[(size_t)nn * nin + c];                                  // embedding part
+        }
       } else {
-        src = s.col0 + kk;
+        v = Wl[(size_t)nn * nin + s.col0 + kk];
       }
-      float v = src >= 0 ? Wl[(size_t)nn * nin + src] : 0.f;
       blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
     }
   } else {
     float* tail = reinterpret_cast<float*>(out + blob_total);
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < T_TOTAL; idx += gridDim.x * blockDim.x) {
       float v = 0.f;
-      if (idx < T_WSIG) { int m = idx / 256, c = idx % 256; int pl = param_layer(m); v = c < layer_out(pl) ? p.b[pl][c] : 0.f; }
-      else if (idx < T_WRGB2) v = p.w[L_SIGMA][idx - T_WSIG];
+      if (idx < T_WRGB2) v = p.w[L_SIGMA][idx - T_WSIG];
       else if (idx < T_BSIG) v = p.w[L_RGB2][idx - T_WRGB2];
       else if (idx == T_BSIG) v = p.b[L_SIGMA][0];
       else v = p.b[L_RGB2][idx - T_BRGB2];
@@ -533,6 +632,7 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
 
 static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1, 2 or 4)
 static long long* g_dbg = nullptr;
+static int g_flags = 0;          // experiment switches (diagnostics only)
 
 template <bool BG, int CLUSTER>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
@@ -558,14 +658,15 @@ static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, cons
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_dr, num_tiles, g_dbg);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_dr, num_tiles, g_dbg, g_flags);
   if (e != cudaSuccess) { npp_set_error("field_tc launch (cluster %d): %s", CLUSTER, cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 
-// debug hook (tests/diag only): device buffer of 4 x gridDim.x int64 receiving the MMA thread's cycle counters
+// debug hooks (tests/diag only): device buffer of 8 x gridDim.x int64 receiving per-role cycle counters
 extern "C" void nerfpp_debug_set_tc_timers(long long* dev_buf) { g_dbg = dev_buf; }
 extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = c; }
+extern "C" void nerfpp_debug_set_tc_flags(int f) { g_flags = f; }
 
 int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
                  float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st) {
@@ -576,9 +677,10 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (g_cluster < 0) {
+    if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
     const char* e = getenv("NERFPP_TC_CLUSTER");
-    g_cluster = e ? atoi(e) : 2;
-    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 2;
+    g_cluster = e ? atoi(e) : 1;
+    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 1;
   }
   const long long total = (long long)n * S;
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);

@@ -12,6 +12,8 @@ dev = torch.device("cuda:0")
 L = _lib.lib()
 L.nerfpp_debug_set_tc_timers.argtypes = [ctypes.c_void_p]
 L.nerfpp_debug_set_tc_cluster.argtypes = [ctypes.c_int]
+L.nerfpp_debug_set_tc_flags.argtypes = [ctypes.c_int]
+L.nerfpp_debug_set_tc_flags(int(os.environ.get('FLAGS', '0')))
 nets = make_models([O.densify(O.make_params(), 5.0)])
 net = nets[0].nerf_net
 n, S = 4096, 192
@@ -26,8 +28,8 @@ for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_
     packed = net._packed[is_bg].get(tensors, FIELD_TC)
     for cl in [int(x) for x in os.environ.get("CLUSTERS", "1,2,4").split(",")]:
         L.nerfpp_debug_set_tc_cluster(cl)
-        dbg = torch.zeros(8 * 148, dtype=torch.int64, device=dev)
-        L.nerfpp_debug_set_tc_timers(ctypes.c_void_p(dbg.data_ptr()))
+        dbg = torch.zeros(14 * 148, dtype=torch.int64, device=dev)
+        L.nerfpp_debug_set_tc_timers(ctypes.c_void_p(dbg.data_ptr()) if os.environ.get('TIMERS', '1') == '1' else None)
         try:
             for _ in range(3):
                 sig, rgb, dr = ops.field_forward(packed, is_bg, o, d, z, FIELD_TC)
@@ -41,12 +43,13 @@ for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_
             sig, rgb, dr = ops.field_forward(packed, is_bg, o, d, z, FIELD_TC)
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
-        t = dbg.cpu().numpy().reshape(-1, 8)
-        t = t[t[:, 0] > 0]
+        extra = dbg.cpu().numpy()[8 * 148:10 * 148].reshape(-1, 2); ep = dbg.cpu().numpy()[10 * 148:].reshape(-1, 4); t = dbg.cpu().numpy()[:8 * 148].reshape(-1, 8)
+        t = t[t[:, 0] > 0] if (t[:, 0] > 0).any() else t[:1]
+        print("   issue(incl A waits) %.0f  commits %.0f" % (extra[:, 0].mean(), extra[:, 1].mean()), " epi: ld-wait %.0f cvt %.0f st %.0f arrive %.0f" % tuple(ep.mean(0)))
         key = (is_bg,)
         if key not in ref:
             ref[key] = (sig.clone(), rgb.clone())
         es, er = relerr(sig.cpu().numpy(), ref[key][0].cpu().numpy()), relerr(rgb.cpu().numpy(), ref[key][1].cpu().numpy())
-        print("bg=%d cluster=%d  %.3f ms  %.0f TFLOP/s  ctas=%d  mma-thread cycles: total %.0f  wait_E %.0f  wait_A %.0f  wait_W %.0f issue %.0f | epi warp0: total %.0f wait_acc %.0f embed %.0f  (vs cluster1: sigma %.1e rgb %.1e)"
-              % (is_bg, cl, ms, 2 * macs * n * S / ms / 1e9, len(t), t[:, 0].mean(), t[:, 1].mean(), t[:, 2].mean(), t[:, 3].mean(), t[:, 4].mean(), t[:, 5].mean(), t[:, 6].mean(), t[:, 7].mean(), es, er))
+        print("bg=%d cluster=%d  %.3f ms  %.0f TFLOP/s  ctas=%d  mma-thread cycles: total %.0f  wait_E %.0f  wait_A %.0f  wait_W %.0f | emb total %.0f wait %.0f | epi warp0: total %.0f wait_acc %.0f  (vs cluster1: sigma %.1e rgb %.1e)"
+              % (is_bg, cl, ms, 2 * macs * n * S / ms / 1e9, len(t), t[:, 0].mean(), t[:, 1].mean(), t[:, 2].mean(), t[:, 3].mean(), t[:, 4].mean(), t[:, 7].mean(), t[:, 5].mean(), t[:, 6].mean(), es, er))
     L.nerfpp_debug_set_tc_timers(None)
