@@ -46,7 +46,7 @@ constexpr int NUM_MMA_LAYERS = 10;          // base 0..7, remap, rgb0
 
 // barrier slots
 enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = B_AREADY + 4, B_EEMPTY = B_EFULL + 2,
-       B_ACC = B_EEMPTY + 2, B_COUNT = B_ACC + 2 };
+       B_ACC = B_EEMPTY + 2, B_COUNT = B_ACC + 4 };
 static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 
 // fp32 tail of the packed buffer (float offsets)
@@ -58,42 +58,60 @@ constexpr int T_TOTAL = T_BRGB2 + 3;
 
 __host__ __device__ constexpr int param_layer(int m) { return m < 8 ? m : m == 8 ? L_REMAP : L_RGB0; }
 
-// One ring stage = one weight tile x one operand chunk (+ the layer's bias tile ahead of its first stage).
-// The loader and the packer walk this table; the MMA issuer hard-codes the same order.
+// One ring stage = one or two weight tiles (64 input columns each) of one layer (+ the bias tile ahead of the
+// first stage of a layer / half).  The loader and the packer walk this table; the MMA issuer hard-codes the order.
+//
+// Two schedules (template parameter HALVES of the kernel):
+//   HALVES = 0  every layer is one N=256 accumulation: stages of one [256 x 64] tile.
+//   HALVES = 1  every 256-wide layer is issued as two N=128 halves (output rows [0,128) then [128,256) of the
+//               weight), stages of two [128 x 64] tiles: the epilogue of half 0 runs under the MMAs of half 1
+//               and the next layer's first K-chunks are ready before the tensor pipe needs them.
 enum { SRC_E = 0, SRC_A = 1 };
 struct Step {
-  short layer;     // MMA layer 0..9
+  short layer, half;   // MMA layer 0..9; output half (weight rows [128 half, +n))
   short src;       // SRC_*
-  short chunk;     // 64-column chunk within the E / A region
-  short n;         // MMA N (256 or 128)
-  short bias;      // 1: [N x 16] bias tile at the head of the slot (blob: bias tile then weight tile)
-  int col0;        // first input feature (state-dict column) the tile maps; -2 = view dir + bias columns
+  short chunk;     // first 64-column chunk within the E / A region
+  short ntiles;    // 1 or 2 consecutive chunks
+  short n;         // rows per tile = MMA N (256 or 128)
+  short bias;      // 1: [n x 16] bias tile at the head of the slot (blob: bias tile then weight tiles)
+  int col0, col0b; // first input feature (state-dict column) of each tile; -2 = view dir + bias columns
   int blob_off, blob_bytes;
 };
-struct StepTable { Step s[48]; int n; int total; };
+struct StepTable { Step s[64]; int n; int total; };
 
-__host__ __device__ constexpr StepTable make_table(bool bg) {
+__host__ __device__ constexpr StepTable make_table(bool bg, bool halves) {
   StepTable t{};
   int i = 0, off = 0;
   for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-    const short n = (m == 9) ? 128 : 256;
-    short bias = (m != 9);
-    auto push = [&](short src, short chunk, int col0) {
-      const int bytes = n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
-      t.s[i] = Step{(short)m, src, chunk, n, bias, col0, off, bytes};
-      off += bytes; ++i; bias = 0;
-    };
-    if (m == 0 || m == 5) for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 64 * c);
-    if (m == 9) push(SRC_E, 1, -2);      // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
-    if (m != 0) for (int c = 0; c < 4; ++c) push(SRC_A, (short)c, ((m == 5) ? emb_dim(bg) : 0) + 64 * c);
+    const short n = (m == 9 || halves) ? 128 : 256;
+    const int nh = (halves && m != 9) ? 2 : 1;
+    const int abase = (m == 5) ? emb_dim(bg) : 0;
+    for (int h = 0; h < nh; ++h) {
+      short bias = (m != 9);
+      auto push = [&](short src, short chunk, short ntiles, int col0, int col0b) {
+        const int bytes = ntiles * n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
+        t.s[i] = Step{(short)m, (short)h, src, chunk, ntiles, n, bias, col0, col0b, off, bytes};
+        off += bytes; ++i; bias = 0;
+      };
+      if (m == 0 || m == 5) {
+        if (halves) push(SRC_E, 0, (short)(bg ? 2 : 1), 0, 64);
+        else for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 1, 64 * c, 0);
+      }
+      if (m == 9) push(SRC_E, 1, 1, -2, 0);   // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
+      if (m != 0) {
+        if (halves) for (int p = 0; p < 2; ++p) push(SRC_A, (short)(2 * p), 2, abase + 128 * p, abase + 128 * p + 64);
+        else for (int c = 0; c < 4; ++c) push(SRC_A, (short)c, 1, abase + 64 * c, 0);
+      }
+    }
   }
   t.n = i;
   t.total = off;
   return t;
 }
 
-__constant__ StepTable c_tab[2] = {make_table(false), make_table(true)};
-static const StepTable h_tab[2] = {make_table(false), make_table(true)};
+// [halves][bg]
+__constant__ StepTable c_tab[2][2] = {{make_table(false, false), make_table(true, false)}, {make_table(false, true), make_table(true, true)}};
+static const StepTable h_tab[2][2] = {{make_table(false, false), make_table(true, false)}, {make_table(false, true), make_table(true, true)}};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,6 +174,26 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Lean forms for the issue loop: descriptors as (lo, hi) words -- only lo changes between MMAs -- and a
+// compile-time accumulate flag, so one MMA costs the issuing thread a couple of integer adds.
+constexpr uint32_t SW128_HI = 64u | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t NOSW_HI = (128u >> 4) | (1u << 14);             // SBO 128 B, version 1, no swizzle
+__device__ __forceinline__ uint32_t sw128_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t bias_lo(uint32_t saddr, uint32_t n) { return ((saddr >> 4) & 0x3FFFu) | (n << 16); }
+template <int ACC>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}" ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 db;\nsetp.ne.b32 p, %5, 0;\nmov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(SW128_HI), "r"(idesc), "n"(ACC)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -243,14 +281,14 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
-template <bool BG, int CLUSTER>
+template <bool BG, int CLUSTER, bool HALVES>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
                 float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
-  const StepTable& tab = c_tab[BG ? 1 : 0];
+  const StepTable& tab = c_tab[HALVES ? 1 : 0][BG ? 1 : 0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
@@ -269,7 +307,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(B_EFULL + i), NUM_EMB_WARPS); mbar_init(bar(B_EEMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACC + i), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == LOAD_WARP) {
@@ -302,6 +340,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
           // a stage without bias tile lands straight on the weight area of the slot
           const uint32_t dst = s_base + OFF_W + st * STAGE_BYTES + (tab.s[i].bias ? (uint32_t)(AUX_BYTES - tab.s[i].n * BIAS_ROW_BYTES) : (uint32_t)AUX_BYTES);
           mbar_wait(bar(B_WEMPTY + st), ph ^ 1);          // every CTA of the cluster has consumed this stage
+          if ((flags & 8) && it >= NSTAGE) { mbar_arrive(bar(B_WFULL + st)); continue; }   // timing experiment: no refill (wrong results)
           mbar_expect_tx(bar(B_WFULL + st), bytes);
           if (CLUSTER == 1) {
             bulk_g2s(dst, blobs + tab.s[i].blob_off, bytes, bar(B_WFULL + st));
@@ -314,104 +353,134 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer =================
+    // One thread; everything it executes between two MMAs is potential tensor-pipe idle time (a single warp
+    // cannot hide its own instruction latencies), so the ring position is kept as running registers and the
+    // descriptors as 32-bit words that advance by constants.
     if (lane == 0) {
-      uint32_t st = 0, ph = 0, a_par = 0, tile_i = 0;
-      long long t_e = 0, t_a = 0, t_w = 0, t_i = 0, t_c = 0, t0 = clock64(), tt = 0;
       constexpr uint32_t ID256 = idesc_f16(256), ID128 = idesc_f16(128);
       constexpr int E_CHUNKS = BG ? 2 : 1;
+      const uint32_t ring0 = s_base + OFF_W, wfull0 = bar(B_WFULL), wempty0 = bar(B_WEMPTY);
+      uint32_t st = 0, ph = 0, slot = ring0, wfull = wfull0, wempty = wempty0;   // ring position
+      uint32_t a_par = 0, tile_i = 0;
+      const long long t0 = clock64();
+      long long t_first = 0;
+      auto wait_stage = [&]() { mbar_wait(wfull, ph); tc_fence_after(); };
       auto commit_stage = [&]() {
-        if (CLUSTER == 1) tc_commit(bar(B_WEMPTY + st)); else tc_commit_mcast(bar(B_WEMPTY + st), kMask);
-        if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        if (CLUSTER == 1) tc_commit(wempty); else tc_commit_mcast(wempty, kMask);
+        ++st; slot += STAGE_BYTES; wfull += 8; wempty += 8;
+        if (st == NSTAGE) { st = 0; ph ^= 1; slot = ring0; wfull = wfull0; wempty = wempty0; }
       };
       for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
         const uint32_t eb = tile_i & 1;
         const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
-        const uint64_t one_desc = sw128_desc(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
-        if (timing) tt = clock64();
+        const uint32_t one_lo = sw128_lo(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
         mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
-        // overwrite: wait until those MMAs have completed (ACC[1] completes 5 times per tile; layer 9 is the 5th)
-        if (tile_i > 0) mbar_wait(bar(B_ACC + 1), (tile_i - 1) & 1);
-        if (timing) t_e += clock64() - tt;
+        // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
+        if (tile_i > 0) mbar_wait(bar(B_ACC + (HALVES ? 2 : 1)), (tile_i - 1) & 1);
+        if constexpr (HALVES) {
 #pragma unroll 1
-        for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
-          const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
-          const uint32_t idesc = (m == 9) ? ID128 : ID256;
-          uint32_t acc = 0u;
-          if (m == 0 || m == 5) {      // embedding chunks (+ the bias tile with the first)
+          for (int mh = 0; mh < 2 * NUM_MMA_LAYERS - 1; ++mh) {
+            const int m = mh >> 1, h = mh & 1;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u + 128u * (uint32_t)h;
+            const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
+            if (m == 0 || m == 5) {      // bias tile + embedding chunks, one stage
+              // (half 0 overwrites columns [0,128) of the buffer the previous layer's half 1 still reads A chunk 3 from,
+              //  columns [192,256): disjoint, so no ordering beyond issue order is needed)
+              wait_stage();
+              mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot + AUX_BYTES - 128 * BIAS_ROW_BYTES, 128), NOSW_HI, ID128);
 #pragma unroll
-            for (int c = 0; c < E_CHUNKS; ++c) {
-              const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
-              if (timing) tt = clock64();
-              mbar_wait(bar(B_WFULL + st), ph);
-              if (timing) t_w += clock64() - tt;
-              tc_fence_after();
-              if (c == 0) { umma_f16(d_tmem, one_desc, bias_desc(slot, 256), idesc, 0u); acc = 1u; }
-              const uint64_t ad = sw128_desc(e_addr + c * CHUNK_BYTES), bd = sw128_desc(slot + AUX_BYTES);
+              for (int c = 0; c < E_CHUNKS; ++c) {
+                const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES + c * CHUNK_BYTES);
 #pragma unroll
-              for (int k = 0; k < (c == 1 ? 2 : 4); ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, idesc, 1u);
+                for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, ID128);
+              }
               commit_stage();
             }
-          }
-          if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
-            const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
-            if (timing) tt = clock64();
-            mbar_wait(bar(B_WFULL + st), ph);
-            if (timing) t_w += clock64() - tt;
-            tc_fence_after();
-            const uint64_t ad = sw128_desc(e_addr + CHUNK_BYTES), bd = sw128_desc(slot + AUX_BYTES);
-            umma_f16(d_tmem, ad + 4u, bd + 4u, idesc, 0u);
-            umma_f16(d_tmem, ad + 6u, bd + 6u, idesc, 1u);
-            acc = 1u;
-            commit_stage();
-            tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
-          }
-          if (m != 0) {
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t slot = s_base + OFF_W + st * STAGE_BYTES;
-              const uint64_t bd = sw128_desc(slot + AUX_BYTES);
-              const uint32_t a0 = a_tmem + 64u * c;
-              long long ti0 = 0;
-              // (The bias MMA must not be hoisted above the AREADY wait: it overwrites the accumulator buffer the
-              //  previous layer's last MMAs still read their A operand from, and consecutive tcgen05.mma are not
-              //  interlocked on TMEM A-read vs D-write.)
-              if (timing) {
-                tt = clock64();
-                mbar_wait(bar(B_WFULL + st), ph);
-                long long t1 = clock64(); t_w += t1 - tt;
-                mbar_wait(bar(B_AREADY + c), a_par);
-                t_a += clock64() - t1;
-              } else {
-                mbar_wait2(bar(B_AREADY + c), a_par, bar(B_WFULL + st), ph);
-              }
-              tc_fence_after();
-              if (timing) ti0 = clock64();
-              if (acc == 0u) { umma_f16(d_tmem, one_desc, bias_desc(slot, 256), idesc, 0u); acc = 1u; }
-              if ((flags & 2) && m != 9) {   // experiment: every N=256 MMA as two N=128 halves
-                for (int hN = 0; hN < 2; ++hN) {
-                  umma_f16_ts(d_tmem + 128u * hN, a0, bd + 1024u * hN, ID128, 1u);
-                  umma_f16_ts(d_tmem + 128u * hN, a0 + 8u, bd + 1024u * hN + 2u, ID128, 1u);
-                  umma_f16_ts(d_tmem + 128u * hN, a0 + 32u, bd + 1024u * hN + 4u, ID128, 1u);
-                  umma_f16_ts(d_tmem + 128u * hN, a0 + 40u, bd + 1024u * hN + 6u, ID128, 1u);
+            if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
+              wait_stage();
+              const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+              mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, ID128);
+              mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, ID128);
+              commit_stage();
+              tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+            }
+            if (m != 0) {
+              const bool need_bias = (m != 5 && m != 9);
+              const bool wait_a = (h == 0 || m == 9);   // half 1 reads the A chunks half 0 already waited for
+#pragma unroll
+              for (int p = 0; p < 2; ++p) {
+                wait_stage();
+                if (p == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot + AUX_BYTES - 128 * BIAS_ROW_BYTES, 128), NOSW_HI, ID128);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                  const int c = 2 * p + cc;
+                  const uint32_t blo = sw128_lo(slot + AUX_BYTES + cc * CHUNK_BYTES);
+                  const uint32_t a0 = a_tmem + 64u * c;
+                  if (wait_a) { mbar_wait(bar(B_AREADY + c), a_par); tc_fence_after(); }
+                  mma_ts<1>(d_tmem, a0, blo, ID128);
+                  mma_ts<1>(d_tmem, a0 + 8u, blo + 2u, ID128);
+                  mma_ts<1>(d_tmem, a0 + 32u, blo + 4u, ID128);
+                  mma_ts<1>(d_tmem, a0 + 40u, blo + 6u, ID128);
                 }
-              } else {
-              umma_f16_ts(d_tmem, a0, bd, idesc, 1u);
-              umma_f16_ts(d_tmem, a0 + 8u, bd + 2u, idesc, 1u);
-              umma_f16_ts(d_tmem, a0 + 32u, bd + 4u, idesc, 1u);
-              umma_f16_ts(d_tmem, a0 + 40u, bd + 6u, idesc, 1u);
+                commit_stage();
               }
-              if (timing) { long long t1 = clock64(); t_i += t1 - ti0; ti0 = t1; }
-              commit_stage();
-              if (timing) t_c += clock64() - ti0;
+              if (h == 1 || m == 9) a_par ^= 1;
             }
-            a_par ^= 1;
+            tc_commit(bar(B_ACC + (m & 1) * 2 + h));
           }
-          tc_commit(bar(B_ACC + (m & 1)));
+        } else {
+#pragma unroll 1
+          for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
+            const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
+            const uint32_t idesc = (m == 9) ? ID128 : ID256;
+            if (m == 0 || m == 5) {      // embedding chunks (+ the bias tile with the first)
+#pragma unroll
+              for (int c = 0; c < E_CHUNKS; ++c) {
+                wait_stage();
+                if (c == 0) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+#pragma unroll
+                for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
+                commit_stage();
+              }
+            }
+            if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
+              wait_stage();
+              const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+              mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
+              mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
+              commit_stage();
+              tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+            }
+            if (m != 0) {
+              const bool need_bias = (m != 5 && m != 9);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t blo = sw128_lo(slot + AUX_BYTES);
+                const uint32_t a0 = a_tmem + 64u * c;
+                // (The bias MMA must not be hoisted above the AREADY wait: it overwrites the accumulator buffer the
+                //  previous layer's last MMAs still read their A operand from, and consecutive tcgen05.mma are not
+                //  interlocked on TMEM A-read vs D-write.)
+                mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
+                tc_fence_after();
+                if (timing && c == 0 && tile_i == 5 && m == 3) t_first = clock64();
+                if (c == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                mma_ts<1>(d_tmem, a0, blo, idesc);
+                mma_ts<1>(d_tmem, a0 + 8u, blo + 2u, idesc);
+                mma_ts<1>(d_tmem, a0 + 32u, blo + 4u, idesc);
+                mma_ts<1>(d_tmem, a0 + 40u, blo + 6u, idesc);
+                commit_stage();
+              }
+              a_par ^= 1;
+            }
+            tc_commit(bar(B_ACC + (m & 1)));
+            if (timing && tile_i == 5 && m == 2) dbg[14 * 148 + 16 * blockIdx.x + 0] = clock64();
+          }
         }
       }
-      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[8 * blockIdx.x + 1] = t_e; dbg[8 * blockIdx.x + 2] = t_a; dbg[8 * blockIdx.x + 3] = t_w; dbg[8 * 148 + 2 * blockIdx.x] = t_i; dbg[8 * 148 + 2 * blockIdx.x + 1] = t_c; }
+      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[14 * 148 + 16 * blockIdx.x + 4] = t_first; }
     }
   } else if (warp >= EMB_WARP0) {
     // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
@@ -465,22 +534,26 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       const long long g = (long long)tile * TILE + row;
       const bool valid = g < total;
       float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+      constexpr int UNITS = HALVES ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, half) accumulations per tile
 #pragma unroll 1
-      for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-        const int ab = m & 1;
+      for (int un = 0; un < UNITS; ++un) {
+        const int m = HALVES ? (un >> 1) : un, h = HALVES ? (un & 1) : 0;
+        const int ab = HALVES ? (m & 1) * 2 + h : (m & 1);
         if (timing) ett = clock64();
         mbar_wait(bar(B_ACC + ab), (acc_par >> ab) & 1u);
         if (timing) e_wait += clock64() - ett;
         acc_par ^= 1u << ab;
         tc_fence_after();
-        const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
-        const int nchunk = (m == 9) ? 2 : 4;
+        const bool probe = timing && threadIdx.x == 0 && !HALVES && m == 2 && grp == group0 + 5 * group_step;
+        if (probe) dbg[14 * 148 + 16 * blockIdx.x + 1] = clock64();
+        const uint32_t acc_addr = lane_addr + (uint32_t)((m & 1) * 256 + 32 * hh);
+        const int j0 = 2 * h, nchunk = (HALVES || m == 9) ? j0 + 2 : 4;     // 64-column chunks [j0, nchunk) of the layer output
         uint32_t v[2][32];
-        tmem_ld32(acc_addr, v[0]);
+        tmem_ld32(acc_addr + 64u * j0, v[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j < nchunk) {
-            uint32_t (&cur)[32] = v[j & 1];
+          if (j >= j0 && j < nchunk) {
+            uint32_t (&cur)[32] = v[j & 1];   // j0 is even: chunk j0 sits in v[0]
             if (timing) ett = clock64();
             tmem_ld_wait(cur);
             if (timing) { long long t1 = clock64(); e_ld += t1 - ett; ett = t1; }
@@ -526,6 +599,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(B_AREADY + j));
               if (timing) { long long t1 = clock64(); e_arr += t1 - ett; ett = t1; }
+              if (probe) dbg[14 * 148 + 16 * blockIdx.x + 8 + j] = clock64();
             }
           }
         }
@@ -560,20 +634,21 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
 }
 
 // ---- packer: state-dict tensors -> fp16 tiles in MMA issue order + fp32 tail ------------------------
-__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__ out, int blob_total) {
-  const StepTable& tab = c_tab[bg ? 1 : 0];
+__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, bool halves, uint8_t* __restrict__ out, int blob_total) {
+  const StepTable& tab = c_tab[halves ? 1 : 0][bg ? 1 : 0];
   const int i = blockIdx.y;
   if (i < tab.n) {
     const Step s = tab.s[i];
     const int pl = param_layer(s.layer), nin = layer_in(pl, bg);
     const float* Wl = p.w[pl];
     const float* Bl = p.b[pl];
+    const int row0 = 128 * s.half;
     const int bias_bytes = s.bias ? s.n * BIAS_ROW_BYTES : 0;
     if (s.bias) {
       __half* bt = reinterpret_cast<__half*>(out + s.blob_off);
       for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 16; idx += gridDim.x * blockDim.x) {
         const int nn = idx >> 4, kk = idx & 15;
-        const float b = Bl[nn];
+        const float b = Bl[row0 + nn];
         const __half hi = __float2half_rn(b);
         __half v = __float2half_rn(0.f);
         if (kk == ONE_COL - 112) v = hi;
@@ -581,27 +656,32 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
         bt[bias_tile_off(s.n, nn, kk) / 2] = v;
       }
     }
-    __half* blob = reinterpret_cast<__half*>(out + s.blob_off + bias_bytes);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 64; idx += gridDim.x * blockDim.x) {
-      const int nn = idx >> 6, kk = idx & 63;
-      float v = 0.f;
-      if (s.src == SRC_E) {
-        if (s.col0 == -2) {           // rgb.0: view part + bias columns
-          const int c = 64 + kk;
-          if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)nn * nin + W + (c - VIEW_COL)];
-          else if (c == ONE_COL || c == ONE_COL + 1) {
-            const float b = Bl[nn];
-            const float hi = __half2float(__float2half_rn(b));
-            v = (c == ONE_COL) ? hi : b - hi;
+    for (int u = 0; u < s.ntiles; ++u) {
+      __half* blob = reinterpret_cast<__half*>(out + s.blob_off + bias_bytes + u * s.n * 128);
+      const int col0 = u ? s.col0b : s.col0;
+      const int chunk = s.chunk + u;
+      for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 64; idx += gridDim.x * blockDim.x) {
+        const int nn = idx >> 6, kk = idx & 63;
+        const int orow = row0 + nn;
+        float v = 0.f;
+        if (s.src == SRC_E) {
+          if (col0 == -2) {           // rgb.0: view part + bias columns
+            const int c = 64 * chunk + kk;
+            if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)orow * nin + W + (c - VIEW_COL)];
+            else if (c == ONE_COL || c == ONE_COL + 1) {
+              const float b = Bl[orow];
+              const float hi = __half2float(__float2half_rn(b));
+              v = (c == ONE_COL) ? hi : b - hi;
+            }
+          } else {
+            const int c = col0 + kk;
+            if (c < emb_dim(bg)) v = Wl[(size_t)orow * nin + c];                                  // embedding part
           }
         } else {
-          const int c = s.col0 + kk;
-          if (c < emb_dim(bg)) v = Wl[(size_t)nn * nin + c];                                  // embedding part
+          v = Wl[(size_t)orow * nin + col0 + kk];
         }
-      } else {
-        v = Wl[(size_t)nn * nin + s.col0 + kk];
+        blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
       }
-      blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
     }
   } else {
     float* tail = reinterpret_cast<float*>(out + blob_total);
@@ -621,23 +701,38 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
 
 using namespace npp;
 
-size_t npp_tc_packed_bytes(bool bg) { return (size_t)tc::h_tab[bg].total + tc::T_TOTAL * sizeof(float); }
+static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1 or 2)
+static int g_halves = -1;       // schedule (see StepTable); NERFPP_TC_HALVES overrides.  Fixed for the life of the process:
+                                // the packed-weight layout depends on it.
+static long long* g_dbg = nullptr;
+static int g_flags = 0;          // experiment switches (diagnostics only)
+
+static void tc_config() {
+  if (g_halves >= 0) return;
+  const char* e = getenv("NERFPP_TC_HALVES");
+  g_halves = e ? (atoi(e) != 0) : 1;
+  if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
+  if (g_cluster < 0) {
+    const char* c = getenv("NERFPP_TC_CLUSTER");
+    g_cluster = c ? atoi(c) : 1;
+  }
+  if (g_cluster != 1 && g_cluster != 2) g_cluster = 1;
+}
+
+size_t npp_tc_packed_bytes(bool bg) { tc_config(); return (size_t)tc::h_tab[g_halves][bg].total + tc::T_TOTAL * sizeof(float); }
 
 int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
-  const tc::StepTable& t = tc::h_tab[bg];
-  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, (uint8_t*)out, t.total);
+  tc_config();
+  const tc::StepTable& t = tc::h_tab[g_halves][bg];
+  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, g_halves != 0, (uint8_t*)out, t.total);
   NPP_CHECK_LAUNCH();
   return 0;
 }
 
-static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1, 2 or 4)
-static long long* g_dbg = nullptr;
-static int g_flags = 0;          // experiment switches (diagnostics only)
-
-template <bool BG, int CLUSTER>
+template <bool BG, int CLUSTER, bool HALVES>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER>;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER, HALVES>;
   static bool configured = false;
   static int max_clusters = 0;
   if (!configured) {
@@ -663,9 +758,9 @@ static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, cons
   return 0;
 }
 
-// debug hooks (tests/diag only): device buffer of 8 x gridDim.x int64 receiving per-role cycle counters
+// debug hooks (tests/diag only): device buffer receiving per-role cycle counters; cluster size override
 extern "C" void nerfpp_debug_set_tc_timers(long long* dev_buf) { g_dbg = dev_buf; }
-extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = c; }
+extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = (c == 2) ? 2 : 1; }
 extern "C" void nerfpp_debug_set_tc_flags(int f) { g_flags = f; }
 
 int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
@@ -676,18 +771,15 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (g_cluster < 0) {
-    if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
-    const char* e = getenv("NERFPP_TC_CLUSTER");
-    g_cluster = e ? atoi(e) : 1;
-    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 1;
-  }
+  tc_config();
   const long long total = (long long)n * S;
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;
-  const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
-#define NPP_TC_LAUNCH(BG, C) launch_tc<BG, C>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, st)
-  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1) : g_cluster == 2 ? NPP_TC_LAUNCH(true, 2) : NPP_TC_LAUNCH(true, 4);
-  return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1) : g_cluster == 2 ? NPP_TC_LAUNCH(false, 2) : NPP_TC_LAUNCH(false, 4);
+  const float* tail = (const float*)(blobs + tc::h_tab[g_halves][bg].total);
+#define NPP_TC_LAUNCH(BG, C, H) launch_tc<BG, C, H>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, st)
+#define NPP_TC_LAUNCH_H(BG, C) (g_halves ? NPP_TC_LAUNCH(BG, C, true) : NPP_TC_LAUNCH(BG, C, false))
+  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH_H(true, 1) : NPP_TC_LAUNCH_H(true, 2);
+  return g_cluster == 1 ? NPP_TC_LAUNCH_H(false, 1) : NPP_TC_LAUNCH_H(false, 2);
+#undef NPP_TC_LAUNCH_H
 #undef NPP_TC_LAUNCH
 }
