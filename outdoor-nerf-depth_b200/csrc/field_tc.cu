@@ -58,60 +58,43 @@ constexpr int T_TOTAL = T_BRGB2 + 3;
 
 __host__ __device__ constexpr int param_layer(int m) { return m < 8 ? m : m == 8 ? L_REMAP : L_RGB0; }
 
-// One ring stage = one or two weight tiles (64 input columns each) of one layer (+ the bias tile ahead of the
-// first stage of a layer / half).  The loader and the packer walk this table; the MMA issuer hard-codes the order.
-//
-// Two schedules (template parameter HALVES of the kernel):
-//   HALVES = 0  every layer is one N=256 accumulation: stages of one [256 x 64] tile.
-//   HALVES = 1  every 256-wide layer is issued as two N=128 halves (output rows [0,128) then [128,256) of the
-//               weight), stages of two [128 x 64] tiles: the epilogue of half 0 runs under the MMAs of half 1
-//               and the next layer's first K-chunks are ready before the tensor pipe needs them.
+// One ring stage = one [N x 64] weight tile of one layer (+ the layer's bias tile ahead of its first stage).
+// The loader and the packer walk this table; the MMA issuer hard-codes the same order.
 enum { SRC_E = 0, SRC_A = 1 };
 struct Step {
-  short layer, half;   // MMA layer 0..9; output half (weight rows [128 half, +n))
+  short layer;     // MMA layer 0..9
   short src;       // SRC_*
-  short chunk;     // first 64-column chunk within the E / A region
-  short ntiles;    // 1 or 2 consecutive chunks
-  short n;         // rows per tile = MMA N (256 or 128)
-  short bias;      // 1: [n x 16] bias tile at the head of the slot (blob: bias tile then weight tiles)
-  int col0, col0b; // first input feature (state-dict column) of each tile; -2 = view dir + bias columns
+  short chunk;     // 64-column chunk within the E / A region
+  short n;         // rows of the tile = outputs of the layer (256 or 128)
+  short bias;      // 1: [n x 16] bias tile at the head of the slot (blob: bias tile then weight tile)
+  int col0;        // first input feature (state-dict column) of the tile; -2 = view dir + bias columns
   int blob_off, blob_bytes;
 };
-struct StepTable { Step s[64]; int n; int total; };
+struct StepTable { Step s[48]; int n; int total; };
 
-__host__ __device__ constexpr StepTable make_table(bool bg, bool halves) {
+__host__ __device__ constexpr StepTable make_table(bool bg) {
   StepTable t{};
   int i = 0, off = 0;
   for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-    const short n = (m == 9 || halves) ? 128 : 256;
-    const int nh = (halves && m != 9) ? 2 : 1;
+    const short n = (m == 9) ? 128 : 256;
     const int abase = (m == 5) ? emb_dim(bg) : 0;
-    for (int h = 0; h < nh; ++h) {
-      short bias = (m != 9);
-      auto push = [&](short src, short chunk, short ntiles, int col0, int col0b) {
-        const int bytes = ntiles * n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
-        t.s[i] = Step{(short)m, (short)h, src, chunk, ntiles, n, bias, col0, col0b, off, bytes};
-        off += bytes; ++i; bias = 0;
-      };
-      if (m == 0 || m == 5) {
-        if (halves) push(SRC_E, 0, (short)(bg ? 2 : 1), 0, 64);
-        else for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 1, 64 * c, 0);
-      }
-      if (m == 9) push(SRC_E, 1, 1, -2, 0);   // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
-      if (m != 0) {
-        if (halves) for (int p = 0; p < 2; ++p) push(SRC_A, (short)(2 * p), 2, abase + 128 * p, abase + 128 * p + 64);
-        else for (int c = 0; c < 4; ++c) push(SRC_A, (short)c, 1, abase + 64 * c, 0);
-      }
-    }
+    short bias = (m != 9);
+    auto push = [&](short src, short chunk, int col0) {
+      const int bytes = n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
+      t.s[i] = Step{(short)m, src, chunk, n, bias, col0, off, bytes};
+      off += bytes; ++i; bias = 0;
+    };
+    if (m == 0 || m == 5) for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 64 * c);
+    if (m == 9) push(SRC_E, 1, -2);   // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
+    if (m != 0) for (int c = 0; c < 4; ++c) push(SRC_A, (short)c, abase + 64 * c);
   }
   t.n = i;
   t.total = off;
   return t;
 }
 
-// [halves][bg]
-__constant__ StepTable c_tab[2][2] = {{make_table(false, false), make_table(true, false)}, {make_table(false, true), make_table(true, true)}};
-static const StepTable h_tab[2][2] = {{make_table(false, false), make_table(true, false)}, {make_table(false, true), make_table(true, true)}};
+__constant__ StepTable c_tab[2] = {make_table(false), make_table(true)};
+static const StepTable h_tab[2] = {make_table(false), make_table(true)};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +158,14 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// true in exactly one lane of a converged warp.  tcgen05.mma / tcgen05.commit issued under it compile to bare
+// UTCHMMA / UTCBAR; under a plain `lane == 0` branch every one of them is wrapped in a per-lane serialisation loop
+// that nearly doubles the issuing thread's cost per MMA (tests/bench_umma.cu: 56 vs 33 cycles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
 }
 // Lean forms for the issue loop: descriptors as (lo, hi) words -- only lo changes between MMAs -- and a
 // compile-time accumulate flag, so one MMA costs the issuing thread a couple of integer adds.
@@ -281,14 +272,14 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
-template <bool BG, int CLUSTER, bool HALVES>
+template <bool BG, int CLUSTER, bool TAIL>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
                 float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
-  const StepTable& tab = c_tab[HALVES ? 1 : 0][BG ? 1 : 0];
+  const StepTable& tab = c_tab[BG ? 1 : 0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
@@ -353,22 +344,29 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer =================
-    // One thread; everything it executes between two MMAs is potential tensor-pipe idle time (a single warp
-    // cannot hide its own instruction latencies), so the ring position is kept as running registers and the
-    // descriptors as 32-bit words that advance by constants.
-    if (lane == 0) {
-      constexpr uint32_t ID256 = idesc_f16(256), ID128 = idesc_f16(128);
+    // The whole warp runs the control flow (waits, ring bookkeeping) converged; one elected lane issues.  Whatever
+    // this warp executes between two MMAs is potential tensor-pipe idle time (a single warp cannot hide its own
+    // instruction latencies), so the ring position is kept as running registers and descriptors as 32-bit words
+    // that advance by constants.
+    {
+      // (flags & 64: timing experiment -- N=16 MMAs leave the tensor pipe idle, exposing the issue thread's own pace)
+      const uint32_t ID256 = (flags & 64) ? idesc_f16(16) : idesc_f16(256), ID128 = (flags & 64) ? idesc_f16(16) : idesc_f16(128);
       constexpr int E_CHUNKS = BG ? 2 : 1;
       const uint32_t ring0 = s_base + OFF_W, wfull0 = bar(B_WFULL), wempty0 = bar(B_WEMPTY);
       uint32_t st = 0, ph = 0, slot = ring0, wfull = wfull0, wempty = wempty0;   // ring position
       uint32_t a_par = 0, tile_i = 0;
       const long long t0 = clock64();
-      long long t_first = 0;
       auto wait_stage = [&]() { mbar_wait(wfull, ph); tc_fence_after(); };
-      auto commit_stage = [&]() {
-        if (CLUSTER == 1) tc_commit(wempty); else tc_commit_mcast(wempty, kMask);
+      auto release = [&](uint32_t wempty_bar) { if (CLUSTER == 1) tc_commit(wempty_bar); else tc_commit_mcast(wempty_bar, kMask); };
+      auto advance = [&]() {
         ++st; slot += STAGE_BYTES; wfull += 8; wempty += 8;
         if (st == NSTAGE) { st = 0; ph ^= 1; slot = ring0; wfull = wfull0; wempty = wempty0; }
+      };
+      auto ts4 = [&](uint32_t d, uint32_t a0, uint32_t blo, uint32_t idesc) {   // one 64-column A chunk from TMEM
+        mma_ts<1>(d, a0, blo, idesc);
+        mma_ts<1>(d, a0 + 8u, blo + 2u, idesc);
+        mma_ts<1>(d, a0 + 32u, blo + 4u, idesc);
+        mma_ts<1>(d, a0 + 40u, blo + 6u, idesc);
       };
       for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
         const uint32_t eb = tile_i & 1;
@@ -377,57 +375,130 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
         // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
-        if (tile_i > 0) mbar_wait(bar(B_ACC + (HALVES ? 2 : 1)), (tile_i - 1) & 1);
-        if constexpr (HALVES) {
+        if (tile_i > 0) mbar_wait(bar(B_ACC + (TAIL ? 2 : 1)), (tile_i - 1) & 1);
+        tc_fence_after();
+        if constexpr (TAIL) {
+          // Tail-split schedule.  An N=128 MMA runs at the same rate per FLOP as an N=256 one (64 vs 128 cycles,
+          // tests/bench_umma.cu), so any part of a layer can be issued as two column halves at no tensor-pipe cost:
+          //   [bias|c0](cols 0-127) [bias|c0](cols 128-255) c1 [c2,c3](cols 0-127) -> ACC_h0 ... [c2,c3](cols 128-255) -> ACC_h1
+          // Columns 0-127 of the layer output are complete 8 MMAs (512 cycles) before the layer ends, so the epilogue's
+          // latency chain for the next layer's first K-chunks runs under MMAs instead of under an idle pipe; and the
+          // next layer begins with column-half MMAs whose accumulator writes (cols 0-127) cannot collide with the
+          // A-operand reads of this layer's tail (chunks 2,3 = cols 128-255 of the same TMEM buffer).
 #pragma unroll 1
-          for (int mh = 0; mh < 2 * NUM_MMA_LAYERS - 1; ++mh) {
-            const int m = mh >> 1, h = mh & 1;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u + 128u * (uint32_t)h;
+          for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
             const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
-            if (m == 0 || m == 5) {      // bias tile + embedding chunks, one stage
-              // (half 0 overwrites columns [0,128) of the buffer the previous layer's half 1 still reads A chunk 3 from,
-              //  columns [192,256): disjoint, so no ordering beyond issue order is needed)
+            // before this layer first writes cols 128-255 of its buffer: the previous layer's second half (which read
+            // its A chunks 2,3 from exactly those columns) must have completed
+            auto wait_prev_h1 = [&]() {
+              if (m == 0) return;
+              const int l = m - 1, k = l >> 1;
+              if (l & 1) mbar_wait(bar(B_ACC + 3), (uint32_t)k & 1u); else mbar_wait(bar(B_ACC + 1), (tile_i + (uint32_t)k) & 1u);
+              tc_fence_after();
+            };
+            if (m == 9) {                // rgb.0, N=128: view/bias columns of E, then the 4 A chunks
               wait_stage();
-              mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot + AUX_BYTES - 128 * BIAS_ROW_BYTES, 128), NOSW_HI, ID128);
-#pragma unroll
-              for (int c = 0; c < E_CHUNKS; ++c) {
-                const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES + c * CHUNK_BYTES);
-#pragma unroll
-                for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, ID128);
+              if (elect_one()) {
+                const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+                mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, ID128);
+                mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, ID128);
+                release(wempty);
+                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
               }
-              commit_stage();
-            }
-            if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
-              wait_stage();
-              const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
-              mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, ID128);
-              mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, ID128);
-              commit_stage();
-              tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
-            }
-            if (m != 0) {
-              const bool need_bias = (m != 5 && m != 9);
-              const bool wait_a = (h == 0 || m == 9);   // half 1 reads the A chunks half 0 already waited for
+              __syncwarp();
+              advance();
 #pragma unroll
-              for (int p = 0; p < 2; ++p) {
-                wait_stage();
-                if (p == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot + AUX_BYTES - 128 * BIAS_ROW_BYTES, 128), NOSW_HI, ID128);
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                  const int c = 2 * p + cc;
-                  const uint32_t blo = sw128_lo(slot + AUX_BYTES + cc * CHUNK_BYTES);
-                  const uint32_t a0 = a_tmem + 64u * c;
-                  if (wait_a) { mbar_wait(bar(B_AREADY + c), a_par); tc_fence_after(); }
-                  mma_ts<1>(d_tmem, a0, blo, ID128);
-                  mma_ts<1>(d_tmem, a0 + 8u, blo + 2u, ID128);
-                  mma_ts<1>(d_tmem, a0 + 32u, blo + 4u, ID128);
-                  mma_ts<1>(d_tmem, a0 + 40u, blo + 6u, ID128);
+              for (int c = 0; c < 4; ++c) {
+                mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                  ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), ID128);
+                  release(wempty);
+                  if (c == 3) tc_commit(bar(B_ACC + 2));
                 }
-                commit_stage();
+                __syncwarp();
+                advance();
               }
-              if (h == 1 || m == 9) a_par ^= 1;
+              a_par ^= 1;
+              continue;
             }
-            tc_commit(bar(B_ACC + (m & 1) * 2 + h));
+            if (m == 0 || m == 5) {      // bias + embedding chunks, both column halves (independent of the epilogue)
+              wait_stage();
+              const uint32_t slot0 = slot, wempty_e0 = wempty;
+              if (E_CHUNKS == 2) { advance(); wait_stage(); }   // second E tile = next stage; both stay live
+              const uint32_t slot1 = slot;
+#pragma unroll
+              for (int hN = 0; hN < 2; ++hN) {
+                if (hN == 1) wait_prev_h1();
+                if (elect_one()) {
+                  const uint32_t d = d_tmem + 128u * hN;
+                  mma_ss<0>(d, one_lo, SW128_HI, bias_lo(slot0, 256) + 128u * hN, NOSW_HI, ID128);
+#pragma unroll
+                  for (int c = 0; c < E_CHUNKS; ++c) {
+                    const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo((c ? slot1 : slot0) + AUX_BYTES) + 1024u * hN;
+#pragma unroll
+                    for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, ID128);
+                  }
+                  if (m == 0) tc_commit(bar(B_ACC + hN));
+                  if (hN == 1) { if (E_CHUNKS == 2) release(wempty_e0); release(wempty); }
+                }
+                __syncwarp();
+              }
+              advance();
+              if (m == 0) continue;
+            }
+            // ---- A chunks: c0 as column halves (m != 5: with the bias), c1 whole, c2/c3 as column halves ----
+            mbar_wait2(bar(B_AREADY + 0), a_par, wfull, ph);
+            tc_fence_after();
+            if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * blockIdx.x + 4] = clock64();
+            if (elect_one()) {
+              const uint32_t blo = sw128_lo(slot + AUX_BYTES);
+              if (m != 5) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, ID128);
+              ts4(d_tmem, a_tmem, blo, ID128);
+            }
+            __syncwarp();
+            if (m != 5) wait_prev_h1();
+            if (elect_one()) {
+              const uint32_t blo = sw128_lo(slot + AUX_BYTES) + 1024u;
+              if (m != 5) mma_ss<0>(d_tmem + 128u, one_lo, SW128_HI, bias_lo(slot, 256) + 128u, NOSW_HI, ID128);
+              ts4(d_tmem + 128u, a_tmem, blo, ID128);
+              release(wempty);
+            }
+            __syncwarp();
+            advance();
+            mbar_wait2(bar(B_AREADY + 1), a_par, wfull, ph);
+            tc_fence_after();
+            if (elect_one()) {
+              ts4(d_tmem, a_tmem + 64u, sw128_lo(slot + AUX_BYTES), ID256);
+              release(wempty);
+            }
+            __syncwarp();
+            advance();
+            {
+              // stages of c2 and c3 are both live until the second column half has been issued
+              const uint32_t slot2 = slot, wempty2 = wempty;
+              mbar_wait2(bar(B_AREADY + 2), a_par, wfull, ph);
+              advance();
+              mbar_wait2(bar(B_AREADY + 3), a_par, wfull, ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b2 = sw128_lo(slot2 + AUX_BYTES), b3 = sw128_lo(slot + AUX_BYTES);
+                const uint32_t a2 = a_tmem + 128u, a3 = a_tmem + 192u;
+                ts4(d_tmem, a2, b2, ID128);
+                ts4(d_tmem, a3, b3, ID128);
+                tc_commit(bar(B_ACC + (m & 1) * 2));
+                ts4(d_tmem + 128u, a2, b2 + 1024u, ID128);
+                release(wempty2);
+                ts4(d_tmem + 128u, a3, b3 + 1024u, ID128);
+                release(wempty);
+                tc_commit(bar(B_ACC + (m & 1) * 2 + 1));
+              }
+              __syncwarp();
+              advance();
+              if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * blockIdx.x + (m == 2 ? 0 : 12)] = clock64();
+            }
+            a_par ^= 1;
           }
         } else {
 #pragma unroll 1
@@ -439,48 +510,56 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
 #pragma unroll
               for (int c = 0; c < E_CHUNKS; ++c) {
                 wait_stage();
-                if (c == 0) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
-                const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+                if (elect_one()) {
+                  if (c == 0) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                  const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
 #pragma unroll
-                for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
-                commit_stage();
+                  for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
+                  release(wempty);
+                  if (m == 0 && c == E_CHUNKS - 1) tc_commit(bar(B_ACC));
+                }
+                __syncwarp();
+                advance();
               }
             }
             if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
               wait_stage();
-              const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
-              mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
-              mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
-              commit_stage();
-              tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+              if (elect_one()) {
+                const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+                mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
+                mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
+                release(wempty);
+                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+              }
+              __syncwarp();
+              advance();
             }
             if (m != 0) {
               const bool need_bias = (m != 5 && m != 9);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const uint32_t blo = sw128_lo(slot + AUX_BYTES);
-                const uint32_t a0 = a_tmem + 64u * c;
                 // (The bias MMA must not be hoisted above the AREADY wait: it overwrites the accumulator buffer the
                 //  previous layer's last MMAs still read their A operand from, and consecutive tcgen05.mma are not
                 //  interlocked on TMEM A-read vs D-write.)
                 mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
                 tc_fence_after();
-                if (timing && c == 0 && tile_i == 5 && m == 3) t_first = clock64();
-                if (c == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
-                mma_ts<1>(d_tmem, a0, blo, idesc);
-                mma_ts<1>(d_tmem, a0 + 8u, blo + 2u, idesc);
-                mma_ts<1>(d_tmem, a0 + 32u, blo + 4u, idesc);
-                mma_ts<1>(d_tmem, a0 + 40u, blo + 6u, idesc);
-                commit_stage();
+                if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * blockIdx.x + 4 + c] = clock64();
+                if (elect_one()) {
+                  if (c == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                  ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), idesc);
+                  release(wempty);
+                  if (c == 3) tc_commit(bar(B_ACC + (m & 1)));
+                }
+                __syncwarp();
+                advance();
               }
               a_par ^= 1;
             }
-            tc_commit(bar(B_ACC + (m & 1)));
-            if (timing && tile_i == 5 && m == 2) dbg[14 * 148 + 16 * blockIdx.x + 0] = clock64();
+            if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * blockIdx.x + (m == 2 ? 0 : 12)] = clock64();
           }
         }
       }
-      if (timing) { dbg[8 * blockIdx.x] = clock64() - t0; dbg[14 * 148 + 16 * blockIdx.x + 4] = t_first; }
+      if (timing && lane == 0) dbg[8 * blockIdx.x] = clock64() - t0;
     }
   } else if (warp >= EMB_WARP0) {
     // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
@@ -534,20 +613,20 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       const long long g = (long long)tile * TILE + row;
       const bool valid = g < total;
       float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
-      constexpr int UNITS = HALVES ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, half) accumulations per tile
+      constexpr int UNITS = TAIL ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, half) accumulations per tile
 #pragma unroll 1
       for (int un = 0; un < UNITS; ++un) {
-        const int m = HALVES ? (un >> 1) : un, h = HALVES ? (un & 1) : 0;
-        const int ab = HALVES ? (m & 1) * 2 + h : (m & 1);
+        const int m = TAIL ? (un >> 1) : un, h = TAIL ? (un & 1) : 0;
+        const int ab = TAIL ? (m & 1) * 2 + h : (m & 1);
         if (timing) ett = clock64();
         mbar_wait(bar(B_ACC + ab), (acc_par >> ab) & 1u);
         if (timing) e_wait += clock64() - ett;
         acc_par ^= 1u << ab;
         tc_fence_after();
-        const bool probe = timing && threadIdx.x == 0 && !HALVES && m == 2 && grp == group0 + 5 * group_step;
+        const bool probe = timing && threadIdx.x == 0 && m == 2 && h == 0 && grp == group0 + 5 * group_step;
         if (probe) dbg[14 * 148 + 16 * blockIdx.x + 1] = clock64();
         const uint32_t acc_addr = lane_addr + (uint32_t)((m & 1) * 256 + 32 * hh);
-        const int j0 = 2 * h, nchunk = (HALVES || m == 9) ? j0 + 2 : 4;     // 64-column chunks [j0, nchunk) of the layer output
+        const int j0 = 2 * h, nchunk = (TAIL || m == 9) ? j0 + 2 : 4;     // 64-column chunks [j0, nchunk) of the layer output
         uint32_t v[2][32];
         tmem_ld32(acc_addr + 64u * j0, v[0]);
 #pragma unroll
@@ -634,21 +713,20 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
 }
 
 // ---- packer: state-dict tensors -> fp16 tiles in MMA issue order + fp32 tail ------------------------
-__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, bool halves, uint8_t* __restrict__ out, int blob_total) {
-  const StepTable& tab = c_tab[halves ? 1 : 0][bg ? 1 : 0];
+__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__ out, int blob_total) {
+  const StepTable& tab = c_tab[bg ? 1 : 0];
   const int i = blockIdx.y;
   if (i < tab.n) {
     const Step s = tab.s[i];
     const int pl = param_layer(s.layer), nin = layer_in(pl, bg);
     const float* Wl = p.w[pl];
     const float* Bl = p.b[pl];
-    const int row0 = 128 * s.half;
     const int bias_bytes = s.bias ? s.n * BIAS_ROW_BYTES : 0;
     if (s.bias) {
       __half* bt = reinterpret_cast<__half*>(out + s.blob_off);
       for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 16; idx += gridDim.x * blockDim.x) {
         const int nn = idx >> 4, kk = idx & 15;
-        const float b = Bl[row0 + nn];
+        const float b = Bl[nn];
         const __half hi = __float2half_rn(b);
         __half v = __float2half_rn(0.f);
         if (kk == ONE_COL - 112) v = hi;
@@ -656,32 +734,27 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, bool halves, uint8_t*
         bt[bias_tile_off(s.n, nn, kk) / 2] = v;
       }
     }
-    for (int u = 0; u < s.ntiles; ++u) {
-      __half* blob = reinterpret_cast<__half*>(out + s.blob_off + bias_bytes + u * s.n * 128);
-      const int col0 = u ? s.col0b : s.col0;
-      const int chunk = s.chunk + u;
-      for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 64; idx += gridDim.x * blockDim.x) {
-        const int nn = idx >> 6, kk = idx & 63;
-        const int orow = row0 + nn;
-        float v = 0.f;
-        if (s.src == SRC_E) {
-          if (col0 == -2) {           // rgb.0: view part + bias columns
-            const int c = 64 * chunk + kk;
-            if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)orow * nin + W + (c - VIEW_COL)];
-            else if (c == ONE_COL || c == ONE_COL + 1) {
-              const float b = Bl[orow];
-              const float hi = __half2float(__float2half_rn(b));
-              v = (c == ONE_COL) ? hi : b - hi;
-            }
-          } else {
-            const int c = col0 + kk;
-            if (c < emb_dim(bg)) v = Wl[(size_t)orow * nin + c];                                  // embedding part
+    __half* blob = reinterpret_cast<__half*>(out + s.blob_off + bias_bytes);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s.n * 64; idx += gridDim.x * blockDim.x) {
+      const int nn = idx >> 6, kk = idx & 63;
+      float v = 0.f;
+      if (s.src == SRC_E) {
+        if (s.col0 == -2) {           // rgb.0: view part + bias columns
+          const int c = 64 * s.chunk + kk;
+          if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)nn * nin + W + (c - VIEW_COL)];
+          else if (c == ONE_COL || c == ONE_COL + 1) {
+            const float b = Bl[nn];
+            const float hi = __half2float(__float2half_rn(b));
+            v = (c == ONE_COL) ? hi : b - hi;
           }
         } else {
-          v = Wl[(size_t)orow * nin + col0 + kk];
+          const int c = s.col0 + kk;
+          if (c < emb_dim(bg)) v = Wl[(size_t)nn * nin + c];                                  // embedding part
         }
-        blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
+      } else {
+        v = Wl[(size_t)nn * nin + s.col0 + kk];
       }
+      blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
     }
   } else {
     float* tail = reinterpret_cast<float*>(out + blob_total);
@@ -702,15 +775,14 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, bool halves, uint8_t*
 using namespace npp;
 
 static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1 or 2)
-static int g_halves = -1;       // schedule (see StepTable); NERFPP_TC_HALVES overrides.  Fixed for the life of the process:
-                                // the packed-weight layout depends on it.
+static int g_tail = -1;         // MMA schedule: 1 = tail-split (default), 0 = whole layers; NERFPP_TC_TAIL overrides
 static long long* g_dbg = nullptr;
 static int g_flags = 0;          // experiment switches (diagnostics only)
 
 static void tc_config() {
-  if (g_halves >= 0) return;
-  const char* e = getenv("NERFPP_TC_HALVES");
-  g_halves = e ? (atoi(e) != 0) : 1;
+  if (g_tail >= 0) return;
+  const char* e = getenv("NERFPP_TC_TAIL");
+  g_tail = e ? (atoi(e) != 0) : 1;
   if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
   if (g_cluster < 0) {
     const char* c = getenv("NERFPP_TC_CLUSTER");
@@ -719,20 +791,20 @@ static void tc_config() {
   if (g_cluster != 1 && g_cluster != 2) g_cluster = 1;
 }
 
-size_t npp_tc_packed_bytes(bool bg) { tc_config(); return (size_t)tc::h_tab[g_halves][bg].total + tc::T_TOTAL * sizeof(float); }
+size_t npp_tc_packed_bytes(bool bg) { tc_config(); return (size_t)tc::h_tab[bg].total + tc::T_TOTAL * sizeof(float); }
 
 int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
   tc_config();
-  const tc::StepTable& t = tc::h_tab[g_halves][bg];
-  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, g_halves != 0, (uint8_t*)out, t.total);
+  const tc::StepTable& t = tc::h_tab[bg];
+  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, (uint8_t*)out, t.total);
   NPP_CHECK_LAUNCH();
   return 0;
 }
 
-template <bool BG, int CLUSTER, bool HALVES>
+template <bool BG, int CLUSTER, bool TAIL>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER, HALVES>;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER, TAIL>;
   static bool configured = false;
   static int max_clusters = 0;
   if (!configured) {
@@ -775,9 +847,9 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
   const long long total = (long long)n * S;
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;
-  const float* tail = (const float*)(blobs + tc::h_tab[g_halves][bg].total);
+  const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
 #define NPP_TC_LAUNCH(BG, C, H) launch_tc<BG, C, H>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, st)
-#define NPP_TC_LAUNCH_H(BG, C) (g_halves ? NPP_TC_LAUNCH(BG, C, true) : NPP_TC_LAUNCH(BG, C, false))
+#define NPP_TC_LAUNCH_H(BG, C) (g_tail ? NPP_TC_LAUNCH(BG, C, true) : NPP_TC_LAUNCH(BG, C, false))
   if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH_H(true, 1) : NPP_TC_LAUNCH_H(true, 2);
   return g_cluster == 1 ? NPP_TC_LAUNCH_H(false, 1) : NPP_TC_LAUNCH_H(false, 2);
 #undef NPP_TC_LAUNCH_H

@@ -17,6 +17,54 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a, uint64_t b, uint
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// issue pace of the thread itself (N=16 MMAs leave the pipe idle): VAR 0 = one thread of a diverged warp,
+// VAR 1 = converged warp + elect.sync around each group of 4
+template <int VAR>
+__global__ void __launch_bounds__(128, 1) pace(int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t a_s = smem_u32(smem), b_s = a_s + 16384;
+  const uint64_t ad = sw128_desc(a_s), bd = sw128_desc(b_s);
+  const uint32_t id = idesc_f16(16);
+  if (VAR == 0 ? (threadIdx.x == 32) : (warp == 1)) {
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (VAR == 0 || elect_one()) {
+        umma_ts(tmem, tmem + 256, bd, id, 1u);
+        umma_ts(tmem, tmem + 264, bd + 2, id, 1u);
+        umma_ts(tmem, tmem + 288, bd + 4, id, 1u);
+        umma_ts(tmem, tmem + 296, bd + 6, id, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+      if (VAR == 1) __syncwarp();
+    }
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) { out[2 * blockIdx.x] = t1 - t0; out[2 * blockIdx.x + 1] = t1 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 // mode: 0 = SS N=256, 1 = TS N=256, 2 = SS N=128, 3 = TS N=128, 4 = SS N=256 with a commit + mbarrier wait every 4 MMAs
 template <int mode>
 __global__ void __launch_bounds__(128, 1) bench(int iters, long long* out) {
@@ -93,14 +141,16 @@ void launch(int mode, int grid, int iters, long long* out) {
     case 2: launch1<2>(grid, iters, out); break; case 3: launch1<3>(grid, iters, out); break;
     case 4: launch1<4>(grid, iters, out); break; case 5: launch1<5>(grid, iters, out); break;
     case 6: launch1<6>(grid, iters, out); break; case 7: launch1<7>(grid, iters, out); break;
+    case 8: cudaFuncSetAttribute(pace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152); pace<0><<<grid, 128, 49152>>>(iters, out); break;
+    case 9: cudaFuncSetAttribute(pace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152); pace<1><<<grid, 128, 49152>>>(iters, out); break;
   }
 }
 int main() {
   long long* out;
   cudaMalloc(&out, 2 * 148 * sizeof(long long));
-  const char* names[] = {"SS N=256", "TS N=256", "SS N=128", "TS N=128", "SS N=256 commit+wait/4", "SS N=256 commit/4", "SS N=256 commit/16", "SS N=256 wait/4"};
+  const char* names[] = {"SS N=256", "TS N=256", "SS N=128", "TS N=128", "SS N=256 commit+wait/4", "SS N=256 commit/4", "SS N=256 commit/16", "SS N=256 wait/4", "pace: diverged thread, N=16 + commit/4", "pace: elect.sync, N=16 + commit/4"};
   for (int grid : {148}) {
-    for (int mode = 0; mode < 8; ++mode) {
+    for (int mode = 0; mode < 10; ++mode) {
       const int iters = 2000;
       launch(mode, grid, iters, out);
       cudaError_t e = cudaDeviceSynchronize();
