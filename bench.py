@@ -33,6 +33,9 @@ LAMBDA_DEPTH = 0.1          # scripts/train.sh:5
 DEPTH_SIGMA, DEPTH_SCALE = 0.01, 0.05
 MACS_FG, MACS_BG = 593408, 604160      # per sample, SURVEY.md section 8(d)
 METRIC = "rays/sec (4096 rays x 128 samples, 8x256 MLP)"
+# dram__bytes_read.sum + dram__bytes_write.sum of field_tc_kernel, mean of the step's four launches, from the
+# `ncu --set full` capture summarised in profiles/r1b_field_tc_ncu.txt (weights + ray inputs; the outputs stay in L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 3.56e6
 WORKLOAD = ("NeRF++ configs[1]: 4096 rays/GPU, cascade 64 -> +128 (192 fine) fg and bg, depth_loss=mse lambda=0.1, "
             "forward of both levels + sampling + composite + losses")
 
@@ -241,7 +244,7 @@ def field_roofline(models, batch, dev, reps=10):
                 n_launch += 1
     achieved = flops / (tot_ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "field_tc_kernel" if impl == 0 else "field_simt_kernel", "achieved": achieved, "peak": burst,
-            "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
+            "unit": "TFLOP/s", "frac": achieved / burst, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
             "launches_per_step": n_launch, "avg_launch_ms": tot_ms / n_launch, "algorithmic_flops_per_step": flops}
 
 
@@ -254,7 +257,7 @@ def reference_step(levels, rays, O):
             O.level_loss(ret, rays["rgb"], rays["depth_sup"], fg_z, far, True, "mse", LAMBDA_DEPTH, DEPTH_SIGMA * DEPTH_SCALE)
 
 
-def cpu_baseline(sample=1024):
+def cpu_baseline(sample=4096, reps=4):
     import nerfpp_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -262,11 +265,12 @@ def cpu_baseline(sample=1024):
     reference_step(levels, make_rays(64, 5), O)     # warm-up
     rays = make_rays(sample, 6)
     t0 = time.perf_counter()
-    reference_step(levels, rays, O)
+    for _ in range(reps):
+        reference_step(levels, rays, O)
     dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d rays of the same workload (oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference, "
-                      "all host threads), %.1f s" % (sample, dt)}
+    return {"value": reps * sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d x %d rays of the same workload (oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference, "
+                      "all host threads), %.1f s" % (reps, sample, dt)}
 
 
 def run_reference(args):

@@ -775,14 +775,14 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
 using namespace npp;
 
 static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1 or 2)
-static int g_tail = -1;         // MMA schedule: 1 = tail-split (default), 0 = whole layers; NERFPP_TC_TAIL overrides
+static int g_tail = -1;         // MMA schedule: 0 = whole layers (default, faster as measured), 1 = tail-split; NERFPP_TC_TAIL overrides
 static long long* g_dbg = nullptr;
 static int g_flags = 0;          // experiment switches (diagnostics only)
 
 static void tc_config() {
   if (g_tail >= 0) return;
   const char* e = getenv("NERFPP_TC_TAIL");
-  g_tail = e ? (atoi(e) != 0) : 1;
+  g_tail = e ? (atoi(e) != 0) : 0;
   if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
   if (g_cluster < 0) {
     const char* c = getenv("NERFPP_TC_CLUSTER");

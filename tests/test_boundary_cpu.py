@@ -125,3 +125,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "nerfpp_oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+
+
+def test_launcher_patches_trainer_functions():
+    """launch_ddp_train_nerf.patch_trainer_module rebinds the three functions the reference defines inside its
+    trainer file (ddp_train_nerf.py:51-130) -- checked on a stub module, the real trainer's deps are not in this image."""
+    import types
+    import launch_ddp_train_nerf as LN
+    from nerfpp_b200 import ops
+    stub = types.ModuleType("ddp_train_nerf")
+    stub.intersect_sphere = stub.perturb_samples = stub.sample_pdf = lambda *a, **k: None
+    LN.patch_trainer_module(stub)
+    assert stub.intersect_sphere is ops.intersect_sphere
+    assert stub.perturb_samples is ops.perturb_samples
+    assert stub.sample_pdf is ops.sample_pdf
