@@ -176,6 +176,36 @@ int nerfpp_depth_loss_backward(const float* depth, const float* depth_sup, const
                                const float* fwd_out, const float* grad_out, float* out_grad,
                                void* stream);
 
+/* ---- A16: mipnerf360 twins (config 3; nerf-methods/mipnerf360/internal/) ------------------------ */
+/* stepfun.sample_intervals (stepfun.py:214-263) with use_gpu_resampling=False: softmax(w_logits) ->
+ * integrate_weights -> sorted_interp(u) -> interval fenceposts (midpoints, reflected + clamped ends).
+ * t [n, M+1] sorted bin edges, w_logits [n, M], u [n, Ns] inverse-CDF ordinates with row stride u_ld
+ * (0 = one shared row: the rng=None deterministic centres); out_t [n, Ns+1].  The reference draws the
+ * jitter with jax.random; the caller supplies u.  M, Ns <= 256. */
+int mip360_sample_intervals(const float* t, const float* w_logits, const float* u, int u_ld, int n_rays,
+                            int n_bins, int n_samples, float domain_min, float domain_max, float* out_t,
+                            void* stream);
+/* render.compute_alpha_weights (render.py:130-151): density [n,S], tdist [n,S+1], dirs [n,3] ->
+ * weights, alpha, trans [n,S] (alpha / trans may be NULL). */
+int mip360_compute_alpha_weights(const float* density, const float* tdist, const float* dirs, int n_rays,
+                                 int n_samples, int opaque_background, float* out_weights, float* out_alpha,
+                                 float* out_trans, void* stream);
+/* render.volumetric_rendering (render.py:154-216), compute_extras=True, extras=None.  rgbs [n,S,3],
+ * weights [n,S], tdist [n,S+1], bg_rgbs [3] (bg_ld 0) or [n,3] (bg_ld 3), t_far [n].
+ * out_rgb [n,3]; out_scalars [n,6] = acc, distance_mean, depth (the fork's addition, :199-201),
+ * distance_percentile_5, distance_median, distance_percentile_95.  S <= 256. */
+int mip360_volumetric_rendering(const float* rgbs, const float* weights, const float* tdist,
+                                const float* bg_rgbs, int bg_ld, const float* t_far, int n_rays, int n_samples,
+                                float* out_rgb, float* out_scalars, void* stream);
+/* Depth-prior losses of the mipnerf360 trainer (train_utils.py:108-129): NERFPP_DEPTH_KL =
+ * depth_loss.depth_loss(..., 'kl') (depth_loss.py:66-97 -> ds_nerf_depth_loss :5-26: 1e-7, /(2*sigma), mean over
+ * rays x samples with invalid rays zeroed but counted); NERFPP_DEPTH_MSE / _L1 on predicted_depth =
+ * rendering['distance_mean'] with the mask multiplied in and the mean over all rays.  out_loss[1] (device). */
+int64_t mip360_depth_loss_workspace_bytes(int n_rays);
+int mip360_depth_loss(const float* weights, const float* tdist, const float* termination_depth,
+                      const float* predicted_depth, const float* dirs, int n_rays, int n_samples,
+                      int depth_loss_type, float sigma, float* out_loss, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

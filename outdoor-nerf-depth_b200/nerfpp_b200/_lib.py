@@ -56,6 +56,11 @@ SIGNATURES = {
     "nerfpp_loss": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "nerfpp_depth_loss": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     "nerfpp_depth_loss_backward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P]),
+    "mip360_sample_intervals": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, P, P]),
+    "mip360_compute_alpha_weights": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "mip360_volumetric_rendering": (c_int, [P, P, P, P, c_int, P, c_int, c_int, P, P, P]),
+    "mip360_depth_loss_workspace_bytes": (c_int64, [c_int]),
+    "mip360_depth_loss": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
 }
 OPTIONAL = {
     "nerfpp_backward_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
