@@ -56,3 +56,87 @@ def render_rays(models, ray_batch, cascade_samples=(64, 128), train=False, depth
                                          ret["fg_dists"], fg_far, depth_sigma * scale))
         res["losses"] = losses
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# A15: render_single_image (ddp_train_nerf.py:133-249)
+# ------------------------------------------------------------------------------------------------
+# every tensor key of NerfNet.forward's dict except the two weight arrays (:210-211), in dict order
+RENDER_KEYS = ("rgb", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth", "bg_lambda", "depth")
+_KEY_WIDTH = dict(rgb=3, fg_rgb=3, bg_rgb=3, fg_depth=1, bg_depth=1, bg_lambda=1, depth=1)   # fg_dists: the level's sample count
+
+
+def band_sizes(n_rays, world_size):
+    """ddp_train_nerf.py:137-143: contiguous row-major bands, pixel count must divide by the world size."""
+    if (n_rays // world_size) * world_size != n_rays:
+        raise Exception("Number of pixels in the image is not divisible by the number of GPUs!\n\t# pixels: {}\n\t# GPUs: {}"
+                        .format(n_rays, world_size))
+    sizes = [n_rays // world_size] * world_size
+    sizes[-1] = n_rays - sum(sizes[:-1])
+    return sizes
+
+
+def _level_widths(models):
+    """Packed channel layout of one ray: for every cascade level the RENDER_KEYS side by side."""
+    layout, off = [], 0
+    samples, tot = models["cascade_samples"], 0
+    for m in range(models["cascade_level"]):
+        tot += samples[m]                      # level m evaluates the union of all depths so far (:457)
+        cols = OrderedDict()
+        for k in RENDER_KEYS:
+            w = tot if k == "fg_dists" else _KEY_WIDTH[k]
+            cols[k] = (off, w)
+            off += w
+        layout.append(cols)
+    return layout, off
+
+
+def _render_chunk_cuda(models, chunk):
+    nets = [models["net_%d" % m] for m in range(models["cascade_level"])]
+    with torch.no_grad():
+        out, _ = cascade_forward(nets, chunk["ray_o"], chunk["ray_d"], chunk["min_depth"], tuple(models["cascade_samples"]),
+                                 train=False)
+    return [ret for ret, _, _ in out]
+
+
+def render_single_image(rank, world_size, models, ray_sampler, chunk_size, render_chunk=None, device=None):
+    """Drop-in for ddp_train_nerf.render_single_image (:133-249): same arguments, same return -- on rank 0 a list
+    (one entry per cascade level) of OrderedDicts of CPU tensors reshaped to (H, W, -1).squeeze(), None elsewhere.
+
+    What changed underneath: each rank renders its band chunk by chunk straight into ONE packed device buffer
+    [rays_of_rank, channels_of_all_levels] (no per-chunk device->host copies, no empty_cache()), and the ranks are
+    merged by ONE all-gather of that buffer (NCCL over NVLink when the process group is NCCL) instead of one CPU
+    gloo gather per key per level (:229-243).  ``render_chunk(models, chunk_dict) -> [ret per level]`` is the
+    per-chunk renderer (default: the CUDA cascade); tests inject a stub to exercise the sharding logic on CPU."""
+    import torch.distributed as dist
+    ray_batch = ray_sampler.get_all()
+    n = ray_batch["ray_d"].shape[0]
+    sizes = band_sizes(n, world_size)
+    if device is None:
+        device = torch.device("cuda", rank) if torch.cuda.is_available() else torch.device("cpu")
+    render_chunk = render_chunk or _render_chunk_cuda
+    local = {k: torch.split(v, sizes)[rank].to(device) for k, v in ray_batch.items() if torch.is_tensor(v)}
+    layout, channels = _level_widths(models)
+    n_local = sizes[rank]
+    packed = torch.empty(n_local, channels, device=device, dtype=torch.float32)
+    for s0 in range(0, n_local, chunk_size):
+        chunk = {k: v[s0:s0 + chunk_size] for k, v in local.items()}
+        rets = render_chunk(models, chunk)
+        for m, ret in enumerate(rets):
+            for k, (off, w) in layout[m].items():
+                packed[s0:s0 + chunk_size, off:off + w] = ret[k].reshape(-1, w)
+    if world_size > 1:
+        gathered = torch.empty(world_size * n_local, channels, device=device, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, packed)       # bands are equal-sized (divisibility check above)
+    else:
+        gathered = packed
+    if rank != 0:
+        return None
+    host = gathered.cpu()
+    out = []
+    for cols in layout:
+        d = OrderedDict()
+        for k, (off, w) in cols.items():
+            d[k] = host[:, off:off + w].reshape(ray_sampler.H, ray_sampler.W, -1).squeeze()
+        out.append(d)
+    return out

@@ -376,3 +376,33 @@ def test_depth2pts_outside_matches_oracle():
     pts, real = ddp_model.depth2pts_outside(o.to(dev()), dd.to(dev()), depth.to(dev()))
     assert torch.allclose(pts.cpu(), pts_ref, rtol=0, atol=2e-6)
     assert relerr(real.cpu().numpy(), real_ref.numpy()) <= 1e-5
+
+
+def test_render_single_image_matches_oracle():
+    """A15: the drop-in render_single_image (ddp_train_nerf.py:133-249) on one GPU vs the oracle's deterministic cascade."""
+    from collections import OrderedDict
+    from nerfpp_b200 import render_single_image
+    H, W = 6, 16
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    rays = O.synthetic_rays(H * W, seed=77)
+
+    class Sampler:
+        def __init__(self):
+            self.H, self.W = H, W
+
+        def get_all(self):
+            return OrderedDict(ray_o=rays["ray_o"], ray_d=rays["ray_d"], min_depth=rays["min_depth"], depth=None, rgb=None,
+                               mask=None, img_name="img.png")
+
+    models = {"cascade_level": 2, "cascade_samples": [64, 128], "net_0": nets[0], "net_1": nets[1]}
+    out = render_single_image(0, 1, models, Sampler(), chunk_size=40)
+    with torch.no_grad():
+        ref, _ = O.cascade_forward(levels, rays["ray_o"], rays["ray_d"], rays["min_depth"], (64, 128), None)
+    assert len(out) == 2
+    for m in range(2):
+        assert list(out[m].keys()) == ["rgb", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth", "bg_lambda", "depth"]
+        for k in ("rgb", "depth", "fg_rgb", "bg_lambda"):
+            want = ref[m][0][k].reshape(H, W, -1).squeeze()
+            assert out[m][k].shape == want.shape and not out[m][k].is_cuda
+            assert relerr(out[m][k].numpy(), want.numpy()) <= 1e-4, (m, k)
