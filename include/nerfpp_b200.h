@@ -140,6 +140,16 @@ int nerfpp_composite(const float* ray_d, const float* fg_z_max, const float* fg_
                      const float* bg_sigma, const float* bg_rgb, const float* bg_depth_real,
                      int n_rays, int s_fg, int s_bg, const NerfppRenderOut* out, void* stream);
 
+/* Backward of nerfpp_composite (autograd of ddp_model.py:95-134).  `grads` holds the upstream gradients on the ten
+ * outputs (const pointers in a NerfppRenderOut; NULL = zero; fg_dists carries none); `fwd` is the forward's output
+ * struct (bg_lambda is read).  Writes gradients on the per-sample sigma (after abs) [n,S] and rgb (after sigmoid)
+ * [n,S,3] of both nets, background in the forward's flipped order. */
+int nerfpp_composite_backward(const float* ray_d, const float* fg_z_max, const float* fg_z, const float* bg_z,
+                              const float* fg_sigma, const float* fg_rgb, const float* bg_sigma,
+                              const float* bg_rgb, const float* bg_depth_real, int n_rays, int s_fg, int s_bg,
+                              const NerfppRenderOut* fwd, const NerfppRenderOut* grads, float* d_fg_sigma,
+                              float* d_fg_rgb, float* d_bg_sigma, float* d_bg_rgb, void* stream);
+
 /* ---- A11: NerfNet.forward (ddp_model.py:74-147) in one call -------------------------------- */
 /* workspace: nerfpp_forward_workspace_bytes(n, s_fg, s_bg) bytes of device memory; holds the
  * per-sample sigma/rgb/depth_real (kept for backward). */

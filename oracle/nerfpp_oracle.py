@@ -221,6 +221,36 @@ def inverted_sphere_points(ray_o, ray_d, depth):
 # ----------------------------------------------------------------------------------------------
 # A9-A11 composite
 # ----------------------------------------------------------------------------------------------
+def composite(fg_sigma, fg_rgb_raw, bg_sigma, bg_rgb_raw, bg_depth_real_flipped, ray_d, fg_z_max, fg_z, bg_z):
+    """The "raw2outputs" inlined in ddp_model.py:95-105 (fg), :118-128 (bg, flipped sample order) and :131-134 (merge).
+    Per-sample inputs of the background are in the flipped order the reference evaluates them in."""
+    d_norm = torch.norm(ray_d, dim=-1, keepdim=True)
+    dz = fg_z[..., 1:] - fg_z[..., :-1]
+    fg_dists = d_norm * torch.cat((dz, fg_z_max[:, None] - fg_z[..., -1:]), -1)
+    alpha = 1.0 - torch.exp(-fg_sigma * fg_dists)
+    T = torch.cumprod(1.0 - alpha + TINY_NUMBER, dim=-1)
+    bg_lambda = T[..., -1]
+    T = torch.cat((torch.ones_like(T[..., :1]), T[..., :-1]), -1)
+    fg_weights = alpha * T
+    fg_rgb = (fg_weights[..., None] * fg_rgb_raw).sum(-2)
+    fg_depth = (fg_weights * fg_z).sum(-1)
+    zf = torch.flip(bg_z, dims=[-1])                                # :117  1 -> 0
+    bg_dists = torch.cat((zf[..., :-1] - zf[..., 1:],
+                          HUGE_NUMBER * torch.ones_like(zf[..., :1])), -1)   # :118-119
+    alpha_b = 1.0 - torch.exp(-bg_sigma * bg_dists)
+    Tb = torch.cumprod(1.0 - alpha_b + TINY_NUMBER, dim=-1)[..., :-1]
+    Tb = torch.cat((torch.ones_like(Tb[..., :1]), Tb), -1)
+    bg_weights = alpha_b * Tb
+    bg_rgb = (bg_weights[..., None] * bg_rgb_raw).sum(-2)
+    bg_depth = (bg_weights * bg_depth_real_flipped).sum(-1)
+    bg_rgb = bg_lambda[..., None] * bg_rgb                           # :131-134
+    bg_depth = bg_lambda * bg_depth
+    return OrderedDict([("rgb", fg_rgb + bg_rgb), ("fg_weights", fg_weights),
+                        ("bg_weights", bg_weights), ("fg_dists", fg_dists), ("fg_rgb", fg_rgb),
+                        ("fg_depth", fg_depth), ("bg_rgb", bg_rgb), ("bg_depth", bg_depth),
+                        ("bg_lambda", bg_lambda), ("depth", fg_depth + bg_depth)])
+
+
 def nerfpp_forward(params, ray_o, ray_d, fg_z_max, fg_z, bg_z, n_freq_pos=10, n_freq_view=4,
                    return_raw=False):
     """ddp_model.py:74-147 (NerfNet.forward).  Returns the 10-key OrderedDict in reference order."""
@@ -235,16 +265,6 @@ def nerfpp_forward(params, ray_o, ray_d, fg_z_max, fg_z, bg_z, n_freq_pos=10, n_
     v = viewdir[:, None, :].expand(N, S, 3)
     pts = o + fg_z[..., None] * d
     fg_rgb_raw, fg_sigma = mlp_field(params, "fg_net", posenc(pts, n_freq_pos), posenc(v, n_freq_view))
-    dz = fg_z[..., 1:] - fg_z[..., :-1]
-    fg_dists = d_norm * torch.cat((dz, fg_z_max[:, None] - fg_z[..., -1:]), -1)
-    alpha = 1.0 - torch.exp(-fg_sigma * fg_dists)
-    T = torch.cumprod(1.0 - alpha + TINY_NUMBER, dim=-1)
-    bg_lambda = T[..., -1]
-    T = torch.cat((torch.ones_like(T[..., :1]), T[..., :-1]), -1)
-    fg_weights = alpha * T
-    fg_rgb = (fg_weights[..., None] * fg_rgb_raw).sum(-2)
-    fg_depth = (fg_weights * fg_z).sum(-1)
-
     # background, ddp_model.py:107-128
     S = bg_z.shape[-1]
     o = ray_o[:, None, :].expand(N, S, 3)
@@ -253,24 +273,8 @@ def nerfpp_forward(params, ray_o, ray_d, fg_z_max, fg_z, bg_z, n_freq_pos=10, n_
     bg_pts, bg_depth_real = inverted_sphere_points(o, d, bg_z)
     pe = torch.flip(posenc(bg_pts, n_freq_pos), dims=[-2])          # :116
     ve = torch.flip(posenc(v, n_freq_view), dims=[-2])
-    zf = torch.flip(bg_z, dims=[-1])                                # :117  1 -> 0
-    bg_dists = torch.cat((zf[..., :-1] - zf[..., 1:],
-                          HUGE_NUMBER * torch.ones_like(zf[..., :1])), -1)   # :118-119
     bg_rgb_raw, bg_sigma = mlp_field(params, "bg_net", pe, ve)
-    alpha_b = 1.0 - torch.exp(-bg_sigma * bg_dists)
-    Tb = torch.cumprod(1.0 - alpha_b + TINY_NUMBER, dim=-1)[..., :-1]
-    Tb = torch.cat((torch.ones_like(Tb[..., :1]), Tb), -1)
-    bg_weights = alpha_b * Tb
-    bg_rgb = (bg_weights[..., None] * bg_rgb_raw).sum(-2)
-    bg_depth = (bg_weights * torch.flip(bg_depth_real, dims=[-1])).sum(-1)
-
-    # merge, ddp_model.py:131-134
-    bg_rgb = bg_lambda[..., None] * bg_rgb
-    bg_depth = bg_lambda * bg_depth
-    ret = OrderedDict([("rgb", fg_rgb + bg_rgb), ("fg_weights", fg_weights),
-                       ("bg_weights", bg_weights), ("fg_dists", fg_dists), ("fg_rgb", fg_rgb),
-                       ("fg_depth", fg_depth), ("bg_rgb", bg_rgb), ("bg_depth", bg_depth),
-                       ("bg_lambda", bg_lambda), ("depth", fg_depth + bg_depth)])
+    ret = composite(fg_sigma, fg_rgb_raw, bg_sigma, bg_rgb_raw, torch.flip(bg_depth_real, dims=[-1]), ray_d, fg_z_max, fg_z, bg_z)
     if return_raw:
         ret["_fg_sigma"], ret["_fg_rgb_raw"] = fg_sigma, fg_rgb_raw
         ret["_bg_sigma"], ret["_bg_rgb_raw"] = bg_sigma, bg_rgb_raw     # flipped order

@@ -50,6 +50,8 @@ SIGNATURES = {
     "nerfpp_field_forward": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P]),
     "nerfpp_depth2pts_outside": (c_int, [P, P, P, c_int64, P, P, P]),
     "nerfpp_composite": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), P]),
+    "nerfpp_composite_backward": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), POINTER(RenderOut),
+                                          P, P, P, P, P]),
     "nerfpp_forward_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "nerfpp_forward": (c_int, [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), P, P]),
     "nerfpp_loss_workspace_bytes": (c_int64, []),

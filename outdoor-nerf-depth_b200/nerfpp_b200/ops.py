@@ -291,6 +291,35 @@ def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, imp
     return outs
 
 
+def composite_backward(ray_d, fg_z_max, fg_z, bg_z, fg_sigma, fg_rgb, bg_sigma, bg_rgb, bg_depth_real, bg_lambda, grads):
+    """Backward of the composite (autograd of ddp_model.py:95-134).  ``grads``: dict key -> upstream gradient for any of
+    the ten output keys (missing/None = zero).  Returns d_fg_sigma [n,S], d_fg_rgb [n,S,3], d_bg_sigma, d_bg_rgb
+    (background in the forward's flipped order)."""
+    d, zmax, fz, bz = _c(ray_d, "ray_d", 2), _c(fg_z_max, "fg_z_max", 1), _c(fg_z, "fg_z", 2), _c(bg_z, "bg_z", 2)
+    n, sf = fz.shape
+    sb = bz.shape[1]
+    ins = [_c(t, nm) for t, nm in ((fg_sigma, "fg_sigma"), (fg_rgb, "fg_rgb"), (bg_sigma, "bg_sigma"), (bg_rgb, "bg_rgb"),
+                                   (bg_depth_real, "bg_depth_real"))]
+    lam = _c(bg_lambda, "bg_lambda", 1)
+    fwd = _lib.RenderOut()
+    fwd.bg_lambda = lam.data_ptr()
+    gst = _lib.RenderOut()
+    keep = []
+    for k in RET_KEYS:
+        g = grads.get(k)
+        if g is not None and k != "fg_dists":
+            g = _c(g.float(), "grad_" + k)
+            keep.append(g)
+            setattr(gst, k, g.data_ptr())
+    outs = [torch.empty(n, sf, device=fz.device), torch.empty(n, sf, 3, device=fz.device),
+            torch.empty(n, sb, device=fz.device), torch.empty(n, sb, 3, device=fz.device)]
+    with torch.cuda.device(fz.device):
+        check(_lib.lib().nerfpp_composite_backward(_p(d), _p(zmax), _p(fz), _p(bz), *[_p(t) for t in ins], n, sf, sb,
+                                                   ctypes.byref(fwd), ctypes.byref(gst), *[_p(t) for t in outs], _stream()),
+              "composite_backward")
+    return tuple(outs)
+
+
 class _NerfppFunction(torch.autograd.Function):
     """Autograd node for NerfNet.forward: forward = nerfpp_forward, backward = nerfpp_backward."""
 
