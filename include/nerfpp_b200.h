@@ -116,6 +116,14 @@ int nerfpp_field_forward(const void* packed, int is_bg, int field_impl, const fl
                          const float* ray_d, const float* z, int n_rays, int n_samples,
                          float* out_sigma, float* out_rgb, float* out_depth_real, void* stream);
 
+/* Training-mode field evaluation (tensor-core path only): same outputs, and additionally saves what the backward
+ * needs into `train_workspace` (nerfpp_field_train_workspace_bytes(n_rays, n_samples) bytes, ~5.1 KB per sample):
+ * every layer's fp16 activations in the MMA operand layout, the encoded inputs, and sigma before the abs(). */
+int64_t nerfpp_field_train_workspace_bytes(int n_rays, int n_samples);
+int nerfpp_field_forward_train(const void* packed, int is_bg, const float* ray_o, const float* ray_d,
+                               const float* z, int n_rays, int n_samples, float* out_sigma, float* out_rgb,
+                               float* out_depth_real, void* train_workspace, void* stream);
+
 /* depth2pts_outside (ddp_model.py:16-45) as a standalone op: ray_o, ray_d [n,3] and depth [n]
  * already expanded per sample -> out_pts [n,4] = (x',y',z',1/r), out_depth_real [n]. */
 int nerfpp_depth2pts_outside(const float* ray_o, const float* ray_d, const float* depth, int64_t n,

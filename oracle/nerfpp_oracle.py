@@ -195,6 +195,27 @@ def mlp_field(params, net, pos_emb, view_emb, depth=8, skips=(4,)):
     return rgb, sigma
 
 
+def mlp_field_acts(params, net, pos_emb, view_emb, depth=8, skips=(4,)):
+    """mlp_field with its intermediates (for the backward tests): ([h0..h7, remap, rgb_hidden], raw_sigma, rgb)."""
+    def lin(name, x):
+        p = "nerf_net.%s.%s" % (net, name)
+        return torch.nn.functional.linear(x, params[p + ".weight"], params[p + ".bias"])
+
+    acts = []
+    h = torch.relu(lin("base_layers.0.0", pos_emb))
+    acts.append(h)
+    for i in range(depth - 1):
+        x = torch.cat((pos_emb, h), -1) if i in skips else h
+        h = torch.relu(lin("base_layers.%d.0" % (i + 1), x))
+        acts.append(h)
+    raw_sigma = lin("sigma_layers.0", h).squeeze(-1)
+    remap = lin("base_remap_layers.0", h)
+    acts.append(remap)
+    c = torch.relu(lin("rgb_layers.0", torch.cat((remap, view_emb), -1)))
+    acts.append(c)
+    return acts, raw_sigma, torch.sigmoid(lin("rgb_layers.2", c))
+
+
 def inverted_sphere_points(ray_o, ray_d, depth):
     """ddp_model.py:16-45 (depth2pts_outside).  ray_o/ray_d [..., 3] (already expanded per sample),
     depth [...] in [0,1] = 1/r.  Returns pts [...,4] = (x', y', z', 1/r) and real depth [...]."""

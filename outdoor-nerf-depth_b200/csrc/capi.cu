@@ -11,7 +11,8 @@ int npp_field_simt(const void* packed, bool bg, const float* ray_o, const float*
 size_t npp_tc_packed_bytes(bool bg);
 int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
 int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
-                 float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st);
+                 float* out_sigma, float* out_rgb, float* out_depth_real, void* train_ws, cudaStream_t st);
+size_t npp_tc_train_ws_bytes(long long n_samples);
 
 static thread_local char g_err[512] = "";
 
@@ -49,8 +50,24 @@ extern "C" int nerfpp_field_forward(const void* packed, int is_bg, int field_imp
   if (field_impl == NERFPP_FIELD_SIMT)
     return npp_field_simt(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, (cudaStream_t)stream);
   if (field_impl == NERFPP_FIELD_TC)
-    return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, (cudaStream_t)stream);
+    return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, nullptr, (cudaStream_t)stream);
   NPP_CHECK_ARG(false, "unknown field_impl");
+}
+
+extern "C" int64_t nerfpp_field_train_workspace_bytes(int n_rays, int n_samples) {
+  if (n_rays < 0 || n_samples < 1) return -1;
+  return (int64_t)npp_tc_train_ws_bytes((long long)n_rays * n_samples);
+}
+
+extern "C" int nerfpp_field_forward_train(const void* packed, int is_bg, const float* ray_o, const float* ray_d, const float* z,
+                                          int n_rays, int n_samples, float* out_sigma, float* out_rgb, float* out_depth_real,
+                                          void* train_workspace, void* stream) {
+  NPP_CHECK_ARG(packed && ray_o && ray_d && z && out_sigma && out_rgb && train_workspace, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "bad shape");
+  NPP_CHECK_ARG(!is_bg || out_depth_real, "background needs out_depth_real");
+  if (n_rays == 0) return 0;
+  return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, train_workspace,
+                      (cudaStream_t)stream);
 }
 
 // workspace of nerfpp_forward: fg sigma [n,Sf], fg rgb [n,Sf,3], bg sigma [n,Sb], bg rgb [n,Sb,3], bg depth_real [n,Sb]

@@ -24,18 +24,15 @@
 // Shared memory (bytes): E 2x32K | ring 4x40K | barriers | scratch.  TMEM: 2 x 256 columns.
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
 // against the fp32 reference: rgb/depth within 3e-5 relative (tests/test_parity_gpu.py).
-#include <cuda_fp16.h>
 #include <cstdlib>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace npp {
 namespace tc {
 
-constexpr int TILE = 128;
 constexpr int NSTAGE = 4;
 constexpr int AUX_BYTES = 8192;             // head of a ring slot: the layer's bias tile (first stage of a layer only)
 constexpr int STAGE_BYTES = AUX_BYTES + 32768;   // + one [256 N x 64 K] SW128 weight tile
-constexpr int CHUNK_BYTES = 16384;          // 128 rows x 64 fp16
 constexpr int BIAS_ROW_BYTES = 32;          // bias tile: [N x 16 K] fp16, unswizzled 8x8 core matrices
 constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir, 123/124 = 1; double-buffered
 constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_SCRATCH = OFF_BAR + 512;
@@ -96,150 +93,12 @@ __host__ __device__ constexpr StepTable make_table(bool bg) {
 __constant__ StepTable c_tab[2] = {make_table(false), make_table(true)};
 static const StepTable h_tab[2] = {make_table(false), make_table(true)};
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
-}
-// waits on two barriers at once (their try_wait latencies overlap)
-__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
-  asm volatile(
-      "{\n.reg .pred p, q;\nWAIT2_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n"
-      "and.pred p, p, q;\n"
-      "@p bra WAIT2_DONE;\nbra WAIT2_LOOP;\nWAIT2_DONE:\n}" ::"r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// one L2 read delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
-__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T: A = fp16 pairs packed in 32-bit TMEM columns, row = lane
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// true in exactly one lane of a converged warp.  tcgen05.mma / tcgen05.commit issued under it compile to bare
-// UTCHMMA / UTCBAR; under a plain `lane == 0` branch every one of them is wrapped in a per-lane serialisation loop
-// that nearly doubles the issuing thread's cost per MMA (tests/bench_umma.cu: 56 vs 33 cycles).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
-  return pred != 0;
-}
-// Lean forms for the issue loop: descriptors as (lo, hi) words -- only lo changes between MMAs -- and a
-// compile-time accumulate flag, so one MMA costs the issuing thread a couple of integer adds.
-constexpr uint32_t SW128_HI = 64u | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SWIZZLE_128B
-constexpr uint32_t NOSW_HI = (128u >> 4) | (1u << 14);             // SBO 128 B, version 1, no swizzle
-__device__ __forceinline__ uint32_t sw128_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
-__device__ __forceinline__ uint32_t bias_lo(uint32_t saddr, uint32_t n) { return ((saddr >> 4) & 0x3FFFu) | (n << 16); }
-template <int ACC>
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
-  asm volatile(
-      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}" ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC)
-      : "memory");
-}
-template <int ACC>
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t idesc) {
-  asm volatile(
-      "{\n.reg .pred p;\n.reg .b64 db;\nsetp.ne.b32 p, %5, 0;\nmov.b64 db, {%2, %3};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(SW128_HI), "r"(idesc), "n"(ACC)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-// tcgen05.ld is asynchronous: its destination registers are only valid after wait::ld.  Binding them to the
-// wait as in/out operands keeps the compiler from reading or moving them across it.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-               :: "memory");
-}
-// two fp32 -> packed fp16x2 (lo in the low half), optionally through ReLU, one instruction
-template <bool RELU>
-__device__ __forceinline__ uint32_t pack_f16x2(uint32_t lo, uint32_t hi) {
-  uint32_t d;
-  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
-  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
-  return d;
-}
-
-// K-major, 128-byte-swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
-// (cute::UMMA::SmemDescriptor: start>>4 | LBO=1<<16 | SBO=64<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// K-major unswizzled [N x 16] tile: 8x8 core matrices of 128 B; N/8 along N (SBO = 128 B), 2 along K (LBO = 16 N B)
-__device__ __forceinline__ uint64_t bias_desc(uint32_t saddr, int n) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)n << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-}
-__host__ __device__ constexpr int bias_tile_off(int n_total, int n, int k) { return (k >> 3) * 16 * n_total + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128
-__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
-// byte offset of element (row r, column c) of a [128 x 64k] region made of 64-column SW128 chunks
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return (uint32_t)((c >> 6) * CHUNK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+// training: one thread's 32 fp16 activations (row `row`, K columns [32 hh, 32 hh + 32) of a chunk) into the chunk's
+// SWIZZLE_128B image in global memory: four 16-byte units, 64 contiguous bytes after the XOR
+__device__ __forceinline__ void store_act_chunk(uint8_t* chunk, int row, int hh, const uint32_t (&pk)[16]) {
+  uint4* rowp = reinterpret_cast<uint4*>(chunk + (row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) rowp[(4 * hh + u) ^ (row & 7)] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
 }
 
 // sin/cos of x * 2^k for the fp16 operand: two-constant Cody-Waite reduction to [-pi, pi] (exact to
@@ -276,7 +135,7 @@ template <bool BG, int CLUSTER, bool TAIL>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
-                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, long long* __restrict__ dbg, int flags) {
+                float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, TrainSave save, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
   const StepTable& tab = c_tab[BG ? 1 : 0];
@@ -373,6 +232,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
         const uint32_t one_lo = sw128_lo(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
         mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
+        if (save.e && lane == 0) bulk_s2g(save.e + (size_t)(grp * CLUSTER + (int)cta_rank) * E_BYTES, e_addr, E_BYTES);   // training: keep the E operand
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
         // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
         if (tile_i > 0) mbar_wait(bar(B_ACC + (TAIL ? 2 : 1)), (tile_i - 1) & 1);
@@ -398,13 +258,15 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               tc_fence_after();
             };
             if (m == 9) {                // rgb.0, N=128: view/bias columns of E, then the 4 A chunks
+              if (save.e && lane == 0) bulk_s2g_wait_read();
+              __syncwarp();
               wait_stage();
               if (elect_one()) {
                 const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
                 mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, ID128);
                 mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, ID128);
                 release(wempty);
-                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer (the bulk store below was waited for)
               }
               __syncwarp();
               advance();
@@ -523,13 +385,15 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
             }
             if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
+              if (save.e && lane == 0) bulk_s2g_wait_read();
+              __syncwarp();
               wait_stage();
               if (elect_one()) {
                 const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
                 mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
                 mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
                 release(wempty);
-                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer
+                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer (the bulk store below was waited for)
               }
               __syncwarp();
               advance();
@@ -648,6 +512,12 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
             }
             if (m == 9) {   // rgb.2 on the fp32 hidden colour features, nerf_network.py:114-117
+              if (save.act) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
+                store_act_chunk(save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
+              }
 #pragma unroll
               for (int t = 0; t < 32; ++t) cur[t] = __float_as_uint(fmaxf(__uint_as_float(cur[t]), 0.f));
 #pragma unroll
@@ -672,6 +542,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
               if (timing) { long long t1 = clock64(); e_cvt += t1 - ett; ett = t1; }
               tmem_st16(acc_addr + 64u * j, pk);
+              if (save.act) store_act_chunk(save.act + act_chunk_off(m, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
               tmem_st_wait();
               if (timing) { long long t1 = clock64(); e_st += t1 - ett; ett = t1; }
               tc_fence_before();
@@ -689,7 +560,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (hh == 0 && valid) {
         float4 p = scratch[row];
-        out_sigma[g] = fabsf(sig_part + p.x + tail[T_BSIG]);
+        const float raw_sigma = sig_part + p.x + tail[T_BSIG];
+        out_sigma[g] = fabsf(raw_sigma);
+        if (save.raw_sigma) save.raw_sigma[g] = raw_sigma;
         float c0 = rgb_part[0] + p.y + tail[T_BRGB2], c1 = rgb_part[1] + p.z + tail[T_BRGB2 + 1], c2 = rgb_part[2] + p.w + tail[T_BRGB2 + 2];
         out_rgb[3 * g] = 1.f / (1.f + expf(-c0));
         out_rgb[3 * g + 1] = 1.f / (1.f + expf(-c1));
@@ -803,7 +676,7 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
 
 template <bool BG, int CLUSTER, bool TAIL>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
-                     int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, cudaStream_t st) {
+                     int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, tc::TrainSave save, cudaStream_t st) {
   auto kern = tc::field_tc_kernel<BG, CLUSTER, TAIL>;
   static bool configured = false;
   static int max_clusters = 0;
@@ -825,7 +698,7 @@ static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, cons
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_dr, num_tiles, g_dbg, g_flags);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_dr, num_tiles, save, g_dbg, g_flags);
   if (e != cudaSuccess) { npp_set_error("field_tc launch (cluster %d): %s", CLUSTER, cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
@@ -835,8 +708,10 @@ extern "C" void nerfpp_debug_set_tc_timers(long long* dev_buf) { g_dbg = dev_buf
 extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = (c == 2) ? 2 : 1; }
 extern "C" void nerfpp_debug_set_tc_flags(int f) { g_flags = f; }
 
+size_t npp_tc_train_ws_bytes(long long n_samples) { return tc::train_ws_bytes((size_t)((n_samples + tc::TILE - 1) / tc::TILE)); }
+
 int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
-                 float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st) {
+                 float* out_sigma, float* out_rgb, float* out_depth_real, void* train_ws, cudaStream_t st) {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -848,7 +723,12 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;
   const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
-#define NPP_TC_LAUNCH(BG, C, H) launch_tc<BG, C, H>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, st)
+  tc::TrainSave save{nullptr, nullptr, nullptr};
+  if (train_ws) {
+    uint8_t* w = (uint8_t*)train_ws;
+    save.act = w; save.e = w + tc::train_ws_e_off((size_t)num_tiles); save.raw_sigma = (float*)(w + tc::train_ws_sigma_off((size_t)num_tiles));
+  }
+#define NPP_TC_LAUNCH(BG, C, H) launch_tc<BG, C, H>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
 #define NPP_TC_LAUNCH_H(BG, C) (g_tail ? NPP_TC_LAUNCH(BG, C, true) : NPP_TC_LAUNCH(BG, C, false))
   if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH_H(true, 1) : NPP_TC_LAUNCH_H(true, 2);
   return g_cluster == 1 ? NPP_TC_LAUNCH_H(false, 1) : NPP_TC_LAUNCH_H(false, 2);

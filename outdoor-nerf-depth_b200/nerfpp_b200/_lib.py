@@ -48,6 +48,8 @@ SIGNATURES = {
     "nerfpp_packed_bytes": (c_int64, [c_int, c_int]),
     "nerfpp_pack_weights": (c_int, [POINTER(NetParams), c_int, c_int, P, P]),
     "nerfpp_field_forward": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P]),
+    "nerfpp_field_train_workspace_bytes": (c_int64, [c_int, c_int]),
+    "nerfpp_field_forward_train": (c_int, [P, c_int, P, P, P, c_int, c_int, P, P, P, P, P]),
     "nerfpp_depth2pts_outside": (c_int, [P, P, P, c_int64, P, P, P]),
     "nerfpp_composite": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), P]),
     "nerfpp_composite_backward": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), POINTER(RenderOut),

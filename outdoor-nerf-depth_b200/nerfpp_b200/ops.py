@@ -260,6 +260,32 @@ def field_forward(packed, is_bg, ray_o, ray_d, z, impl=None):
     return sigma, rgb, dr
 
 
+def field_forward_train(packed, is_bg, ray_o, ray_d, z):
+    """Training-mode field evaluation (tensor-core path): returns (sigma, rgb, depth_real, train_workspace)."""
+    o, d, zz = _c(ray_o, "ray_o", 2), _c(ray_d, "ray_d", 2), _c(z, "z", 2)
+    n, S = zz.shape
+    L = _lib.lib()
+    sigma = torch.empty(n, S, device=zz.device, dtype=torch.float32)
+    rgb = torch.empty(n, S, 3, device=zz.device, dtype=torch.float32)
+    dr = torch.empty(n, S, device=zz.device, dtype=torch.float32) if is_bg else None
+    ws = torch.empty(int(L.nerfpp_field_train_workspace_bytes(n, S)), device=zz.device, dtype=torch.uint8)
+    with torch.cuda.device(zz.device):
+        check(L.nerfpp_field_forward_train(_p(packed), int(is_bg), _p(o), _p(d), _p(zz), n, S, _p(sigma), _p(rgb), _p(dr), _p(ws),
+                                           _stream()), "field_forward")
+    return sigma, rgb, dr, ws
+
+
+def unpack_chunks(buf, n_tiles, n_chunks):
+    """Decodes [n_tiles][n_chunks] SWIZZLE_128B operand chunks (uint8 tensor) into a [n_tiles*128, n_chunks*64] fp16 matrix
+    (diagnostics / tests: the layout is documented in csrc/tc_common.cuh)."""
+    x = buf.view(torch.float16).reshape(n_tiles, n_chunks, 16, 8, 8, 8)     # [tile, chunk, row>>3, row&7, unit, 8 halves]
+    r7 = torch.arange(8, device=buf.device)
+    src_unit = (torch.arange(8, device=buf.device)[None, :] ^ r7[:, None])  # logical unit u of row r lives at u ^ (r & 7)
+    idx = src_unit[None, None, None, :, :, None].expand(n_tiles, n_chunks, 16, 8, 8, 8)
+    y = torch.gather(x, 4, idx)
+    return y.reshape(n_tiles, n_chunks, 128, 64).permute(0, 2, 1, 3).reshape(n_tiles * 128, n_chunks * 64)
+
+
 def _alloc_outputs(n, sf, sb, device):
     shapes = dict(rgb=(n, 3), fg_weights=(n, sf), bg_weights=(n, sb), fg_dists=(n, sf), fg_rgb=(n, 3), fg_depth=(n,),
                   bg_rgb=(n, 3), bg_depth=(n,), bg_lambda=(n,), depth=(n,))
