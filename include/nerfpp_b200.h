@@ -167,6 +167,23 @@ int nerfpp_forward(const void* packed_fg, const void* packed_bg, int field_impl,
                    const float* fg_z, const float* bg_z, int n_rays, int s_fg, int s_bg,
                    const NerfppRenderOut* out, void* workspace, void* stream);
 
+/* ---- training: forward that keeps what the backward needs, and the backward (autograd of NerfNet.forward) ---- */
+/* nerfpp_forward_train = nerfpp_forward + a training workspace (1024-byte aligned,
+ * nerfpp_forward_train_workspace_bytes bytes, ~5.1 KB per sample) holding both nets' fp16 activations.
+ * nerfpp_backward: upstream gradients on the ten outputs (`grads`, NULL members = zero) -> gradients of the 2 x 24
+ * parameter tensors, ACCUMULATED into grads_fg / grads_bg (caller zero-fills).  Tensor-core path only: operands fp16
+ * under a power-of-two loss scale, accumulation fp32.  `workspace` / `train_workspace` are the forward's. */
+int64_t nerfpp_forward_train_workspace_bytes(int n_rays, int s_fg, int s_bg);
+int nerfpp_forward_train(const void* packed_fg, const void* packed_bg, const float* ray_o, const float* ray_d,
+                         const float* fg_z_max, const float* fg_z, const float* bg_z, int n_rays, int s_fg, int s_bg,
+                         const NerfppRenderOut* out, void* workspace, void* train_workspace, void* stream);
+int64_t nerfpp_backward_workspace_bytes(int n_rays, int s_fg, int s_bg);
+int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNetParams* params_bg, const float* ray_d,
+                    const float* fg_z_max, const float* fg_z, const float* bg_z, int n_rays, int s_fg, int s_bg,
+                    const NerfppRenderOut* out, const NerfppRenderOut* grads, const void* workspace,
+                    const void* train_workspace, const NerfppNetGrads* grads_fg, const NerfppNetGrads* grads_bg,
+                    void* bwd_workspace, void* stream);
+
 /* ---- A12-A14: losses (utils.py:12-16, depth_loss.py:4-44, ddp_train_nerf.py:481-493) ------- */
 enum { NERFPP_DEPTH_NONE = 0, NERFPP_DEPTH_MSE = 1, NERFPP_DEPTH_L1 = 2, NERFPP_DEPTH_KL = 3 };
 /* out_loss[4] (device) = { img2mse(rgb, rgb_gt), depth loss, rgb + lambda*depth, #valid rays }.

@@ -105,3 +105,28 @@ extern "C" int nerfpp_forward(const void* packed_fg, const void* packed_bg, int 
   return nerfpp_composite(ray_d, fg_z_max, fg_z, bg_z, w.fg_sigma, w.fg_rgb, w.bg_sigma, w.bg_rgb, w.bg_dr, n_rays, s_fg,
                           s_bg, out, stream);
 }
+
+// ---- training-mode NerfNet.forward: also fills the training workspace [fg net | bg net] the backward reads ----
+extern "C" int64_t nerfpp_forward_train_workspace_bytes(int n_rays, int s_fg, int s_bg) {
+  if (n_rays < 0 || s_fg < 1 || s_bg < 1) return -1;
+  const size_t fg = (npp_tc_train_ws_bytes((long long)n_rays * s_fg) + 1023) & ~(size_t)1023;
+  return (int64_t)(fg + npp_tc_train_ws_bytes((long long)n_rays * s_bg) + 1024);
+}
+
+extern "C" int nerfpp_forward_train(const void* packed_fg, const void* packed_bg, const float* ray_o, const float* ray_d,
+                                    const float* fg_z_max, const float* fg_z, const float* bg_z, int n_rays, int s_fg, int s_bg,
+                                    const NerfppRenderOut* out, void* workspace, void* train_workspace, void* stream) {
+  NPP_CHECK_ARG(packed_fg && packed_bg && workspace && train_workspace && out, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && s_fg >= 1 && s_bg >= 1, "bad shape");
+  NPP_CHECK_ARG(((uintptr_t)train_workspace & 1023) == 0, "train_workspace must be 1024-byte aligned");
+  if (n_rays == 0) return 0;
+  FwdWs w = carve(workspace, n_rays, s_fg, s_bg);
+  const size_t fg_bytes = (npp_tc_train_ws_bytes((long long)n_rays * s_fg) + 1023) & ~(size_t)1023;
+  int rc = nerfpp_field_forward_train(packed_fg, 0, ray_o, ray_d, fg_z, n_rays, s_fg, w.fg_sigma, w.fg_rgb, nullptr, train_workspace, stream);
+  if (rc) return rc;
+  rc = nerfpp_field_forward_train(packed_bg, 1, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr,
+                                  (char*)train_workspace + fg_bytes, stream);
+  if (rc) return rc;
+  return nerfpp_composite(ray_d, fg_z_max, fg_z, bg_z, w.fg_sigma, w.fg_rgb, w.bg_sigma, w.bg_rgb, w.bg_dr, n_rays, s_fg,
+                          s_bg, out, stream);
+}

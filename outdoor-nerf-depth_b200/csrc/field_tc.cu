@@ -93,14 +93,6 @@ __host__ __device__ constexpr StepTable make_table(bool bg) {
 __constant__ StepTable c_tab[2] = {make_table(false), make_table(true)};
 static const StepTable h_tab[2] = {make_table(false), make_table(true)};
 
-// training: one thread's 32 fp16 activations (row `row`, K columns [32 hh, 32 hh + 32) of a chunk) into the chunk's
-// SWIZZLE_128B image in global memory: four 16-byte units, 64 contiguous bytes after the XOR
-__device__ __forceinline__ void store_act_chunk(uint8_t* chunk, int row, int hh, const uint32_t (&pk)[16]) {
-  uint4* rowp = reinterpret_cast<uint4*>(chunk + (row >> 3) * 1024 + (row & 7) * 128);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) rowp[(4 * hh + u) ^ (row & 7)] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-}
-
 // sin/cos of x * 2^k for the fp16 operand: two-constant Cody-Waite reduction to [-pi, pi] (exact to
 // ~3e-7 for |arg| < 2^10), then the SFU approximations (abs error ~5e-7, far below the fp16 rounding
 // of the operand, 2.4e-4).

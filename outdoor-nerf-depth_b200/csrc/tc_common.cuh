@@ -144,6 +144,13 @@ __device__ __forceinline__ uint32_t pack_f16x2(uint32_t lo, uint32_t hi) {
   return d;
 }
 
+// same, saturating to +-65504 instead of overflowing to infinity (gradients under a loss scale)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+
 // K-major, 128-byte-swizzled operand tile: rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 | LBO=1<<16 | SBO=64<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
@@ -171,6 +178,14 @@ __host__ __device__ inline size_t act_layer_off(int layer, size_t n_tiles) { ret
 __host__ __device__ inline size_t act_bytes(size_t n_tiles) { return (9 * 4 + 2) * n_tiles * (size_t)CHUNK_BYTES; }
 __host__ __device__ inline size_t act_chunk_off(int layer, size_t n_tiles, size_t tile, int chunk) {
   return act_layer_off(layer, n_tiles) + (tile * (layer == 9 ? 2 : 4) + chunk) * (size_t)CHUNK_BYTES;
+}
+
+// training: one thread's 32 fp16 activations (row `row`, K columns [32 hh, 32 hh + 32) of a chunk) into the chunk's
+// SWIZZLE_128B image in global memory: four 16-byte units, 64 contiguous bytes after the XOR
+__device__ __forceinline__ void store_act_chunk(uint8_t* chunk, int row, int hh, const uint32_t (&pk)[16]) {
+  uint4* rowp = reinterpret_cast<uint4*>(chunk + (row >> 3) * 1024 + (row & 7) * 128);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) rowp[(4 * hh + u) ^ (row & 7)] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
 }
 
 // What a training-mode forward saves for the backward (all NULL = inference): the fp16 activations of every layer

@@ -1,0 +1,254 @@
+// Backward of the field MLP, weight-gradient half:  dW_l = dZ_l^T X_l  summed over all samples.
+//
+// wgrad_tc_kernel: tcgen05 split-K GEMMs.  M = output features of the layer (two halves of 128 = TMEM lanes),
+// N = input features (<= 256 TMEM columns per half), K = samples.  Both operands are the buffers the forward (ACT, E)
+// and the dgrad kernel (DZ) wrote in the operand-chunk layout: a [128 samples x 64 features] SWIZZLE_128B chunk read
+// MN-major IS the [features x samples] operand, so tiles go HBM -> shared memory with plain bulk copies and no
+// transposition anywhere.  Each CTA owns one (job, sample-range) pair, accumulates in fp32 in TMEM over its tiles and
+// adds its partial into the fp32 gradient with red.global.add (the caller zero-fills or accumulates).
+// This kernel is HBM-bound by construction (128 KB of operands per 2048 tensor-pipe cycles).
+//
+// wgrad_small_kernel: the column sums (bias gradients) and the two tiny heads (sigma 256->1, rgb.2 128->3) on CUDA cores.
+#include "tc_common.cuh"
+
+namespace npp {
+namespace tcw {
+using namespace npp::tc;
+
+constexpr int THREADS = 192;          // warps 0-3 epilogue, 4 MMA issuer, 5 loader
+constexpr int X_BYTES = 4 * CHUNK_BYTES, AH_BYTES = 2 * CHUNK_BYTES;
+constexpr int OFF_X = 0, OFF_A = 2 * X_BYTES, OFF_BAR = OFF_A + 2 * AH_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+enum { B_XFULL = 0, B_XEMPTY = 2, B_AFULL = 4, B_AEMPTY = 6, B_DONE = 8, B_COUNT = 9 };
+
+// One GEMM: dW[:, col0 : col0+ncols] (+)= DZ[a_layer]^T * X
+struct Job {
+  int a_layer;        // DZ layer (rows of dW)
+  int m_halves;       // 2 (256 outputs) or 1 (128)
+  int x_is_e;         // X from the E tiles (1) or from ACT[x_layer] (0)
+  int x_layer, x_chunk0, x_nchunks;
+  int skip;           // leading columns of the first X chunk that map to no weight column (view dir starts at E col 96 = chunk 1 col 32)
+  int ncols;          // weight columns written
+  int w_index;        // NerfppNetGrads.w index
+  int ld, col0;       // row stride (in-features of the layer) and first column in dW
+};
+struct JobTable { Job j[12]; int n; };
+__host__ __device__ constexpr JobTable make_jobs(bool bg) {
+  JobTable t{};
+  const int emb = emb_dim(bg), ech = bg ? 2 : 1;
+  int i = 0;
+  t.j[i++] = Job{0, 2, 1, 0, 0, ech, 0, emb, 0, emb, 0};                                  // base 0: embedding
+  for (int l = 1; l < 8; ++l) {
+    if (l == 5) t.j[i++] = Job{5, 2, 1, 0, 0, ech, 0, emb, 5, emb + W, 0};                // base 5: [embedding | h4]
+    t.j[i++] = Job{l, 2, 0, l - 1, 0, 4, 0, W, l, l == 5 ? emb + W : W, l == 5 ? emb : 0};
+  }
+  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0};                                  // base_remap
+  t.j[i++] = Job{9, 1, 0, 8, 0, 4, 0, W, L_RGB0, W + VIEW_DIM, 0};                        // rgb.0: remap part
+  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W};                // rgb.0: view-direction part
+  t.n = i;
+  return t;
+}
+__constant__ JobTable c_jobs[2] = {make_jobs(false), make_jobs(true)};
+static const JobTable h_jobs[2] = {make_jobs(false), make_jobs(true)};
+
+// MN-major SWIZZLE_128B operand: 64-feature blocks LBO = one chunk apart, 8-sample groups SBO = 1024 B apart
+constexpr uint32_t MN_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t mn_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((uint32_t)(CHUNK_BYTES >> 4) << 16); }
+__host__ __device__ constexpr uint32_t idesc_mn(int n) { return idesc_f16(n) | (1u << 15) | (1u << 16); }   // A and B MN-major
+
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restrict__ etiles, const uint8_t* __restrict__ dz,
+                const float* __restrict__ scale_ptr, int num_tiles, int splits, NerfppNetGrads grads) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  auto bar = [&](int i) { return s_base + OFF_BAR + 8u * i; };
+  if ((s_base & 1023u) != 0) __trap();
+  const Job jb = c_jobs[bg].j[blockIdx.x / splits];
+  const int split = blockIdx.x % splits;
+  const int t_begin = (int)((long long)num_tiles * split / splits), t_end = (int)((long long)num_tiles * (split + 1) / splits);
+  const int N = 64 * jb.x_nchunks;
+  const size_t nt = (size_t)num_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_XEMPTY + i), 1); mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
+    mbar_init(bar(B_DONE), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 5) {
+    // ================= loader: X tile, then the A halves, per sample tile =================
+    if (lane == 0) {
+      uint32_t ix = 0, ia = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const uint32_t xb = ix & 1;
+        mbar_wait(bar(B_XEMPTY + xb), ((ix >> 1) & 1) ^ 1);
+        const uint8_t* xsrc = jb.x_is_e ? etiles + ((size_t)tile * 2 + jb.x_chunk0) * CHUNK_BYTES
+                                        : act + act_chunk_off(jb.x_layer, nt, (size_t)tile, jb.x_chunk0);
+        mbar_expect_tx(bar(B_XFULL + xb), (uint32_t)(jb.x_nchunks * CHUNK_BYTES));
+        bulk_g2s(s_base + OFF_X + xb * X_BYTES, xsrc, (uint32_t)(jb.x_nchunks * CHUNK_BYTES), bar(B_XFULL + xb));
+        ++ix;
+        for (int h = 0; h < jb.m_halves; ++h, ++ia) {
+          const uint32_t ab = ia & 1;
+          mbar_wait(bar(B_AEMPTY + ab), ((ia >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(B_AFULL + ab), AH_BYTES);
+          bulk_g2s(s_base + OFF_A + ab * AH_BYTES, dz + act_chunk_off(jb.a_layer, nt, (size_t)tile, 2 * h), AH_BYTES, bar(B_AFULL + ab));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = idesc_mn(N);
+    uint32_t ix = 0, ia = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++ix) {
+      const uint32_t xb = ix & 1;
+      mbar_wait(bar(B_XFULL + xb), (ix >> 1) & 1);
+      for (int h = 0; h < jb.m_halves; ++h, ++ia) {
+        const uint32_t ab = ia & 1;
+        mbar_wait(bar(B_AFULL + ab), (ia >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t alo = mn_lo(s_base + OFF_A + ab * AH_BYTES), blo = mn_lo(s_base + OFF_X + xb * X_BYTES);
+          const uint32_t d = tmem_base + 256u * (uint32_t)h;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {        // 16 samples per MMA = two 8-sample groups = 2048 B
+            if (k == 0 && tile == t_begin) mma_ss<0>(d, alo, MN_HI, blo, MN_HI, idesc);
+            else mma_ss<1>(d, alo + 128u * k, MN_HI, blo + 128u * k, MN_HI, idesc);
+          }
+          tc_commit(bar(B_AEMPTY + ab));
+          if (h == jb.m_halves - 1) tc_commit(bar(B_XEMPTY + xb));
+          if (tile == t_end - 1 && h == jb.m_halves - 1) tc_commit(bar(B_DONE));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> red.global.add into dW =================
+    if (t_end > t_begin) {
+      mbar_wait(bar(B_DONE), 0);
+      tc_fence_after();
+      const float inv_scale = 1.f / *scale_ptr;
+      float* dW = grads.w[jb.w_index];
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int h = 0; h < jb.m_halves; ++h) {
+        const int orow = 128 * h + warp * 32 + lane;
+        float* wrow = dW + (size_t)orow * jb.ld + jb.col0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + 256u * (uint32_t)h + (uint32_t)c0, v);
+          tmem_ld_wait(v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = c0 + e - jb.skip;
+            if (col >= 0 && col < jb.ncols) atomicAdd(wrow + col, __uint_as_float(v[e]) * inv_scale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// element (row r, column c) of a chunked [tiles][nch][128][64] fp16 operand buffer
+__device__ __forceinline__ float chunk_elem(const uint8_t* layer_base, int nch, size_t tile, int r, int c) {
+  const uint8_t* ch = layer_base + (tile * nch + (c >> 6)) * (size_t)CHUNK_BYTES;
+  const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+  return __half2float(*reinterpret_cast<const __half*>(ch + off));
+}
+
+// blockIdx.y = what: 0..9 bias gradient of the layer whose pre-activation gradient is DZ[y] (column sums);
+//              10 = sigma head (dW = sum d_raw_sigma * h7, db = sum d_raw_sigma); 11 = rgb.2 (dW = d_raw_rgb^T g, db = sum d_raw_rgb)
+// blockIdx.x splits the tiles; one thread per column.
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ dz, const float* __restrict__ d_raw_sigma,
+                   const float* __restrict__ d_raw_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
+                   NerfppNetGrads grads) {
+  const int what = blockIdx.y, c = threadIdx.x;
+  const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
+  const float inv_scale = 1.f / *scale_ptr;
+  const size_t nt = (size_t)num_tiles;
+  __shared__ float s_d[TILE * 3];
+  if (what < 10) {
+    const int ncol = what == 9 ? RGB_HID : W, nch = what == 9 ? 2 : 4;
+    const uint8_t* base = dz + act_layer_off(what, nt);
+    float acc = 0.f;
+    if (c < ncol)
+      for (int tile = t_begin; tile < t_end; ++tile)
+        for (int r = 0; r < TILE; ++r) acc += chunk_elem(base, nch, (size_t)tile, r, c);
+    const int pl = what < 8 ? what : what == 8 ? L_REMAP : L_RGB0;
+    if (c < ncol) atomicAdd(grads.b[pl] + c, acc * inv_scale);
+  } else if (what == 10) {
+    const uint8_t* base = act + act_layer_off(7, nt);
+    float acc = 0.f, bacc = 0.f;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      __syncthreads();
+      if (c < TILE) { const long long g = (long long)tile * TILE + c; s_d[c] = g < total ? d_raw_sigma[g] : 0.f; }
+      __syncthreads();
+      for (int r = 0; r < TILE; ++r) acc = fmaf(s_d[r], chunk_elem(base, 4, (size_t)tile, r, c), acc);
+      if (c == 0) for (int r = 0; r < TILE; ++r) bacc += s_d[r];
+    }
+    atomicAdd(grads.w[L_SIGMA] + c, acc * inv_scale);
+    if (c == 0) atomicAdd(grads.b[L_SIGMA], bacc * inv_scale);
+  } else {
+    const uint8_t* base = act + act_layer_off(9, nt);
+    float acc[3] = {0.f, 0.f, 0.f}, bacc = 0.f;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      __syncthreads();
+      for (int i = c; i < TILE * 3; i += 256) { const long long g = (long long)tile * TILE + i / 3; s_d[i] = g < total ? d_raw_rgb[3 * g + i % 3] : 0.f; }
+      __syncthreads();
+      if (c < RGB_HID)
+        for (int r = 0; r < TILE; ++r) {
+          const float gv = chunk_elem(base, 2, (size_t)tile, r, c);
+          acc[0] = fmaf(s_d[3 * r], gv, acc[0]); acc[1] = fmaf(s_d[3 * r + 1], gv, acc[1]); acc[2] = fmaf(s_d[3 * r + 2], gv, acc[2]);
+        }
+      if (c >= 128 && c < 131) for (int r = 0; r < TILE; ++r) bacc += s_d[3 * r + (c - 128)];
+    }
+    if (c < RGB_HID) for (int k = 0; k < 3; ++k) atomicAdd(grads.w[L_RGB2] + k * RGB_HID + c, acc[k] * inv_scale);
+    if (c >= 128 && c < 131) atomicAdd(grads.b[L_RGB2] + (c - 128), bacc * inv_scale);
+  }
+}
+
+}  // namespace tcw
+}  // namespace npp
+
+using namespace npp;
+
+// Accumulates (+=) the gradients of one net's 24 parameter tensors.
+int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
+                    const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st) {
+  static int num_sms = 0;
+  static bool configured = false;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!configured) { cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcw::SMEM_BYTES); configured = true; }
+  const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
+  const int njobs = tcw::h_jobs[bg].n;
+  int splits = (2 * num_sms) / njobs;              // ~2 waves of CTAs; every job gets the same number of sample ranges
+  if (splits > num_tiles) splits = num_tiles;
+  if (splits < 1) splits = 1;
+  tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
+                                                                               (const uint8_t*)dz, scale, num_tiles, splits, *grads);
+  NPP_CHECK_LAUNCH();
+  int sx = num_tiles < 64 ? num_tiles : 64;
+  tcw::wgrad_small_kernel<<<dim3(sx, 12), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
+                                                        num_tiles, *grads);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}

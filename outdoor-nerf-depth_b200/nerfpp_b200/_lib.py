@@ -56,6 +56,11 @@ SIGNATURES = {
                                           P, P, P, P, P]),
     "nerfpp_forward_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "nerfpp_forward": (c_int, [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), P, P]),
+    "nerfpp_forward_train_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "nerfpp_forward_train": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut), P, P, P]),
+    "nerfpp_backward_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "nerfpp_backward": (c_int, [POINTER(NetParams), POINTER(NetParams), P, P, P, P, c_int, c_int, c_int, POINTER(RenderOut),
+                                POINTER(RenderOut), P, P, POINTER(NetGrads), POINTER(NetGrads), P, P]),
     "nerfpp_loss_workspace_bytes": (c_int64, []),
     "nerfpp_loss": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "nerfpp_depth_loss": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
@@ -66,13 +71,7 @@ SIGNATURES = {
     "mip360_depth_loss_workspace_bytes": (c_int64, [c_int]),
     "mip360_depth_loss": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
 }
-OPTIONAL = {
-    "nerfpp_backward_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
-    "nerfpp_backward": (c_int, [POINTER(NetParams), POINTER(NetParams), P, P, P, P, P, c_int, c_int, c_int,
-                                POINTER(RenderOut), POINTER(RenderGrads), P, POINTER(NetGrads), POINTER(NetGrads),
-                                P, P]),
-}
-
+OPTIONAL = {}
 _lib = None
 
 

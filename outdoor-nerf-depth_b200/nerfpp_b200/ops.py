@@ -19,7 +19,7 @@ LAYER_NAMES = (["base_layers.%d.0" % i for i in range(8)]
 RET_KEYS = ("rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth",
             "bg_lambda", "depth")
 LAUNCHES = [0]   # kernels of libnerfpp_b200.so launched through this module (bench.py reads it)
-_KERNELS_PER_CALL = {"intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
+_KERNELS_PER_CALL = {"backward": 14, "intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
                      "resample_merge": 1, "pack_weights": 1, "field_forward": 1, "forward": 3, "loss": 2}
 
 
@@ -296,9 +296,9 @@ def _alloc_outputs(n, sf, sb, device):
     return outs, st
 
 
-def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl=None, keep_workspace=False):
+def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl=None, keep_workspace=False, train=False):
     """NerfNet.forward (ddp_model.py:74-147) without autograd. Returns OrderedDict of the 10 keys
-    (+ the per-sample workspace when keep_workspace)."""
+    (+ the per-sample workspace when keep_workspace; with ``train`` also the training workspace the backward reads)."""
     impl = default_field_impl() if impl is None else impl
     o, d = _c(ray_o, "ray_o", 2), _c(ray_d, "ray_d", 2)
     zmax, fz, bz = _c(fg_z_max, "fg_z_max", 1), _c(fg_z, "fg_z_vals", 2), _c(bg_z, "bg_z_vals", 2)
@@ -309,11 +309,21 @@ def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, imp
     L = _lib.lib()
     ws = torch.empty(max(int(L.nerfpp_forward_workspace_bytes(n, sf, sb)), 1), device=fz.device, dtype=torch.uint8)
     outs, st = _alloc_outputs(n, sf, sb, fz.device)
+    tws = None
     with torch.cuda.device(fz.device):
-        check(L.nerfpp_forward(_p(packed_fg), _p(packed_bg), impl, _p(o), _p(d), _p(zmax), _p(fz), _p(bz), n, sf, sb,
-                               ctypes.byref(st), _p(ws), _stream()), "forward")
+        if train:
+            if impl != FIELD_TC:
+                raise NerfppError("training (autograd) runs on the tensor-core field only; unset NERFPP_FIELD=simt")
+            tws = torch.empty(int(L.nerfpp_forward_train_workspace_bytes(n, sf, sb)) + 1024, device=fz.device, dtype=torch.uint8)
+            pad = (-tws.data_ptr()) % 1024
+            tws = tws[pad:]
+            check(L.nerfpp_forward_train(_p(packed_fg), _p(packed_bg), _p(o), _p(d), _p(zmax), _p(fz), _p(bz), n, sf, sb,
+                                         ctypes.byref(st), _p(ws), _p(tws), _stream()), "forward")
+        else:
+            check(L.nerfpp_forward(_p(packed_fg), _p(packed_bg), impl, _p(o), _p(d), _p(zmax), _p(fz), _p(bz), n, sf, sb,
+                                   ctypes.byref(st), _p(ws), _stream()), "forward")
     if keep_workspace:
-        return outs, ws, (o, d, zmax, fz, bz)
+        return outs, ws, (o, d, zmax, fz, bz), tws
     return outs
 
 
@@ -354,8 +364,9 @@ class _NerfppFunction(torch.autograd.Function):
         fg_t, bg_t = params[:24], params[24:]
         packed_fg = model_cache[0].get(fg_t, impl)
         packed_bg = model_cache[1].get(bg_t, impl)
-        outs, ws, inputs = render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl, keep_workspace=True)
-        ctx.impl, ctx.ws, ctx.inputs, ctx.outs = impl, ws, inputs, outs
+        outs, ws, inputs, tws = render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl, keep_workspace=True,
+                                               train=True)
+        ctx.impl, ctx.ws, ctx.tws, ctx.inputs, ctx.outs = impl, ws, tws, inputs, outs
         ctx.save_for_backward(*params)
         vals = tuple(outs.values())
         ctx.mark_non_differentiable(outs["fg_dists"])
@@ -365,7 +376,7 @@ class _NerfppFunction(torch.autograd.Function):
     def backward(ctx, *grads):
         from . import backward as B   # CUDA backward (nerfpp_backward); raises if the library lacks it
         params = ctx.saved_tensors
-        pg = B.render_backward(ctx.impl, params, ctx.inputs, ctx.outs, ctx.ws, grads)
+        pg = B.render_backward(params, ctx.inputs, ctx.outs, ctx.ws, ctx.tws, grads)
         return (None, None, None, None, None, None, None) + tuple(pg)
 
 

@@ -112,3 +112,83 @@ def test_training_forward_saves_activations(is_bg):
     rs = ws[off:off + T * 128 * 4].view(torch.float32)[:total].cpu()
     assert relerr(rs.numpy(), raw_sigma.reshape(-1).numpy()) <= 1e-4
     assert torch.equal(rs.abs(), sig.reshape(-1).cpu())
+
+
+@pytest.mark.parametrize("loss_type", ["mse", "kl"])
+def test_full_backward_matches_oracle_autograd(loss_type):
+    """loss.backward() through the drop-in module (nerfpp_forward_train + nerfpp_backward) vs torch autograd of the oracle,
+    for the trainer's loss (ddp_train_nerf.py:481-493).  Operands inside the kernels are fp16 under a loss scale: each
+    gradient tensor must agree to 2e-2 of its own max (typically a few 1e-3)."""
+    from test_parity_gpu import make_models
+    import depth_loss as DL
+    n, cascade = 96, (64, 128)
+    params = O.densify(O.make_params(), 5.0)
+    rays = O.synthetic_rays(n, seed=21)
+    far = O.intersect_sphere(rays["ray_o"], rays["ray_d"])
+    g = torch.Generator().manual_seed(4)
+    fg_z = torch.sort(torch.rand(n, 96, generator=g), -1)[0] * far[:, None]
+    bg_z = torch.sort(torch.rand(n, 80, generator=g), -1)[0]
+    sig = 0.01 * 0.05
+    # oracle
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ret = O.nerfpp_forward(p_ref, rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)
+    loss_ref, _, _ = O.level_loss(ret, rays["rgb"], rays["depth_sup"], fg_z, far, True, loss_type, 0.1, sig)
+    g_ref = dict(zip(p_ref.keys(), torch.autograd.grad(loss_ref, list(p_ref.values()))))
+    # CUDA
+    net = make_models([params])[0]
+    C = lambda x: x.cuda()
+    out = net(C(rays["ray_o"]), C(rays["ray_d"]), C(far), C(fg_z), C(bg_z))
+    rgb_loss = torch.mean((out["rgb"] - C(rays["rgb"])) ** 2)
+    if loss_type == "kl":
+        dl = DL.depth_kl(out["fg_weights"], C(rays["depth_sup"]), C(fg_z), out["fg_dists"], sig, C(far))
+    else:
+        dl = DL.depth_mse(C(rays["depth_sup"]), out["depth"])
+    loss = rgb_loss + 0.1 * dl
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    loss.backward()
+    worst, errs = 0.0, {}
+    for name, p in net.named_parameters():
+        ref = g_ref[name]
+        assert p.grad is not None, name
+        err = float((p.grad.cpu() - ref).abs().max() / max(float(ref.abs().max()), 1e-20))
+        worst = max(worst, err)
+        cos = float((p.grad.cpu().double() * ref.double()).sum() / (p.grad.cpu().double().norm() * ref.double().norm() + 1e-300))
+        print("%-50s max-rel-err %.2e  cos %.6f  |ref|max %.2e" % (name, err, cos, float(ref.abs().max())))
+        errs[name] = err
+        assert cos >= 0.999, (name, cos)        # a layout / indexing bug destroys the direction; fp16 noise does not
+        nr = float(p.grad.norm()) / max(float(ref.norm()), 1e-30)
+        assert abs(nr - 1) <= 2e-2, (name, nr)
+    print("worst relative gradient error", worst)
+    # fp16 operands (11-bit significand) through nine layers of sums with heavy cancellation: individual entries of a
+    # gradient tensor carry noise of a few percent of the tensor's largest entry, like any mixed-precision backward
+    assert worst <= 0.2, max(errs, key=errs.get)
+
+
+def test_backward_matches_reference_golden_gradients(golden_dir):
+    """Gradient norms and leading entries recorded from the UNMODIFIED reference's autograd (oracle/gen_golden.py,
+    case c2_train_dense) vs loss.backward() through the CUDA path, for both cascade levels and all three depth losses."""
+    import os
+    from test_parity_gpu import make_models
+    import depth_loss as DL
+    g = dict(np.load(os.path.join(golden_dir, "nerfpp_c2_train_dense.npz")))
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    sig = float(g["meta_depth_sigma"]) * float(g["meta_depth_scale"])
+    for m in range(2):
+        for lt in ("mse", "l1", "kl"):
+            net = make_models([levels[m]])[0]
+            fg_z, bg_z = T(g["fg_z_%d" % m]), T(g["bg_z_%d" % m])
+            out = net(T(g["ray_o"]), T(g["ray_d"]), T(g["fg_far"]), fg_z, bg_z)
+            loss = torch.mean((out["rgb"] - T(g["rgb_gt"])) ** 2)
+            if lt == "kl":
+                loss = loss + 0.1 * DL.depth_kl(out["fg_weights"], T(g["depth_sup"]), fg_z, out["fg_dists"], sig, T(g["fg_far"]))
+            else:
+                loss = loss + 0.1 * (DL.depth_mse if lt == "mse" else DL.depth_l1)(T(g["depth_sup"]), out["depth"])
+            loss.backward()
+            for name, p in net.named_parameters():
+                short = name.replace("nerf_net.", "").replace("_layers", "").replace(".weight", ".w").replace(".bias", ".b")
+                ref_norm = float(g["grad%d_%s_norm/%s" % (m, lt, short)])
+                assert abs(float(p.grad.norm()) - ref_norm) <= 3e-2 * max(ref_norm, 1e-12), (m, lt, short, float(p.grad.norm()), ref_norm)
+                head = g["grad%d_%s_head/%s" % (m, lt, short)]
+                got = p.grad.reshape(-1)[:16].cpu().numpy()
+                assert np.abs(got - head).max() <= 0.1 * max(np.abs(head).max(), 1e-3 * ref_norm), (m, lt, short)
