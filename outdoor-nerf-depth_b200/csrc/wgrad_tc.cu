@@ -163,62 +163,87 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
   }
 }
 
-// element (row r, column c) of a chunked [tiles][nch][128][64] fp16 operand buffer
-__device__ __forceinline__ float chunk_elem(const uint8_t* layer_base, int nch, size_t tile, int r, int c) {
-  const uint8_t* ch = layer_base + (tile * nch + (c >> 6)) * (size_t)CHUNK_BYTES;
-  const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
-  return __half2float(*reinterpret_cast<const __half*>(ch + off));
+// Weighted column sums over all samples of a chunked [tiles][nch][128 rows][64 cols] fp16 operand buffer:
+//   out[ch][col] += inv_scale * sum_rows wgt[row][ch] * X[row][col]        (wgt == nullptr: plain column sums)
+// This is the bias gradient (X = DZ[l], no weights), the sigma head (X = h7, wgt = d raw sigma) and rgb.2 (X = rgb
+// hidden, wgt = d raw rgb, NCH = 3).  blockIdx.x = sample-range split; one thread owns one 16-byte unit (8 columns) of
+// four rows of every chunk, so all loads are 16-byte and a warp reads 512 contiguous bytes; the 8-column partials meet in
+// shared memory and leave with one atomicAdd per column per CTA.  HBM-bound: every operand byte is read exactly once.
+template <int NCH>
+__device__ __forceinline__ void weighted_colsum(const uint8_t* __restrict__ layer_base, int nch, const float* __restrict__ wgt,
+                                                long long total, int t_begin, int t_end, float inv_scale, float* s_acc,
+                                                float* __restrict__ out, int out_ld) {
+  const int tid = threadIdx.x, u = tid & 7, r8 = tid >> 3;          // physical unit, row group: rows r8 + 32 k
+  const int lu = u ^ (r8 & 7);                                       // logical unit (columns 8 lu .. 8 lu + 7) of all four rows
+  for (int i = tid; i < NCH * 64 * nch; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  for (int c = 0; c < nch; ++c) {
+    float acc[NCH][8];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[ch][e] = 0.f;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const uint8_t* chunk = layer_base + ((size_t)tile * nch + c) * (size_t)CHUNK_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r8 + 32 * k;
+        const uint4 v = *reinterpret_cast<const uint4*>(chunk + (r >> 3) * 1024 + (r & 7) * 128 + u * 16);
+        const __half2* hp = reinterpret_cast<const __half2*>(&v);
+        float w[NCH];
+        const long long g = (long long)tile * TILE + r;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) w[ch] = wgt ? (g < total ? wgt[(size_t)g * NCH + ch] : 0.f) : 1.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(hp[e]);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) { acc[ch][2 * e] = fmaf(w[ch], f.x, acc[ch][2 * e]); acc[ch][2 * e + 1] = fmaf(w[ch], f.y, acc[ch][2 * e + 1]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[ch * 64 * nch + c * 64 + lu * 8 + e], acc[ch][e]);
+  }
+  __syncthreads();
+  for (int i = tid; i < NCH * 64 * nch; i += 256) {
+    const int ch = i / (64 * nch), col = i % (64 * nch);
+    atomicAdd(out + (size_t)ch * out_ld + col, s_acc[i] * inv_scale);
+  }
 }
 
-// blockIdx.y = what: 0..9 bias gradient of the layer whose pre-activation gradient is DZ[y] (column sums);
-//              10 = sigma head (dW = sum d_raw_sigma * h7, db = sum d_raw_sigma); 11 = rgb.2 (dW = d_raw_rgb^T g, db = sum d_raw_rgb)
-// blockIdx.x splits the tiles; one thread per column.
+// blockIdx.y = what: 0..9 bias gradient of the layer whose pre-activation gradient is DZ[y];
+//              10 = sigma head weights, 11 = rgb.2 weights; their two bias gradients (plain sums of 1 / 3 numbers per sample)
+//              are done by the y = 10 / 11 CTAs as well.
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ dz, const float* __restrict__ d_raw_sigma,
                    const float* __restrict__ d_raw_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
                    NerfppNetGrads grads) {
-  const int what = blockIdx.y, c = threadIdx.x;
+  __shared__ float s_acc[3 * RGB_HID + W];
+  const int what = blockIdx.y;
   const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
   const float inv_scale = 1.f / *scale_ptr;
   const size_t nt = (size_t)num_tiles;
-  __shared__ float s_d[TILE * 3];
   if (what < 10) {
-    const int ncol = what == 9 ? RGB_HID : W, nch = what == 9 ? 2 : 4;
-    const uint8_t* base = dz + act_layer_off(what, nt);
-    float acc = 0.f;
-    if (c < ncol)
-      for (int tile = t_begin; tile < t_end; ++tile)
-        for (int r = 0; r < TILE; ++r) acc += chunk_elem(base, nch, (size_t)tile, r, c);
     const int pl = what < 8 ? what : what == 8 ? L_REMAP : L_RGB0;
-    if (c < ncol) atomicAdd(grads.b[pl] + c, acc * inv_scale);
-  } else if (what == 10) {
-    const uint8_t* base = act + act_layer_off(7, nt);
-    float acc = 0.f, bacc = 0.f;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      __syncthreads();
-      if (c < TILE) { const long long g = (long long)tile * TILE + c; s_d[c] = g < total ? d_raw_sigma[g] : 0.f; }
-      __syncthreads();
-      for (int r = 0; r < TILE; ++r) acc = fmaf(s_d[r], chunk_elem(base, 4, (size_t)tile, r, c), acc);
-      if (c == 0) for (int r = 0; r < TILE; ++r) bacc += s_d[r];
-    }
-    atomicAdd(grads.w[L_SIGMA] + c, acc * inv_scale);
-    if (c == 0) atomicAdd(grads.b[L_SIGMA], bacc * inv_scale);
-  } else {
-    const uint8_t* base = act + act_layer_off(9, nt);
-    float acc[3] = {0.f, 0.f, 0.f}, bacc = 0.f;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      __syncthreads();
-      for (int i = c; i < TILE * 3; i += 256) { const long long g = (long long)tile * TILE + i / 3; s_d[i] = g < total ? d_raw_rgb[3 * g + i % 3] : 0.f; }
-      __syncthreads();
-      if (c < RGB_HID)
-        for (int r = 0; r < TILE; ++r) {
-          const float gv = chunk_elem(base, 2, (size_t)tile, r, c);
-          acc[0] = fmaf(s_d[3 * r], gv, acc[0]); acc[1] = fmaf(s_d[3 * r + 1], gv, acc[1]); acc[2] = fmaf(s_d[3 * r + 2], gv, acc[2]);
-        }
-      if (c >= 128 && c < 131) for (int r = 0; r < TILE; ++r) bacc += s_d[3 * r + (c - 128)];
-    }
-    if (c < RGB_HID) for (int k = 0; k < 3; ++k) atomicAdd(grads.w[L_RGB2] + k * RGB_HID + c, acc[k] * inv_scale);
-    if (c >= 128 && c < 131) atomicAdd(grads.b[L_RGB2] + (c - 128), bacc * inv_scale);
+    weighted_colsum<1>(dz + act_layer_off(what, nt), what == 9 ? 2 : 4, nullptr, total, t_begin, t_end, inv_scale, s_acc, grads.b[pl], 0);
+    return;
+  }
+  if (what == 10) weighted_colsum<1>(act + act_layer_off(7, nt), 4, d_raw_sigma, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_SIGMA], 0);
+  else weighted_colsum<3>(act + act_layer_off(9, nt), 2, d_raw_rgb, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_RGB2], RGB_HID);
+  // bias of the head: sum over the CTA's samples of d raw sigma / d raw rgb
+  const int nch = what == 10 ? 1 : 3;
+  const float* d = what == 10 ? d_raw_sigma : d_raw_rgb;
+  float* bout = what == 10 ? grads.b[L_SIGMA] : grads.b[L_RGB2];
+  long long lo = (long long)t_begin * TILE, hi = (long long)t_end * TILE;
+  if (hi > total) hi = total;
+  for (int ch = 0; ch < nch; ++ch) {
+    float a = 0.f;
+    for (long long g = lo + threadIdx.x; g < hi; g += 256) a += d[(size_t)g * nch + ch];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0 && a != 0.f) atomicAdd(bout + ch, a * inv_scale);
   }
 }
 
@@ -246,7 +271,7 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
                                                                                (const uint8_t*)dz, scale, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
-  int sx = num_tiles < 64 ? num_tiles : 64;
+  int sx = num_tiles < 48 ? num_tiles : 48;         // 12 x 48 CTAs ~ 4 per SM
   tcw::wgrad_small_kernel<<<dim3(sx, 12), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
                                                         num_tiles, *grads);
   NPP_CHECK_LAUNCH();
