@@ -190,6 +190,9 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = (world * N_RAYS * 4 * 4 if world > 1 else N_RAYS * 4 * 4) + 2 * 4 * 4
 
+    # ---- informational: one trainer step (ddp_train_nerf.py:432-498: per level forward, loss, backward, Adam) ----
+    train = train_step_rate(models, batch, dev) if (world == 1 and not args.no_train) else None
+
     # ---- roofline of the dominant kernel (field_tc_kernel), timed alone with CUDA events ----
     roof = field_roofline(models, batch, dev)
     cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
@@ -208,11 +211,57 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof,
         }
+        if train is not None:
+            line["train"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_rate(models, batch, dev, steps=5):
+    """rays/s of the reference trainer's step on the same 4096 rays: for each cascade level forward (training mode),
+    rgb MSE + 0.1 * depth_mse, loss.backward() through nerfpp_backward, Adam step.  Reported beside the headline metric;
+    not part of `value`."""
+    import depth_loss as DL
+    from nerfpp_b200 import ops
+    import copy
+    nets = [copy.deepcopy(m) for m in models]
+    opts = [torch.optim.Adam(n.parameters(), lr=5e-4) for n in nets]
+    n = batch["ray_o"].shape[0]
+
+    def step():
+        far = ops.intersect_sphere(batch["ray_o"], batch["ray_d"])
+        fg_z = bg_z = ret = None
+        for m, S in enumerate(CASCADE):
+            if m == 0:
+                fg_z, bg_z = ops.coarse_depths(batch["min_depth"], far, S, torch.rand(n, S, device=dev), torch.rand(n, S, device=dev))
+            else:
+                fg_z = ops.resample_merge(fg_z, ret["fg_weights"].detach(), S)
+                bg_z = ops.resample_merge(bg_z, ret["bg_weights"].detach(), S)
+            opts[m].zero_grad()
+            ret = nets[m](batch["ray_o"], batch["ray_d"], far, fg_z, bg_z)
+            loss = torch.mean((ret["rgb"] - batch["rgb"]) ** 2) + LAMBDA_DEPTH * DL.depth_mse(batch["depth_sup"], ret["depth"])
+            loss.backward()
+            opts[m].step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    del nets, opts
+    torch.cuda.empty_cache()
+    return {"value": n / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+            "what": "forward + loss + backward (tcgen05 dgrad/wgrad kernels) + torch Adam, both cascade levels, 4096 rays; "
+                    "unit U2 fwd+bwd = 7.535 TFLOP algorithmic"}
 
 
 def field_roofline(models, batch, dev, reps=10):
@@ -310,6 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the informational trainer-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
