@@ -211,6 +211,18 @@ int nerfpp_depth_loss_backward(const float* depth, const float* depth_sup, const
                                const float* fwd_out, const float* grad_out, float* out_grad,
                                void* stream);
 
+/* ---- N1: ray generation + batch gather on the device -------------------------------- */
+/* get_rays_single_image (nerf_sample_ray_split.py:10-34) for the selected pixels only, fused with the gathers of
+ * RaySamplerSingleImage.random_sample / get_all (:131-221).  kinv_host = inverse of the 3x3 intrinsics (row-major,
+ * HOST memory, 9 floats), c2w_host = 4x4 camera-to-world (row-major, HOST memory), cam_depth = inv(c2w)[2,3].
+ * pixel_ids: int64 [n] device (row-major pixel index v*W+u; NULL = all n = H*W pixels in order).  img_*: the image's
+ * device-resident arrays [H*W,3] / [H*W] (NULL = absent; min depth then defaults to 1e-4).  Outputs [n,..]; rgb,
+ * depth, depth_sup, min_depth may be NULL. */
+int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, float cam_depth, int W, const int64_t* pixel_ids,
+                    int64_t n, const float* img_rgb, const float* img_depth_sup, const float* img_min_depth,
+                    float* ray_o, float* ray_d, float* depth, float* rgb, float* depth_sup, float* min_depth,
+                    void* stream);
+
 /* ---- A16: mipnerf360 twins (config 3; nerf-methods/mipnerf360/internal/) ------------------------ */
 /* stepfun.sample_intervals (stepfun.py:214-263) with use_gpu_resampling=False: softmax(w_logits) ->
  * integrate_weights -> sorted_interp(u) -> interval fenceposts (midpoints, reflected + clamped ends).

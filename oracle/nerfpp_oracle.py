@@ -418,3 +418,34 @@ def synthetic_rand(n_rays, cascade_samples=(64, 128), seed=1):
         r["u_fg_%d" % m] = torch.rand(n_rays, cascade_samples[m], generator=g)
         r["u_bg_%d" % m] = torch.rand(n_rays, cascade_samples[m], generator=g)
     return r
+
+
+# ----------------------------------------------------------------------------------------------
+# N1: ray generation and batch sampling, nerf_sample_ray_split.py
+# ----------------------------------------------------------------------------------------------
+def get_rays_single_image(H, W, intrinsics, c2w):
+    """nerf_sample_ray_split.py:10-34 (numpy, float32 inputs): pixel centres -> K^-1 -> camera-to-world rotation.
+    Returns rays_o [H*W,3], rays_d [H*W,3] (NOT normalised), depth [H*W] (= inv(c2w)[2,3])."""
+    import numpy as np
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    u = u.reshape(-1).astype(dtype=np.float32) + 0.5
+    v = v.reshape(-1).astype(dtype=np.float32) + 0.5
+    pixels = np.stack((u, v, np.ones_like(u)), axis=0)
+    rays_d = np.dot(np.linalg.inv(intrinsics[:3, :3]), pixels)
+    rays_d = np.dot(c2w[:3, :3], rays_d).transpose((1, 0))
+    rays_o = np.tile(c2w[:3, 3].reshape((1, 3)), (rays_d.shape[0], 1))
+    depth = np.linalg.inv(c2w)[2, 3] * np.ones((rays_o.shape[0],), dtype=np.float32)
+    return rays_o, rays_d, depth
+
+
+def sample_ray_batch(H, W, intrinsics, c2w, select_inds, img=None, depth_sup=None, min_depth=None):
+    """RaySamplerSingleImage.random_sample (nerf_sample_ray_split.py:155-221) for given pixel indices: a gather of the
+    per-image arrays; min_depth defaults to 1e-4 (:194-197)."""
+    import numpy as np
+    ro, rd, dp = get_rays_single_image(H, W, intrinsics, c2w)
+    ret = OrderedDict(ray_o=ro[select_inds], ray_d=rd[select_inds], depth=dp[select_inds])
+    ret["rgb"] = img.reshape(-1, 3)[select_inds] if img is not None else None
+    ret["min_depth"] = min_depth.reshape(-1)[select_inds] if min_depth is not None else 1e-4 * np.ones_like(ret["ray_d"][..., 0])
+    if depth_sup is not None:
+        ret["depth_sup"] = depth_sup.reshape(-1)[select_inds]
+    return ret

@@ -175,6 +175,32 @@ resample_merge_kernel(const float* __restrict__ z_prev, const float* __restrict_
   }
 }
 
+// ---- N1: ray generation + batch gather (nerf_sample_ray_split.py:10-34, 155-221) ------------------------------------
+// ray_d = R_c2w (K^-1 [u+.5, v+.5, 1]) evaluated per selected pixel instead of for the whole image on the host; the
+// per-image arrays the trainer gathers with numpy fancy indexing (rgb, depth prior, min depth) are gathered here too.
+struct RayCam { float kinv[9]; float rot[9]; float org[3]; float depth; };
+__global__ void gen_rays_kernel(RayCam cam, int W, const long long* __restrict__ ids, long long n, const float* __restrict__ img,
+                                const float* __restrict__ img_depth_sup, const float* __restrict__ img_min_depth,
+                                float* __restrict__ ray_o, float* __restrict__ ray_d, float* __restrict__ depth, float* __restrict__ rgb,
+                                float* __restrict__ depth_sup, float* __restrict__ min_depth) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long id = ids ? ids[i] : i;
+  const float u = (float)(id % W) + 0.5f, v = (float)(id / W) + 0.5f;     // :19-21, add half pixel
+  float c[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) c[r] = __fmaf_rn(cam.kinv[3 * r + 2], 1.f, __fmaf_rn(cam.kinv[3 * r + 1], v, __fmul_rn(cam.kinv[3 * r], u)));
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    ray_d[3 * i + r] = __fmaf_rn(cam.rot[3 * r + 2], c[2], __fmaf_rn(cam.rot[3 * r + 1], c[1], __fmul_rn(cam.rot[3 * r], c[0])));
+    ray_o[3 * i + r] = cam.org[r];
+  }
+  if (depth) depth[i] = cam.depth;
+  if (rgb && img) { rgb[3 * i] = img[3 * id]; rgb[3 * i + 1] = img[3 * id + 1]; rgb[3 * i + 2] = img[3 * id + 2]; }
+  if (depth_sup && img_depth_sup) depth_sup[i] = img_depth_sup[id];
+  if (min_depth) min_depth[i] = img_min_depth ? img_min_depth[id] : 1e-4f;   // :194-197
+}
+
 }  // namespace npp
 
 using namespace npp;
@@ -247,6 +273,21 @@ extern "C" int nerfpp_resample_merge(const float* z_prev, const float* w_prev, c
   if (smem > 48 * 1024) cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   resample_merge_kernel<<<(n_rays + SAMP_WARPS - 1) / SAMP_WARPS, SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
       z_prev, w_prev, u, u_ld, n_rays, n_prev, n_new, out_z);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, float cam_depth, int W, const int64_t* pixel_ids,
+                               int64_t n, const float* img_rgb, const float* img_depth_sup, const float* img_min_depth, float* ray_o,
+                               float* ray_d, float* depth, float* rgb, float* depth_sup, float* min_depth, void* stream) {
+  NPP_CHECK_ARG(kinv_host && c2w_host && ray_o && ray_d && W >= 1 && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  RayCam cam;
+  for (int i = 0; i < 9; ++i) cam.kinv[i] = kinv_host[i];
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) cam.rot[3 * r + c] = c2w_host[4 * r + c]; cam.org[r] = c2w_host[4 * r + 3]; }
+  cam.depth = cam_depth;
+  gen_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cam, W, (const long long*)pixel_ids, n, img_rgb, img_depth_sup,
+                                                                              img_min_depth, ray_o, ray_d, depth, rgb, depth_sup, min_depth);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -125,3 +125,14 @@ def test_depth_losses_edge_cases():
     assert torch.isnan(O.depth_mse(gt, pred)) and torch.isnan(O.depth_l1(gt, pred))   # empty mean => NaN
     w = torch.rand(7, 5)
     assert float(O.depth_kl(w, gt, torch.rand(7, 5), torch.rand(7, 5), 0.01, torch.ones(7))) == 0.0
+
+
+def test_ray_generation_matches_reference(golden_dir):
+    """N1: oracle get_rays_single_image vs rays recorded from the unmodified reference sampler (gen_golden_rays.py)."""
+    g = dict(np.load(os.path.join(golden_dir, "rays_tat_truck.npz")))
+    for ci in range(2):
+        H, W = (int(x) for x in g["hw%d" % ci])
+        ro, rd, dp = O.get_rays_single_image(H, W, g["K%d" % ci], g["c2w%d" % ci])
+        ids = g["ids%d" % ci]
+        assert np.array_equal(rd[ids].astype(np.float32), g["ray_d%d" % ci]) and np.array_equal(ro[ids].astype(np.float32), g["ray_o%d" % ci])
+        assert np.array_equal(dp[ids].astype(np.float32), g["depth%d" % ci])
