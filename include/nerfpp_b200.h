@@ -223,6 +223,15 @@ int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, float cam_dep
                     float* ray_o, float* ray_d, float* depth, float* rgb, float* depth_sup, float* min_depth,
                     void* stream);
 
+/* ---- N3: image metrics of the test loop (ddp_train_nerf.py:556-600) -------------------- */
+/* out_metrics[8] (device) = mse, psnr = -10 log10(mse + 1e-6), #valid depth pixels, rmse, rmse_log, abs_diff, abs_rel,
+ * sq_rel; depth metrics over pixels with 1e-3 < gt/depth_scale < cap (cap = 80 m in the reference), both sides clipped to
+ * [1e-3, cap].  rgb_gt / depth_gt may be NULL (their outputs are then 0 / NaN).  workspace:
+ * nerfpp_loss_workspace_bytes() * 2 bytes. */
+int nerfpp_image_metrics(const float* rgb, const float* rgb_gt, const float* depth, const float* depth_gt,
+                         int64_t n_pixels, float depth_scale, float cap, float* out_metrics, void* workspace,
+                         void* stream);
+
 /* ---- A16: mipnerf360 twins (config 3; nerf-methods/mipnerf360/internal/) ------------------------ */
 /* stepfun.sample_intervals (stepfun.py:214-263) with use_gpu_resampling=False: softmax(w_logits) ->
  * integrate_weights -> sorted_interp(u) -> interval fenceposts (midpoints, reflected + clamped ends).

@@ -449,3 +449,23 @@ def sample_ray_batch(H, W, intrinsics, c2w, select_inds, img=None, depth_sup=Non
     if depth_sup is not None:
         ret["depth_sup"] = depth_sup.reshape(-1)[select_inds]
     return ret
+
+
+def image_metrics(im, gt_im, depth_pred, depth_gt, depth_scale, cap=80):
+    """N3: the test loop's per-image metrics, ddp_train_nerf.py:556-600 (numpy, as the reference computes them)."""
+    import numpy as np
+    r = {}
+    mse = np.mean((gt_im - im) * (gt_im - im))
+    r["mse"], r["psnr"] = float(mse), float(-10. * np.log(mse + TINY_NUMBER) / np.log(10.))
+    gt_sparse = depth_gt / depth_scale
+    pred = depth_pred / depth_scale
+    valid = (gt_sparse < cap) & (gt_sparse > 1e-3)
+    vg = gt_sparse[valid].clip(1e-3, cap)
+    vp = pred[valid].clip(1e-3, cap)
+    r["n_valid"] = float(valid.sum())
+    r["rmse"] = float(np.sqrt(np.mean((vg - vp) ** 2)))
+    r["rmse_log"] = float(np.sqrt(np.mean((np.log(vg) - np.log(vp)) ** 2)))
+    r["abs_diff"] = float(np.mean(np.abs(vg - vp)))
+    r["abs_rel"] = float(np.mean(np.abs(vg - vp) / vg))
+    r["sq_rel"] = float(np.mean(((vg - vp) ** 2) / vg))
+    return r

@@ -114,6 +114,49 @@ __global__ void depth_loss_backward_kernel(const float* __restrict__ depth, cons
   }
 }
 
+// ---- N3: image metrics of the test loop (ddp_train_nerf.py:556-600) ------------------------------------------------
+// partial [block][8] doubles: sum sq rgb err, valid count, sum (gt-pred)^2, sum (log gt - log pred)^2, sum |gt-pred|,
+// sum |gt-pred|/gt, sum (gt-pred)^2/gt, unused
+__global__ void __launch_bounds__(LOSS_THREADS)
+metrics_partial_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb_gt, const float* __restrict__ depth,
+                       const float* __restrict__ depth_gt, long long n, float depth_scale, float cap, double* __restrict__ partial) {
+  __shared__ double sh[LOSS_THREADS / 32];
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (rgb_gt)
+      for (int c = 0; c < 3; ++c) { const float d = rgb_gt[3 * i + c] - rgb[3 * i + c]; a[0] += (double)(d * d); }
+    if (depth_gt) {
+      const float gt = depth_gt[i] / depth_scale, pr0 = depth[i] / depth_scale;        // :567-569
+      if (gt < cap && gt > 1e-3f) {                                                     // :575
+        const float g = fminf(fmaxf(gt, 1e-3f), cap), p = fminf(fmaxf(pr0, 1e-3f), cap);
+        const float d = g - p, dl = logf(g) - logf(p);
+        a[1] += 1.0; a[2] += (double)(d * d); a[3] += (double)(dl * dl); a[4] += (double)fabsf(d);
+        a[5] += (double)(fabsf(d) / g); a[6] += (double)(d * d / g);
+      }
+    }
+  }
+  for (int k = 0; k < 7; ++k) {
+    const double t = block_sum(a[k], sh);
+    if (threadIdx.x == 0) partial[8 * blockIdx.x + k] = t;
+  }
+}
+// out[8] = mse, psnr (utils.py:31), #valid depth pixels, rmse, rmse_log, abs_diff, abs_rel, sq_rel
+__global__ void metrics_final_kernel(const double* __restrict__ partial, int nblocks, long long n, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nblocks; ++i)
+    for (int k = 0; k < 7; ++k) a[k] += partial[8 * i + k];
+  const double mse = a[0] / (3.0 * (double)n), c = a[1];
+  out[0] = (float)mse;
+  out[1] = (float)(-10.0 * log(mse + 1e-6) / log(10.0));
+  out[2] = (float)c;
+  out[3] = (float)sqrt(a[2] / c);
+  out[4] = (float)sqrt(a[3] / c);
+  out[5] = (float)(a[4] / c);
+  out[6] = (float)(a[5] / c);
+  out[7] = (float)(a[6] / c);
+}
+
 }  // namespace npp
 
 using namespace npp;
@@ -163,6 +206,21 @@ extern "C" int nerfpp_loss(const float* rgb, const float* rgb_gt, const float* d
   NPP_CHECK_LAUNCH();
   loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, blocks, n_rays, s_fg, depth_loss_type,
                                                        lambda_depth, out_loss);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nerfpp_image_metrics(const float* rgb, const float* rgb_gt, const float* depth, const float* depth_gt, int64_t n_pixels,
+                                    float depth_scale, float cap, float* out_metrics, void* workspace, void* stream) {
+  NPP_CHECK_ARG(out_metrics && workspace && n_pixels >= 1, "bad argument");
+  NPP_CHECK_ARG(!rgb_gt || rgb, "rgb_gt without rgb");
+  NPP_CHECK_ARG(!depth_gt || depth, "depth_gt without depth");
+  int blocks = (int)((n_pixels + LOSS_THREADS - 1) / LOSS_THREADS);
+  if (blocks > LOSS_MAX_BLOCKS) blocks = LOSS_MAX_BLOCKS;
+  metrics_partial_kernel<<<blocks, LOSS_THREADS, 0, (cudaStream_t)stream>>>(rgb, rgb_gt, depth, depth_gt, n_pixels, depth_scale, cap,
+                                                                           (double*)workspace);
+  NPP_CHECK_LAUNCH();
+  metrics_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, blocks, n_pixels, out_metrics);
   NPP_CHECK_LAUNCH();
   return 0;
 }

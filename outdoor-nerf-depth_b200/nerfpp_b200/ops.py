@@ -416,3 +416,23 @@ def fused_loss(rgb, rgb_gt, depth=None, depth_sup=None, depth_loss_type=None, la
         check(L.nerfpp_loss(_p(r), _p(g), _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(args[5]),
                             n, S, typ, float(lambda_depth), float(kl_sigma), _p(out), _p(ws), _stream()), "loss")
     return out
+
+
+METRIC_KEYS = ("mse", "psnr", "n_valid", "rmse", "rmse_log", "abs_diff", "abs_rel", "sq_rel")
+
+
+def image_metrics(rgb, rgb_gt=None, depth=None, depth_gt=None, depth_scale=1.0, cap=80.0):
+    """The per-image metrics of the reference's test loop (ddp_train_nerf.py:556-600) on device tensors of any shape
+    ([H,W,3] / [H,W]); returns a dict of python floats (one device->host read)."""
+    r = _c(rgb, "rgb").reshape(-1, 3) if rgb is not None else None
+    n = r.shape[0] if r is not None else depth.numel()
+    g = _c(rgb_gt, "rgb_gt").reshape(-1, 3) if rgb_gt is not None else None
+    d = _c(depth, "depth").reshape(-1) if depth is not None else None
+    dg = _c(depth_gt, "depth_gt").reshape(-1) if depth_gt is not None else None
+    dev = (r if r is not None else d).device
+    L = _lib.lib()
+    out = torch.empty(8, device=dev, dtype=torch.float32)
+    ws = torch.empty(2 * int(L.nerfpp_loss_workspace_bytes()), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        check(L.nerfpp_image_metrics(_p(r), _p(g), _p(d), _p(dg), n, float(depth_scale), float(cap), _p(out), _p(ws), _stream()), "loss")
+    return dict(zip(METRIC_KEYS, out.cpu().tolist()))

@@ -53,3 +53,19 @@ def test_sampler_gathers_and_get_all_match_oracle(golden_dir):
     assert cc["ray_d"].shape == (16, 3)
     dv = s.random_sample(50, device_rng=True)
     assert dv["ray_d"].shape == (50, 3)
+
+
+def test_image_metrics_match_oracle():
+    """N3: PSNR / RMSE / AbsRel ... of the reference's test loop (ddp_train_nerf.py:556-600)."""
+    from nerfpp_b200 import ops
+    rng = np.random.default_rng(0)
+    H, W, scale = 64, 96, 0.05
+    im, gt = rng.random((H, W, 3), dtype=np.float32), rng.random((H, W, 3), dtype=np.float32)
+    dgt = (rng.random((H, W), dtype=np.float32) * 100 * scale).astype(np.float32)     # some beyond the 80 m cap
+    dgt[::4] = 0                                                                       # sparse LiDAR
+    dpred = (dgt + rng.normal(0, 0.2, (H, W)).astype(np.float32) * scale).astype(np.float32)
+    ref = O.image_metrics(im, gt, dpred, dgt, scale)
+    got = ops.image_metrics(torch.from_numpy(im).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(dpred).cuda(),
+                            torch.from_numpy(dgt).cuda(), scale)
+    for k, v in ref.items():
+        assert abs(got[k] - v) <= 2e-5 * max(abs(v), 1e-6), (k, got[k], v)
