@@ -126,10 +126,15 @@ def run_ours(args):
     gathered = torch.empty(world * N_RAYS, 4, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    pending_flag = [None]
+
     def step(b):
         with torch.no_grad():
+            if pending_flag[0] is not None:          # the previous step's out-of-sphere flag (its work is long done)
+                pending_flag[0].raise_if_set()
             res = render_rays(models, b, CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH,
-                              depth_sigma=DEPTH_SIGMA)
+                              depth_sigma=DEPTH_SIGMA, defer_unbounded_check=True)
+            pending_flag[0] = res["unbounded"]
             ret = res["levels"][-1][0]
             if world > 1:
                 tile = torch.cat((ret["rgb"], ret["depth"][:, None]), -1)

@@ -70,9 +70,33 @@ def _rows(t):
 # ------------------------------------------------------------------------------------------------
 # A1-A5 sampling
 # ------------------------------------------------------------------------------------------------
-def intersect_sphere(ray_o, ray_d):
+class UnboundedFlag(object):
+    """Deferred form of the reference's out-of-sphere check (ddp_train_nerf.py:62-63): the kernel sets a device flag;
+    ``raise_if_set()`` reads it (one host sync) and raises the reference's exception."""
+
+    _pinned, _next = [], [0]
+
+    def __init__(self, flag):
+        # the flag travels to a pinned host word right behind the kernel that sets it, so reading it later waits for
+        # that kernel only, not for whatever has been enqueued since
+        if len(self._pinned) < 16:
+            self._pinned.append(torch.empty(1, dtype=torch.int32, pin_memory=True))
+        self.host = self._pinned[self._next[0] % len(self._pinned)]
+        self._next[0] += 1
+        self.host.copy_(flag, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def raise_if_set(self):
+        self.event.synchronize()
+        if int(self.host[0]) != 0:
+            raise Exception(UNBOUNDED_MSG)
+
+
+def intersect_sphere(ray_o, ray_d, deferred=False):
     """ddp_train_nerf.py:51-66. ray_o, ray_d [..., 3] -> [...]. Raises like the reference when a
-    camera is outside the unit sphere (same data-dependent host sync as its ``.any()``)."""
+    camera is outside the unit sphere (same data-dependent host sync as its ``.any()``).  ``deferred=True`` returns
+    (far, UnboundedFlag) without synchronising, for callers that check once at the end of a step."""
     o, lead = _rows(_c(ray_o, "ray_o"))
     d, _ = _rows(_c(ray_d, "ray_d"))
     if o.shape[-1] != 3 or d.shape != o.shape:
@@ -82,8 +106,9 @@ def intersect_sphere(ray_o, ray_d):
     flag = torch.zeros(1, device=o.device, dtype=torch.int32)
     with torch.cuda.device(o.device):
         check(_lib.lib().nerfpp_intersect_sphere(_p(o), _p(d), n, _p(far), _p(flag), _stream()), "intersect_sphere")
-    if int(flag.item()) != 0:
-        raise Exception(UNBOUNDED_MSG)
+    if deferred:
+        return far.reshape(lead), UnboundedFlag(flag)
+    UnboundedFlag(flag).raise_if_set()
     return far.reshape(lead)
 
 

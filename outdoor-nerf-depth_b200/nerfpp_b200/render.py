@@ -8,14 +8,17 @@ from . import ops
 
 
 def cascade_forward(models, ray_o, ray_d, min_depth, cascade_samples=(64, 128), train=False, rand=None, impl=None,
-                    fg_far=None):
+                    fg_far=None, unbounded_check=None):
     """Runs every cascade level. ``models[m]`` is a ddp_model.NerfNetWithAutoExpo (or anything with
     the same forward signature). ``train`` selects the stochastic path (perturbed coarse depths,
     random inverse-CDF draws, :440-465) vs the deterministic test path (:166-196).  ``rand`` may
     carry explicit draws {'t_fg','t_bg','u_fg_1','u_bg_1',...} (tests).
     Returns ([(ret, fg_z, bg_z) per level], fg_far)."""
+    flag = None
     if fg_far is None:
-        fg_far = ops.intersect_sphere(ray_o, ray_d)
+        # the reference raises inside intersect_sphere (a host sync before anything else is enqueued); here the whole
+        # cascade is enqueued first and the flag is read once at the end: same exception, no pipeline bubble
+        fg_far, flag = ops.intersect_sphere(ray_o, ray_d, deferred=True)
     out = []
     fg_z = bg_z = ret = None
     n = ray_o.shape[0]
@@ -33,17 +36,23 @@ def cascade_forward(models, ray_o, ray_d, min_depth, cascade_samples=(64, 128), 
             bg_z = ops.resample_merge(bg_z, ret["bg_weights"], S, det=not train, u=u_bg)
         ret = models[m](ray_o, ray_d, fg_far, fg_z, bg_z) if impl is None else models[m](ray_o, ray_d, fg_far, fg_z, bg_z, impl=impl)
         out.append((ret, fg_z, bg_z))
+    if flag is not None:
+        if unbounded_check is None:
+            flag.raise_if_set()
+        else:
+            unbounded_check.append(flag)      # the caller reads it when convenient (e.g. one step later)
     return out, fg_far
 
 
 def render_rays(models, ray_batch, cascade_samples=(64, 128), train=False, depth_loss_type=None, lambda_depth=0.0,
-                depth_sigma=0.01, rand=None, impl=None):
+                depth_sigma=0.01, rand=None, impl=None, defer_unbounded_check=False):
     """One pass of the whole hot path over a ray batch (a dict like RaySamplerSingleImage yields:
     ray_o, ray_d, min_depth, and optionally rgb, depth_sup, depth_scale).  Returns an OrderedDict
     with the finest level's outputs, the per-level depths, and -- when ``rgb`` is present -- the
     loss vector [rgb_loss, depth_loss, total, n_valid] per level (ddp_train_nerf.py:481-493)."""
+    pending = []
     out, fg_far = cascade_forward(models, ray_batch["ray_o"], ray_batch["ray_d"], ray_batch["min_depth"],
-                                  cascade_samples, train, rand, impl)
+                                  cascade_samples, train, rand, impl, unbounded_check=pending)
     res = OrderedDict(levels=out, fg_far=fg_far)
     if "rgb" in ray_batch:
         losses = []
@@ -55,6 +64,12 @@ def render_rays(models, ray_batch, cascade_samples=(64, 128), train=False, depth
                                          depth_loss_type if use_depth else None, lambda_depth, ret["fg_weights"], fg_z,
                                          ret["fg_dists"], fg_far, depth_sigma * scale))
         res["losses"] = losses
+    # ddp_train_nerf.py:62-63 raises as soon as a camera is outside the unit sphere; here everything has been enqueued
+    # first.  With defer_unbounded_check the flag is handed to the caller (res["unbounded"].raise_if_set()).
+    if defer_unbounded_check:
+        res["unbounded"] = pending[0] if pending else None
+    elif pending:
+        pending[0].raise_if_set()
     return res
 
 
