@@ -121,6 +121,83 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
   }
 }
 
+// Epilogue of one layer for one thread (= one accumulator row, TMEM lane).  The layer kinds are compile-time variants so
+// that the per-chunk chain  tcgen05.ld -> cvt -> tcgen05.st -> fence -> mbarrier arrive  carries no layer tests: the
+// tensor pipe idles for exactly this chain at every layer boundary (profiles/r1c_*: a generic loop with the layer
+// tests inside ran ~3x longer per chunk than the bare sequence).
+//   KIND 0  hidden layer: ReLU + fp16 pack, written back over the fp32 columns just read = next layer's A operand
+//   KIND 1  base layer 7: the same, then the sigma head (nerf_network.py:133) on the fp32 values AFTER the arrive
+//   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
+//   KIND 3  rgb.0: ReLU, then rgb.2 (nerf_network.py:114-117) as fp32 dot products; no A operand follows
+// Chunks [J0, J0 + NCH) of the layer output (the tail-split schedule hands the two column halves over separately).
+template <int KIND, bool SAVE, int J0, int NCH>
+__device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
+                                               const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
+                                               float (&rgb_part)[3], long long* probe_slot) {
+  uint32_t v[2][32];
+  tmem_ld32(acc_addr + 64u * J0, v[J0 & 1]);
+#pragma unroll
+  for (int j = J0; j < J0 + NCH; ++j) {
+    uint32_t (&cur)[32] = v[j & 1];
+    tmem_ld_wait(cur);
+    if (j + 1 < J0 + NCH) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
+    if (KIND != 3) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
+      tmem_st16(acc_addr + 64u * j, pk);
+      if (SAVE) store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(aready_bar + 8u * j);
+      if (probe_slot) probe_slot[j] = clock64();
+      if (KIND == 1) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh) + t);
+          s[0] = fmaf(fmaxf(__uint_as_float(cur[4 * t]), 0.f), w4.x, s[0]);
+          s[1] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f), w4.y, s[1]);
+          s[2] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), w4.z, s[2]);
+          s[3] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f), w4.w, s[3]);
+        }
+        sig_part += (s[0] + s[1]) + (s[2] + s[3]);
+      }
+    } else {
+      if (SAVE) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
+        store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float a0 = fmaxf(__uint_as_float(cur[4 * t]), 0.f), a1 = fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f);
+        const float a2 = fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), a3 = fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * j + 32 * hh) + t);
+          rgb_part[c] = fmaf(a0, w4.x, rgb_part[c]);
+          rgb_part[c] = fmaf(a1, w4.y, rgb_part[c]);
+          rgb_part[c] = fmaf(a2, w4.z, rgb_part[c]);
+          rgb_part[c] = fmaf(a3, w4.w, rgb_part[c]);
+        }
+      }
+    }
+  }
+}
+
+template <bool SAVE, int J0, int NCH>
+__device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
+                                                  const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
+                                                  float (&rgb_part)[3], long long* probe_slot) {
+  if (m < 7) epilogue_layer<0, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
+  else if (m == 7) epilogue_layer<1, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
+  else if (m == 8) epilogue_layer<2, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
+  else epilogue_layer<3, SAVE, 0, 2>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
+}
+
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
 template <bool BG, int CLUSTER, bool TAIL>
@@ -131,7 +208,12 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int D = BG ? 4 : 3;
   const StepTable& tab = c_tab[BG ? 1 : 0];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // read the thread coordinates once through volatile asm: otherwise ptxas re-reads %tid / %ctaid with S2R (tens of cycles
+  // each) inside the epilogue's per-chunk loop, on the critical path of every mbarrier arrive
+  uint32_t tid_pinned, cta_pinned;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_pinned));
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta_pinned));
+  const int warp = (int)(tid_pinned >> 5), lane = (int)(tid_pinned & 31);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
   auto bar = [&](int i) { return bar0 + 8u * i; };
@@ -142,8 +224,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
   // tiles: cluster c takes groups of CLUSTER consecutive tiles; every CTA of a cluster runs the same
   // number of (possibly empty) tiles so the shared weight ring stays in step
   const int n_groups = (num_tiles + CLUSTER - 1) / CLUSTER;
-  const int group0 = blockIdx.x / CLUSTER, group_step = gridDim.x / CLUSTER;
-  const bool timing = dbg != nullptr;
+  const int group0 = (int)cta_pinned / CLUSTER, group_step = gridDim.x / CLUSTER;
+  const bool probing = dbg != nullptr;                 // single-shot timestamps of one layer boundary (tile 5, layers 2-3)
+  const bool timing = probing && !(flags & 128);      // + per-role cycle accumulators (perturbs the epilogue by ~2x)
 
   if (warp == MMA_WARP && lane == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
@@ -157,9 +240,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp < NUM_EPI_WARPS) {   // zero both E buffers once (padding columns are never written again), then the two ones
-    for (int i = threadIdx.x; i < 2 * E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = (int)tid_pinned; i < 2 * E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int eb = threadIdx.x >> 7, row = threadIdx.x & 127;
+    const int eb = (int)tid_pinned >> 7, row = (int)tid_pinned & 127;
     *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL)) = __float2half_rn(1.f);
     *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL + 1)) = __float2half_rn(1.f);
     fence_proxy_async();
@@ -305,7 +388,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
             // ---- A chunks: c0 as column halves (m != 5: with the bias), c1 whole, c2/c3 as column halves ----
             mbar_wait2(bar(B_AREADY + 0), a_par, wfull, ph);
             tc_fence_after();
-            if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * blockIdx.x + 4] = clock64();
+            if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * (int)cta_pinned + 4] = clock64();
             if (elect_one()) {
               const uint32_t blo = sw128_lo(slot + AUX_BYTES);
               if (m != 5) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, ID128);
@@ -350,7 +433,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
               __syncwarp();
               advance();
-              if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * blockIdx.x + (m == 2 ? 0 : 12)] = clock64();
+              if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * (int)cta_pinned + (m == 2 ? 0 : 12)] = clock64();
             }
             a_par ^= 1;
           }
@@ -399,7 +482,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                 //  interlocked on TMEM A-read vs D-write.)
                 mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
                 tc_fence_after();
-                if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * blockIdx.x + 4 + c] = clock64();
+                if (probing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * (int)cta_pinned + 4 + c] = clock64();
                 if (elect_one()) {
                   if (c == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
                   ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), idesc);
@@ -411,15 +494,15 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
               a_par ^= 1;
             }
-            if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * blockIdx.x + (m == 2 ? 0 : 12)] = clock64();
+            if (probing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * (int)cta_pinned + (m == 2 ? 0 : 12)] = clock64();
           }
         }
       }
-      if (timing && lane == 0) dbg[8 * blockIdx.x] = clock64() - t0;
+      if (probing && lane == 0) dbg[8 * (int)cta_pinned] = clock64() - t0;
     }
   } else if (warp >= EMB_WARP0) {
     // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
-    const int row = threadIdx.x - EMB_WARP0 * 32;    // 0..127
+    const int row = (int)tid_pinned - EMB_WARP0 * 32;    // 0..127
     uint32_t tile_i = 0;
     long long m_t0 = clock64(), m_wait = 0, mtt = 0;
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
@@ -446,13 +529,15 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
       float dn = norm3(d[0], d[1], d[2]);
       float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
-      embed_vec(x, D, NF_POS, sE, row, 0);
-      embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
+      if (!(flags & 512)) {   // experiment: 512 = no embedding work (results wrong, timing only)
+        embed_vec(x, D, NF_POS, sE, row, 0);
+        embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EFULL + eb));
     }
-    if (timing && threadIdx.x == EMB_WARP0 * 32) { dbg[8 * blockIdx.x + 4] = clock64() - m_t0; dbg[8 * blockIdx.x + 7] = m_wait; }
+    if (timing && (int)tid_pinned == EMB_WARP0 * 32) { dbg[8 * (int)cta_pinned + 4] = clock64() - m_t0; dbg[8 * (int)cta_pinned + 7] = m_wait; }
   } else {
     // ================= epilogue warps =================
     // Thread = one accumulator row (TMEM lane); warps w and w+4 split each 64-column chunk.  The fp16
@@ -463,13 +548,16 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_par = 0;
-    long long e_wait = 0, e_t0 = clock64(), ett = 0, e_ld = 0, e_cvt = 0, e_st = 0, e_arr = 0;
+    long long e_wait = 0, e_t0 = clock64(), ett = 0;
     for (int grp = group0; grp < n_groups; grp += group_step) {
       const int tile = grp * CLUSTER + (int)cta_rank;
       const long long g = (long long)tile * TILE + row;
       const bool valid = g < total;
       float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
-      constexpr int UNITS = TAIL ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, half) accumulations per tile
+      long long* const probe_base = (probing && (int)tid_pinned == 0 && grp == group0 + 5 * group_step) ? dbg + 14 * 148 + 16 * (int)cta_pinned : nullptr;
+      uint8_t* const act_tile = save.act ? save.act + act_chunk_off(0, (size_t)num_tiles, (size_t)tile, 0) : nullptr;
+      const size_t act_layer_stride = act_layer_off(1, (size_t)num_tiles);
+      constexpr int UNITS = TAIL ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, column half) accumulations per tile
 #pragma unroll 1
       for (int un = 0; un < UNITS; ++un) {
         const int m = TAIL ? (un >> 1) : un, h = TAIL ? (un & 1) : 0;
@@ -479,71 +567,22 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (timing) e_wait += clock64() - ett;
         acc_par ^= 1u << ab;
         tc_fence_after();
-        const bool probe = timing && threadIdx.x == 0 && m == 2 && h == 0 && grp == group0 + 5 * group_step;
-        if (probe) dbg[14 * 148 + 16 * blockIdx.x + 1] = clock64();
+        long long* const probe = (probe_base && m == 2 && h == 0) ? probe_base + 8 : nullptr;
+        if (probe) probe_base[1] = clock64();
         const uint32_t acc_addr = lane_addr + (uint32_t)((m & 1) * 256 + 32 * hh);
-        const int j0 = 2 * h, nchunk = (TAIL || m == 9) ? j0 + 2 : 4;     // 64-column chunks [j0, nchunk) of the layer output
-        uint32_t v[2][32];
-        tmem_ld32(acc_addr + 64u * j0, v[0]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j >= j0 && j < nchunk) {
-            uint32_t (&cur)[32] = v[j & 1];   // j0 is even: chunk j0 sits in v[0]
-            if (timing) ett = clock64();
-            tmem_ld_wait(cur);
-            if (timing) { long long t1 = clock64(); e_ld += t1 - ett; ett = t1; }
-            if (j + 1 < nchunk) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
-            if (m == 7) {   // sigma head on the fp32 activations, nerf_network.py:133
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh) + t);
-                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t]), 0.f), w4.x, sig_part);
-                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f), w4.y, sig_part);
-                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), w4.z, sig_part);
-                sig_part = fmaf(fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f), w4.w, sig_part);
-              }
-            }
-            if (m == 9) {   // rgb.2 on the fp32 hidden colour features, nerf_network.py:114-117
-              if (save.act) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
-                store_act_chunk(save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
-              }
-#pragma unroll
-              for (int t = 0; t < 32; ++t) cur[t] = __float_as_uint(fmaxf(__uint_as_float(cur[t]), 0.f));
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * j + 32 * hh) + t);
-                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t]), w4.x, rgb_part[c]);
-                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 1]), w4.y, rgb_part[c]);
-                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 2]), w4.z, rgb_part[c]);
-                  rgb_part[c] = fmaf(__uint_as_float(cur[4 * t + 3]), w4.w, rgb_part[c]);
-                }
-              }
-            } else {        // next layer's A operand: 32 fp16 = 16 packed columns, in place
-              uint32_t pk[16];
-              if (m == 8) {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<false>(cur[2 * t], cur[2 * t + 1]);
-              } else {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
-              }
-              if (timing) { long long t1 = clock64(); e_cvt += t1 - ett; ett = t1; }
-              tmem_st16(acc_addr + 64u * j, pk);
-              if (save.act) store_act_chunk(save.act + act_chunk_off(m, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
-              tmem_st_wait();
-              if (timing) { long long t1 = clock64(); e_st += t1 - ett; ett = t1; }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_AREADY + j));
-              if (timing) { long long t1 = clock64(); e_arr += t1 - ett; ett = t1; }
-              if (probe) dbg[14 * 148 + 16 * blockIdx.x + 8 + j] = clock64();
-            }
+        const uint32_t aready = bar(B_AREADY);
+        uint8_t* const act = !act_tile ? nullptr : (m == 9) ? save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0) : act_tile + m * act_layer_stride;
+        if (TAIL) {
+          if (act) {
+            if (h == 0) epilogue_dispatch<true, 0, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
+            else epilogue_dispatch<true, 2, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
+          } else {
+            if (h == 0) epilogue_dispatch<false, 0, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
+            else epilogue_dispatch<false, 2, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
           }
+        } else {
+          if (act) epilogue_dispatch<true, 0, 4>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
+          else epilogue_dispatch<false, 0, 4>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
         }
       }
       // ---- combine the two column halves of each row, write sigma / rgb -------------------------------
@@ -562,10 +601,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    if (timing && threadIdx.x == 0) {
-      dbg[8 * blockIdx.x + 5] = clock64() - e_t0; dbg[8 * blockIdx.x + 6] = e_wait;
-      long long* x = dbg + 10 * 148 + 4 * blockIdx.x;
-      x[0] = e_ld; x[1] = e_cvt; x[2] = e_st; x[3] = e_arr;
+    if (timing && (int)tid_pinned == 0) {
+      dbg[8 * (int)cta_pinned + 5] = clock64() - e_t0; dbg[8 * (int)cta_pinned + 6] = e_wait;
     }
   }
   tc_fence_before();

@@ -49,7 +49,7 @@ for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_
         if pr[:, 0].any():
             q = pr[pr[:, 0] > 0]
             rel = (q - q[:, :1]).mean(0)
-            print("   chain (cycles after ACC commit of layer 2): epi wake %.0f | epi arrive c0..3 %s | mma past AREADY c0..3 %s | layer 3 ACC commit issued %.0f" % (rel[1], rel[8:12].round(), rel[4:8].round(), rel[12]))
+            print("   chain (cycles after ACC commit of layer 2): epi wake %.0f | epi arrive c0..3 %s | mma past AREADY c0..3 %s | layer 3 ACC commit issued %.0f | chunk 0: ld done %.0f cvt done %.0f st done %.0f" % (rel[1], rel[8:12].round(), rel[4:8].round(), rel[12], rel[2], rel[3], rel[13]))
         key = (is_bg,)
         if key not in ref:
             ref[key] = (sig.clone(), rgb.clone())
