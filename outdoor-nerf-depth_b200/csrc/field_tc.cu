@@ -21,7 +21,7 @@
 //              4 x 40 KB shared-memory ring with cp.async.bulk (+cluster multicast) and mbarriers
 //   warp 10-13 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128)
 //
-// Shared memory (bytes): E 2x32K | ring 4x40K | barriers | scratch.  TMEM: 2 x 256 columns.
+// Shared memory (bytes): E 2x32K | ring 4x40K | barriers | fp32 head weights.  TMEM: 2 x 256 columns.
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
 // against the fp32 reference: rgb/depth within 3e-5 relative (tests/test_parity_gpu.py).
 #include <cstdlib>
@@ -35,16 +35,15 @@ constexpr int AUX_BYTES = 8192;             // head of a ring slot: the layer's 
 constexpr int STAGE_BYTES = AUX_BYTES + 32768;   // + one [256 N x 64 K] SW128 weight tile
 constexpr int BIAS_ROW_BYTES = 32;          // bias tile: [N x 16 K] fp16, unswizzled 8x8 core matrices
 constexpr int E_BYTES = 2 * CHUNK_BYTES;    // 128 columns: [0,emb) position, [96,123) view dir, 123/124 = 1; double-buffered
-constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_SCRATCH = OFF_BAR + 512;
-constexpr int SMEM_BYTES = OFF_SCRATCH + 128 * 16;
+constexpr int OFF_E = 0, OFF_W = 2 * E_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_TAIL = OFF_BAR + 256;
 constexpr int VIEW_COL = 96, ONE_COL = 123;  // ONE_COL, ONE_COL+1 hold 1.0 (bias hi / lo)
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, EMB_WARP0 = 10, NUM_EMB_WARPS = 4, THREADS = 448;
 constexpr int NUM_MMA_LAYERS = 10;          // base 0..7, remap, rgb0
 
 // barrier slots
 enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = B_AREADY + 4, B_EEMPTY = B_EFULL + 2,
-       B_ACC = B_EEMPTY + 2, B_COUNT = B_ACC + 4 };
-static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
+       B_ACC = B_EEMPTY + 2, B_RGBREADY = B_ACC + 2, B_RGBFREE = B_RGBREADY + 1, B_COUNT = B_RGBFREE + 1 };
+static_assert(8 * B_COUNT + 8 <= 256, "barrier area");
 
 // fp32 tail of the packed buffer (float offsets)
 constexpr int T_WSIG = 0;                    // 256
@@ -52,6 +51,8 @@ constexpr int T_WRGB2 = 256;                 // 3 x 128
 constexpr int T_BSIG = 256 + 384;
 constexpr int T_BRGB2 = T_BSIG + 1;
 constexpr int T_TOTAL = T_BRGB2 + 3;
+constexpr int SMEM_BYTES = OFF_TAIL + T_TOTAL * 4;   // the fp32 head weights live in shared memory for the whole kernel
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 
 __host__ __device__ constexpr int param_layer(int m) { return m < 8 ? m : m == 8 ? L_REMAP : L_RGB0; }
 
@@ -123,84 +124,107 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 
 // Epilogue of one layer for one thread (= one accumulator row, TMEM lane).  The layer kinds are compile-time variants so
 // that the per-chunk chain  tcgen05.ld -> cvt -> tcgen05.st -> fence -> mbarrier arrive  carries no layer tests: the
-// tensor pipe idles for exactly this chain at every layer boundary (profiles/r1c_*: a generic loop with the layer
-// tests inside ran ~3x longer per chunk than the bare sequence).
+// tensor pipe idles for exactly this chain at every layer boundary (a generic loop with the layer tests inside ran
+// ~3x longer per chunk than the bare sequence).
 //   KIND 0  hidden layer: ReLU + fp16 pack, written back over the fp32 columns just read = next layer's A operand
 //   KIND 1  base layer 7: the same, then the sigma head (nerf_network.py:133) on the fp32 values AFTER the arrive
 //   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
-//   KIND 3  rgb.0: ReLU, then rgb.2 (nerf_network.py:114-117) as fp32 dot products; no A operand follows
-// Chunks [J0, J0 + NCH) of the layer output (the tail-split schedule hands the two column halves over separately).
-template <int KIND, bool SAVE, int J0, int NCH>
+template <int KIND, bool SAVE>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
-                                               float (&rgb_part)[3], long long* probe_slot) {
+                                               long long* probe_slot) {
   uint32_t v[2][32];
-  tmem_ld32(acc_addr + 64u * J0, v[J0 & 1]);
+  tmem_ld32(acc_addr, v[0]);
 #pragma unroll
-  for (int j = J0; j < J0 + NCH; ++j) {
+  for (int j = 0; j < 4; ++j) {       // 64-column chunks of the layer output
     uint32_t (&cur)[32] = v[j & 1];
     tmem_ld_wait(cur);
-    if (j + 1 < J0 + NCH) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
-    if (KIND != 3) {
-      uint32_t pk[16];
+    if (j + 1 < 4) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
+    uint32_t pk[16];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
-      tmem_st16(acc_addr + 64u * j, pk);
-      if (SAVE) store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(aready_bar + 8u * j);
-      if (probe_slot) probe_slot[j] = clock64();
-      if (KIND == 1) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh) + t);
-          s[0] = fmaf(fmaxf(__uint_as_float(cur[4 * t]), 0.f), w4.x, s[0]);
-          s[1] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f), w4.y, s[1]);
-          s[2] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), w4.z, s[2]);
-          s[3] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f), w4.w, s[3]);
-        }
-        sig_part += (s[0] + s[1]) + (s[2] + s[3]);
-      }
-    } else {
-      if (SAVE) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
-        store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
-      }
+    for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
+    tmem_st16(acc_addr + 64u * j, pk);
+    if (SAVE) store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(aready_bar + 8u * j);
+    if (probe_slot) probe_slot[j] = clock64();
+    if (KIND == 1) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const float a0 = fmaxf(__uint_as_float(cur[4 * t]), 0.f), a1 = fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f);
-        const float a2 = fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), a3 = fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 64 * j + 32 * hh) + t);
-          rgb_part[c] = fmaf(a0, w4.x, rgb_part[c]);
-          rgb_part[c] = fmaf(a1, w4.y, rgb_part[c]);
-          rgb_part[c] = fmaf(a2, w4.z, rgb_part[c]);
-          rgb_part[c] = fmaf(a3, w4.w, rgb_part[c]);
-        }
+        const float4 w4 = reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh)[t];
+        s[0] = fmaf(fmaxf(__uint_as_float(cur[4 * t]), 0.f), w4.x, s[0]);
+        s[1] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f), w4.y, s[1]);
+        s[2] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), w4.z, s[2]);
+        s[3] = fmaf(fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f), w4.w, s[3]);
       }
+      sig_part += (s[0] + s[1]) + (s[2] + s[3]);
     }
   }
 }
 
-template <bool SAVE, int J0, int NCH>
+template <bool SAVE>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                   const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
-                                                  float (&rgb_part)[3], long long* probe_slot) {
-  if (m < 7) epilogue_layer<0, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
-  else if (m == 7) epilogue_layer<1, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
-  else if (m == 8) epilogue_layer<2, SAVE, J0, NCH>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
-  else epilogue_layer<3, SAVE, 0, 2>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, rgb_part, probe_slot);
+                                                  long long* probe_slot) {
+  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
+  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
+  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
+}
+
+// Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
+// (ReLU applied here), then the sigmoid (nerf_network.py:139).  Run by the embedding warps, which are idle most of a
+// tile and -- being four consecutive warps -- reach all four TMEM lane quadrants; the epilogue warps go straight on to
+// the next tile.  `free_bar` is arrived on once the last accumulator column is in registers: layer 1 of the next tile
+// (the next writer of this TMEM buffer) waits for it.
+template <bool SAVE>
+__device__ __forceinline__ void rgb_head(uint32_t acc_addr, uint32_t free_bar, int lane, int row, const float* __restrict__ tail,
+                                         uint8_t* act_chunk0, float* __restrict__ out_rgb3) {
+  float acc[3] = {tail[T_BRGB2], tail[T_BRGB2 + 1], tail[T_BRGB2 + 2]};
+  uint32_t v[2][32];
+  tmem_ld32(acc_addr, v[0]);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {       // 32-column pieces
+    uint32_t (&cur)[32] = v[p & 1];
+    tmem_ld_wait(cur);
+    if (p + 1 < 4) {
+      tmem_ld32(acc_addr + 32u * (p + 1), v[(p + 1) & 1]);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(free_bar);
+    }
+    if (SAVE) {     // training keeps relu(rgb.0) like every other layer's activations
+      uint32_t pk[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<true>(cur[2 * t], cur[2 * t + 1]);
+      store_act_chunk(act_chunk0 + (size_t)(p >> 1) * CHUNK_BYTES, row, p & 1, pk);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float a0 = fmaxf(__uint_as_float(cur[4 * t]), 0.f), a1 = fmaxf(__uint_as_float(cur[4 * t + 1]), 0.f);
+      const float a2 = fmaxf(__uint_as_float(cur[4 * t + 2]), 0.f), a3 = fmaxf(__uint_as_float(cur[4 * t + 3]), 0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 w4 = reinterpret_cast<const float4*>(tail + T_WRGB2 + c * RGB_HID + 32 * p)[t];
+        acc[c] = fmaf(a0, w4.x, acc[c]);
+        acc[c] = fmaf(a1, w4.y, acc[c]);
+        acc[c] = fmaf(a2, w4.z, acc[c]);
+        acc[c] = fmaf(a3, w4.w, acc[c]);
+      }
+    }
+  }
+  if (out_rgb3) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out_rgb3[c] = 1.f / (1.f + expf(-acc[c]));
+  }
 }
 
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
-template <bool BG, int CLUSTER, bool TAIL>
+template <bool BG, int CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
@@ -232,7 +256,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(B_EFULL + i), NUM_EMB_WARPS); mbar_init(bar(B_EEMPTY + i), 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACC + i), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACC + i), 1);
+    mbar_init(bar(B_RGBREADY), 1);
+    mbar_init(bar(B_RGBFREE), NUM_EMB_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == LOAD_WARP) {
@@ -247,6 +273,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL + 1)) = __float2half_rn(1.f);
     fence_proxy_async();
   }
+  float* const tail_s = reinterpret_cast<float*>(smem + OFF_TAIL);
+  for (int i = (int)tid_pinned; i < T_TOTAL; i += THREADS) tail_s[i] = tail[i];
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote targets them
@@ -310,134 +338,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (save.e && lane == 0) bulk_s2g(save.e + (size_t)(grp * CLUSTER + (int)cta_rank) * E_BYTES, e_addr, E_BYTES);   // training: keep the E operand
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
         // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
-        if (tile_i > 0) mbar_wait(bar(B_ACC + (TAIL ? 2 : 1)), (tile_i - 1) & 1);
+        if (tile_i > 0) mbar_wait(bar(B_ACC + 1), (tile_i - 1) & 1);
         tc_fence_after();
-        if constexpr (TAIL) {
-          // Tail-split schedule.  An N=128 MMA runs at the same rate per FLOP as an N=256 one (64 vs 128 cycles,
-          // tests/bench_umma.cu), so any part of a layer can be issued as two column halves at no tensor-pipe cost:
-          //   [bias|c0](cols 0-127) [bias|c0](cols 128-255) c1 [c2,c3](cols 0-127) -> ACC_h0 ... [c2,c3](cols 128-255) -> ACC_h1
-          // Columns 0-127 of the layer output are complete 8 MMAs (512 cycles) before the layer ends, so the epilogue's
-          // latency chain for the next layer's first K-chunks runs under MMAs instead of under an idle pipe; and the
-          // next layer begins with column-half MMAs whose accumulator writes (cols 0-127) cannot collide with the
-          // A-operand reads of this layer's tail (chunks 2,3 = cols 128-255 of the same TMEM buffer).
-#pragma unroll 1
-          for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
-            const uint32_t a_tmem = tmem_base + (uint32_t)((m - 1) & 1) * 256u;
-            // before this layer first writes cols 128-255 of its buffer: the previous layer's second half (which read
-            // its A chunks 2,3 from exactly those columns) must have completed
-            auto wait_prev_h1 = [&]() {
-              if (m == 0) return;
-              const int l = m - 1, k = l >> 1;
-              if (l & 1) mbar_wait(bar(B_ACC + 3), (uint32_t)k & 1u); else mbar_wait(bar(B_ACC + 1), (tile_i + (uint32_t)k) & 1u);
-              tc_fence_after();
-            };
-            if (m == 9) {                // rgb.0, N=128: view/bias columns of E, then the 4 A chunks
-              if (save.e && lane == 0) bulk_s2g_wait_read();
-              __syncwarp();
-              wait_stage();
-              if (elect_one()) {
-                const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
-                mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, ID128);
-                mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, ID128);
-                release(wempty);
-                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer (the bulk store below was waited for)
-              }
-              __syncwarp();
-              advance();
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
-                tc_fence_after();
-                if (elect_one()) {
-                  ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), ID128);
-                  release(wempty);
-                  if (c == 3) tc_commit(bar(B_ACC + 2));
-                }
-                __syncwarp();
-                advance();
-              }
-              a_par ^= 1;
-              continue;
-            }
-            if (m == 0 || m == 5) {      // bias + embedding chunks, both column halves (independent of the epilogue)
-              wait_stage();
-              const uint32_t slot0 = slot, wempty_e0 = wempty;
-              if (E_CHUNKS == 2) { advance(); wait_stage(); }   // second E tile = next stage; both stay live
-              const uint32_t slot1 = slot;
-#pragma unroll
-              for (int hN = 0; hN < 2; ++hN) {
-                if (hN == 1) wait_prev_h1();
-                if (elect_one()) {
-                  const uint32_t d = d_tmem + 128u * hN;
-                  mma_ss<0>(d, one_lo, SW128_HI, bias_lo(slot0, 256) + 128u * hN, NOSW_HI, ID128);
-#pragma unroll
-                  for (int c = 0; c < E_CHUNKS; ++c) {
-                    const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo((c ? slot1 : slot0) + AUX_BYTES) + 1024u * hN;
-#pragma unroll
-                    for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, ID128);
-                  }
-                  if (m == 0) tc_commit(bar(B_ACC + hN));
-                  if (hN == 1) { if (E_CHUNKS == 2) release(wempty_e0); release(wempty); }
-                }
-                __syncwarp();
-              }
-              advance();
-              if (m == 0) continue;
-            }
-            // ---- A chunks: c0 as column halves (m != 5: with the bias), c1 whole, c2/c3 as column halves ----
-            mbar_wait2(bar(B_AREADY + 0), a_par, wfull, ph);
-            tc_fence_after();
-            if (timing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * (int)cta_pinned + 4] = clock64();
-            if (elect_one()) {
-              const uint32_t blo = sw128_lo(slot + AUX_BYTES);
-              if (m != 5) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, ID128);
-              ts4(d_tmem, a_tmem, blo, ID128);
-            }
-            __syncwarp();
-            if (m != 5) wait_prev_h1();
-            if (elect_one()) {
-              const uint32_t blo = sw128_lo(slot + AUX_BYTES) + 1024u;
-              if (m != 5) mma_ss<0>(d_tmem + 128u, one_lo, SW128_HI, bias_lo(slot, 256) + 128u, NOSW_HI, ID128);
-              ts4(d_tmem + 128u, a_tmem, blo, ID128);
-              release(wempty);
-            }
-            __syncwarp();
-            advance();
-            mbar_wait2(bar(B_AREADY + 1), a_par, wfull, ph);
-            tc_fence_after();
-            if (elect_one()) {
-              ts4(d_tmem, a_tmem + 64u, sw128_lo(slot + AUX_BYTES), ID256);
-              release(wempty);
-            }
-            __syncwarp();
-            advance();
-            {
-              // stages of c2 and c3 are both live until the second column half has been issued
-              const uint32_t slot2 = slot, wempty2 = wempty;
-              mbar_wait2(bar(B_AREADY + 2), a_par, wfull, ph);
-              advance();
-              mbar_wait2(bar(B_AREADY + 3), a_par, wfull, ph);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t b2 = sw128_lo(slot2 + AUX_BYTES), b3 = sw128_lo(slot + AUX_BYTES);
-                const uint32_t a2 = a_tmem + 128u, a3 = a_tmem + 192u;
-                ts4(d_tmem, a2, b2, ID128);
-                ts4(d_tmem, a3, b3, ID128);
-                tc_commit(bar(B_ACC + (m & 1) * 2));
-                ts4(d_tmem + 128u, a2, b2 + 1024u, ID128);
-                release(wempty2);
-                ts4(d_tmem + 128u, a3, b3 + 1024u, ID128);
-                release(wempty);
-                tc_commit(bar(B_ACC + (m & 1) * 2 + 1));
-              }
-              __syncwarp();
-              advance();
-              if (timing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * (int)cta_pinned + (m == 2 ? 0 : 12)] = clock64();
-            }
-            a_par ^= 1;
-          }
-        } else {
 #pragma unroll 1
           for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(m & 1) * 256u;
@@ -474,20 +376,31 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               advance();
             }
             if (m != 0) {
-              const bool need_bias = (m != 5 && m != 9);
+              const bool early_bias = (m != 1 && m != 5 && m != 9);
+              if (early_bias) {
+                // The bias MMA does not depend on the epilogue, so it runs under the epilogue's latency chain -- once the
+                // previous layer has completed (it overwrites the accumulator buffer that layer's MMAs read their A operand
+                // from).  Not for layer 1: its buffer still holds the previous tile's rgb.0 accumulators until the colour
+                // head has read them (B_RGBFREE); there the bias goes with chunk 0.
+                mbar_wait2(bar(B_ACC + ((m - 1) & 1)), (tile_i + (uint32_t)((m - 1) >> 1)) & 1u, wfull, ph);
+                tc_fence_after();
+                if (elect_one()) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                __syncwarp();
+              }
+              if (m == 1 && tile_i > 0) mbar_wait(bar(B_RGBFREE), (tile_i - 1) & 1);   // previous tile's rgb.0 accumulators have been read
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                // (The bias MMA must not be hoisted above the AREADY wait: it overwrites the accumulator buffer the
-                //  previous layer's last MMAs still read their A operand from, and consecutive tcgen05.mma are not
-                //  interlocked on TMEM A-read vs D-write.)
                 mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
                 tc_fence_after();
                 if (probing && lane == 0 && tile_i == 5 && m == 3) dbg[14 * 148 + 16 * (int)cta_pinned + 4 + c] = clock64();
                 if (elect_one()) {
-                  if (c == 0 && need_bias) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
+                  if (c == 0 && m == 1) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
                   ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), idesc);
                   release(wempty);
-                  if (c == 3) tc_commit(bar(B_ACC + (m & 1)));
+                  if (c == 3) {
+                    tc_commit(bar(B_ACC + (m & 1)));
+                    if (m == 9) tc_commit(bar(B_RGBREADY));   // the colour head (embedding warps) has its own barrier: one phase per tile
+                  }
                 }
                 __syncwarp();
                 advance();
@@ -495,19 +408,34 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               a_par ^= 1;
             }
             if (probing && lane == 0 && tile_i == 5 && (m == 2 || m == 3)) dbg[14 * 148 + 16 * (int)cta_pinned + (m == 2 ? 0 : 12)] = clock64();
+            if (probing && lane == 0 && (tile_i == 5 || (tile_i == 6 && m < 2))) dbg[32 * 148 + 40 * (int)cta_pinned + m + (tile_i == 6 ? 30 : 0)] = clock64();   // whole-tile timeline
           }
-        }
       }
       if (probing && lane == 0) dbg[8 * (int)cta_pinned] = clock64() - t0;
     }
   } else if (warp >= EMB_WARP0) {
-    // ================= embedding producers: E operand of the NEXT tile while the current one runs ======
+    // ================= embedding producers: E operand of the NEXT tile while the current one runs; =====
+    // ================= then the colour head of the tile that has just finished                      =====
     const int row = (int)tid_pinned - EMB_WARP0 * 32;    // 0..127
+    const int hq = warp & 3, hrow = hq * 32 + lane;      // colour head: the TMEM lane quadrant this warp can address
+    const uint32_t rgb0_addr = tmem_base + ((uint32_t)(hq * 32) << 16) + 256u;   // rgb.0 accumulators: buffer 1, columns [0,128)
     uint32_t tile_i = 0;
     long long m_t0 = clock64(), m_wait = 0, mtt = 0;
+    auto tile_of = [&](uint32_t ti) { return (group0 + (int)ti * group_step) * CLUSTER + (int)cta_rank; };
+    auto colour_head = [&](int tile, uint32_t ti) {
+      mbar_wait(bar(B_RGBREADY), ti & 1);
+      tc_fence_after();
+      const long long hg = (long long)tile * TILE + hrow;
+      float* const dst = hg < total ? out_rgb + 3 * hg : nullptr;
+      if (save.act) rgb_head<true>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0), dst);
+      else rgb_head<false>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, nullptr, dst);
+    };
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
       const uint32_t eb = tile_i & 1;
       const int tile = grp * CLUSTER + (int)cta_rank;
+      // tile_i - 2 finishes its layer 9 about when it releases the E buffer this iteration refills: the colour head is
+      // the urgent one (layer 1 of tile_i - 1 waits for it), the embedding is not needed for another tile
+      if (tile_i >= 2) colour_head(tile_of(tile_i - 2), tile_i - 2);
       if (timing) mtt = clock64();
       mbar_wait(bar(B_EEMPTY + eb), ((tile_i >> 1) & 1) ^ 1);
       if (timing) m_wait += clock64() - mtt;
@@ -537,6 +465,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EFULL + eb));
     }
+    for (uint32_t ti = tile_i >= 2 ? tile_i - 2 : 0; ti < tile_i; ++ti) colour_head(tile_of(ti), ti);
     if (timing && (int)tid_pinned == EMB_WARP0 * 32) { dbg[8 * (int)cta_pinned + 4] = clock64() - m_t0; dbg[8 * (int)cta_pinned + 7] = m_wait; }
   } else {
     // ================= epilogue warps =================
@@ -549,58 +478,62 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_par = 0;
     long long e_wait = 0, e_t0 = clock64(), ett = 0;
+    float pend = 0.f;            // raw sigma of the previous tile's row, written out under the next tile's layer-1 MMAs
+    long long pend_g = -1;
+    auto flush_pending = [&]() {
+      if (pend_g >= 0) {
+        out_sigma[pend_g] = fabsf(pend);
+        if (save.raw_sigma) save.raw_sigma[pend_g] = pend;
+        pend_g = -1;
+      }
+    };
     for (int grp = group0; grp < n_groups; grp += group_step) {
       const int tile = grp * CLUSTER + (int)cta_rank;
       const long long g = (long long)tile * TILE + row;
       const bool valid = g < total;
-      float sig_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+      float sig_part = 0.f;
       long long* const probe_base = (probing && (int)tid_pinned == 0 && grp == group0 + 5 * group_step) ? dbg + 14 * 148 + 16 * (int)cta_pinned : nullptr;
       uint8_t* const act_tile = save.act ? save.act + act_chunk_off(0, (size_t)num_tiles, (size_t)tile, 0) : nullptr;
       const size_t act_layer_stride = act_layer_off(1, (size_t)num_tiles);
-      constexpr int UNITS = TAIL ? 2 * NUM_MMA_LAYERS - 1 : NUM_MMA_LAYERS;   // (layer, column half) accumulations per tile
 #pragma unroll 1
-      for (int un = 0; un < UNITS; ++un) {
-        const int m = TAIL ? (un >> 1) : un, h = TAIL ? (un & 1) : 0;
-        const int ab = TAIL ? (m & 1) * 2 + h : (m & 1);
+      for (int m = 0; m < NUM_MMA_LAYERS - 1; ++m) {       // rgb.0 (layer 9) is read by the colour head, not here
+        const int ab = m & 1;
         if (timing) ett = clock64();
         mbar_wait(bar(B_ACC + ab), (acc_par >> ab) & 1u);
         if (timing) e_wait += clock64() - ett;
         acc_par ^= 1u << ab;
         tc_fence_after();
-        long long* const probe = (probe_base && m == 2 && h == 0) ? probe_base + 8 : nullptr;
+        long long* const probe = (probe_base && m == 2) ? probe_base + 8 : nullptr;
         if (probe) probe_base[1] = clock64();
-        const uint32_t acc_addr = lane_addr + (uint32_t)((m & 1) * 256 + 32 * hh);
-        const uint32_t aready = bar(B_AREADY);
-        uint8_t* const act = !act_tile ? nullptr : (m == 9) ? save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0) : act_tile + m * act_layer_stride;
-        if (TAIL) {
-          if (act) {
-            if (h == 0) epilogue_dispatch<true, 0, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-            else epilogue_dispatch<true, 2, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-          } else {
-            if (h == 0) epilogue_dispatch<false, 0, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-            else epilogue_dispatch<false, 2, 2>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-          }
-        } else {
-          if (act) epilogue_dispatch<true, 0, 4>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-          else epilogue_dispatch<false, 0, 4>(m, acc_addr, aready, lane, row, hh, tail, act, sig_part, rgb_part, probe);
-        }
+        if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 10 + m] = clock64();
+        const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
+        if (act_tile) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride, sig_part, probe);
+        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, sig_part, probe);
+        if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
+        if (m == 0) flush_pending();
       }
-      // ---- combine the two column halves of each row, write sigma / rgb -------------------------------
-      float4* scratch = reinterpret_cast<float4*>(smem + OFF_SCRATCH);
-      if (hh == 1) scratch[row] = make_float4(sig_part, rgb_part[0], rgb_part[1], rgb_part[2]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (hh == 0 && valid) {
-        float4 p = scratch[row];
-        const float raw_sigma = sig_part + p.x + tail[T_BSIG];
-        out_sigma[g] = fabsf(raw_sigma);
-        if (save.raw_sigma) save.raw_sigma[g] = raw_sigma;
-        float c0 = rgb_part[0] + p.y + tail[T_BRGB2], c1 = rgb_part[1] + p.z + tail[T_BRGB2 + 1], c2 = rgb_part[2] + p.w + tail[T_BRGB2 + 2];
-        out_rgb[3 * g] = 1.f / (1.f + expf(-c0));
-        out_rgb[3 * g + 1] = 1.f / (1.f + expf(-c1));
-        out_rgb[3 * g + 2] = 1.f / (1.f + expf(-c2));
+      // layer 9's phase of accumulator barrier 1 is not waited for here; it has completed by the time this warp next
+      // waits on that barrier (layer 1 of the next tile is issued behind the next layer 0, whose completion it awaits first)
+      acc_par ^= 2u;
+      // ---- combine the two column halves of sigma -------------------------------------------------------
+      // Warps w and w+4 own the same TMEM lanes, so the hh = 1 partial sum crosses over through TMEM columns that are
+      // free between base_remap and the next tile's layer 1 (buffer 1, columns 128-131).
+      const uint32_t xaddr = lane_addr + 256u + 128u;
+      if (hh == 1) {
+        tmem_st4(xaddr, __float_as_uint(sig_part), 0u, 0u, 0u);
+        tmem_st_wait();
       }
+      tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc_fence_after();
+      if (hh == 0) {
+        uint32_t p[4];
+        tmem_ld4_sync(xaddr, p);
+        pend = sig_part + __uint_as_float(p[0]) + tail_s[T_BSIG];
+        pend_g = valid ? g : -1;
+      }
     }
+    flush_pending();
     if (timing && (int)tid_pinned == 0) {
       dbg[8 * (int)cta_pinned + 5] = clock64() - e_t0; dbg[8 * (int)cta_pinned + 6] = e_wait;
     }
@@ -677,14 +610,13 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
 using namespace npp;
 
 static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1 or 2)
-static int g_tail = -1;         // MMA schedule: 0 = whole layers (default, faster as measured), 1 = tail-split; NERFPP_TC_TAIL overrides
 static long long* g_dbg = nullptr;
 static int g_flags = 0;          // experiment switches (diagnostics only)
 
 static void tc_config() {
-  if (g_tail >= 0) return;
-  const char* e = getenv("NERFPP_TC_TAIL");
-  g_tail = e ? (atoi(e) != 0) : 0;
+  static bool done = false;
+  if (done) return;
+  done = true;
   if (const char* f = getenv("NERFPP_TC_FLAGS")) g_flags = atoi(f);
   if (g_cluster < 0) {
     const char* c = getenv("NERFPP_TC_CLUSTER");
@@ -703,10 +635,10 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
   return 0;
 }
 
-template <bool BG, int CLUSTER, bool TAIL>
+template <bool BG, int CLUSTER>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, tc::TrainSave save, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER, TAIL>;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER>;
   static bool configured = false;
   static int max_clusters = 0;
   if (!configured) {
@@ -757,10 +689,8 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     uint8_t* w = (uint8_t*)train_ws;
     save.act = w; save.e = w + tc::train_ws_e_off((size_t)num_tiles); save.raw_sigma = (float*)(w + tc::train_ws_sigma_off((size_t)num_tiles));
   }
-#define NPP_TC_LAUNCH(BG, C, H) launch_tc<BG, C, H>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
-#define NPP_TC_LAUNCH_H(BG, C) (g_tail ? NPP_TC_LAUNCH(BG, C, true) : NPP_TC_LAUNCH(BG, C, false))
-  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH_H(true, 1) : NPP_TC_LAUNCH_H(true, 2);
-  return g_cluster == 1 ? NPP_TC_LAUNCH_H(false, 1) : NPP_TC_LAUNCH_H(false, 2);
-#undef NPP_TC_LAUNCH_H
+#define NPP_TC_LAUNCH(BG, C) launch_tc<BG, C>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
+  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1) : NPP_TC_LAUNCH(true, 2);
+  return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1) : NPP_TC_LAUNCH(false, 2);
 #undef NPP_TC_LAUNCH
 }

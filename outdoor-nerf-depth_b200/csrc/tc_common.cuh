@@ -135,6 +135,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
                  "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                :: "memory");
 }
+// four columns of the warp's 32 TMEM lanes (one value per lane and column)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_sync(uint32_t taddr, uint32_t (&v)[4]) {   // load + wait::ld
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 // two fp32 -> packed fp16x2 (lo in the low half), optionally through ReLU, one instruction
 template <bool RELU>
 __device__ __forceinline__ uint32_t pack_f16x2(uint32_t lo, uint32_t hi) {

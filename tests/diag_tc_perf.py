@@ -28,7 +28,7 @@ for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_
     packed = net._packed[is_bg].get(tensors, FIELD_TC)
     for cl in [int(x) for x in os.environ.get("CLUSTERS", "1,2,4").split(",")]:
         L.nerfpp_debug_set_tc_cluster(cl)
-        dbg = torch.zeros(30 * 148, dtype=torch.int64, device=dev)
+        dbg = torch.zeros(80 * 148, dtype=torch.int64, device=dev)
         L.nerfpp_debug_set_tc_timers(ctypes.c_void_p(dbg.data_ptr()) if os.environ.get('TIMERS', '1') == '1' else None)
         try:
             for _ in range(3):
@@ -43,13 +43,19 @@ for is_bg, z, tensors, macs in ((0, fg_z, net.fg_net.tensors(), 593408), (1, bg_
             sig, rgb, dr = ops.field_forward(packed, is_bg, o, d, z, FIELD_TC)
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
-        extra = dbg.cpu().numpy()[8 * 148:10 * 148].reshape(-1, 2); ep = dbg.cpu().numpy()[10 * 148:14 * 148].reshape(-1, 4); pr = dbg.cpu().numpy()[14 * 148:].reshape(-1, 16); t = dbg.cpu().numpy()[:8 * 148].reshape(-1, 8)
+        extra = dbg.cpu().numpy()[8 * 148:10 * 148].reshape(-1, 2); ep = dbg.cpu().numpy()[10 * 148:14 * 148].reshape(-1, 4); pr = dbg.cpu().numpy()[14 * 148:30 * 148].reshape(-1, 16); tl = dbg.cpu().numpy()[32 * 148:72 * 148].reshape(-1, 40); t = dbg.cpu().numpy()[:8 * 148].reshape(-1, 8)
         t = t[t[:, 0] > 0] if (t[:, 0] > 0).any() else t[:1]
         print("   issue(incl A waits) %.0f  commits %.0f" % (extra[:, 0].mean(), extra[:, 1].mean()), " epi: ld-wait %.0f cvt %.0f st %.0f arrive %.0f" % tuple(ep.mean(0)))
         if pr[:, 0].any():
             q = pr[pr[:, 0] > 0]
             rel = (q - q[:, :1]).mean(0)
             print("   chain (cycles after ACC commit of layer 2): epi wake %.0f | epi arrive c0..3 %s | mma past AREADY c0..3 %s | layer 3 ACC commit issued %.0f | chunk 0: ld done %.0f cvt done %.0f st done %.0f" % (rel[1], rel[8:12].round(), rel[4:8].round(), rel[12], rel[2], rel[3], rel[13]))
+        if tl[:, 0].any():
+            q = tl[tl[:, 0] > 0].astype(np.float64)
+            rel = (q - q[:, :1]).mean(0)
+            print("   tile timeline (cycles after layer-0 ACC commit issue): mma commit issued L0..9 %s | next tile L0,L1 %s" % (rel[0:10].round(), rel[30:32].round()))
+            print("       epilogue wake L0..9 %s" % rel[10:20].round())
+            print("       epilogue done L0..9 %s" % rel[20:30].round())
         key = (is_bg,)
         if key not in ref:
             ref[key] = (sig.clone(), rgb.clone())
