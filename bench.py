@@ -34,8 +34,8 @@ DEPTH_SIGMA, DEPTH_SCALE = 0.01, 0.05
 MACS_FG, MACS_BG = 593408, 604160      # per sample, SURVEY.md section 8(d)
 METRIC = "rays/sec (4096 rays x 128 samples, 8x256 MLP)"
 # dram__bytes_read.sum + dram__bytes_write.sum of field_tc_kernel, mean of the step's four launches, from the
-# `ncu --set full` capture summarised in profiles/r1b_field_tc_ncu.txt (weights + ray inputs; the outputs stay in L2)
-NCU_DRAM_BYTES_PER_LAUNCH = 3.56e6
+# `ncu --set full` capture summarised in profiles/r1c_field_tc_ncu.txt (weights + ray inputs; the outputs stay in L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 3.60e6
 WORKLOAD = ("NeRF++ configs[1]: 4096 rays/GPU, cascade 64 -> +128 (192 fine) fg and bg, depth_loss=mse lambda=0.1, "
             "forward of both levels + sampling + composite + losses")
 

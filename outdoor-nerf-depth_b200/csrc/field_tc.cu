@@ -3,23 +3,24 @@
 // One persistent CTA per SM walks 128-sample tiles (samples of all rays packed along the MMA M
 // axis).  Per tile the ten dense layers (base 0..7, base_remap, rgb.0) run as tcgen05.mma
 // (M=128, N=256|128, K=16, fp16 operands, fp32 accumulators in TMEM); sigma (256->1) and rgb.2
-// (128->3) are fp32 dot products in the epilogue on the fp32 accumulators.
-// (N=128 halves would let the epilogue of one half hide under the MMAs of the other, but at M=128 an
-// N=128 MMA is operand-bandwidth bound -- measured 2x slower per FLOP -- so layers stay N=256.)
+// (128->3) are fp32 dot products on the fp32 accumulators.
+// (N=128 column halves would let the epilogue of one half hide under the MMAs of the other; measured, the
+// overlap is cancelled by the slower epilogue/issue under a busy pipe -- DESIGN.md 4.1 -- so layers stay N=256.)
 //
 // The bias is part of the contraction: the E operand carries two constant-one columns and every
-// layer starts with a K=16 MMA against a [N x 16] tile holding the bias split into fp16 hi + lo,
-// so the epilogue is TMEM load -> cvt.rn.relu.f16x2 -> TMEM store and nothing else; the bias and
-// embedding steps of layer l+1 do not depend on layer l and run under its epilogue latency.
+// layer has a K=16 MMA against a [N x 16] tile holding the bias split into fp16 hi + lo, so the
+// epilogue is TMEM load -> cvt.rn.relu.f16x2 -> TMEM store and nothing else; the bias and embedding
+// MMAs of layer l+1 do not depend on layer l's epilogue and run under its latency.
 //
 //   warp 0-7   epilogue: per layer TMEM -> regs, ReLU + fp16 pack -> written back to TMEM in place as
-//              the A operand of the next layer, 64 columns at a time
+//              the A operand of the next layer, 64 columns at a time; sigma head after layer 7
 //   warp 8     one lane issues every tcgen05.mma (A from TMEM or the E tile, B from shared memory);
 //              layer l+1's K-chunk j starts as soon as the epilogue of layer l has produced columns
 //              [64j,64j+64) (two TMEM accumulators ping-pong between consecutive layers)
 //   warp 9     one lane streams the pre-swizzled weight tiles (in MMA issue order) from L2 into a
 //              4 x 40 KB shared-memory ring with cp.async.bulk (+cluster multicast) and mbarriers
-//   warp 10-13 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128)
+//   warp 10-13 positional encoding of the NEXT tile into the double-buffered E operand (fp16, SW128);
+//              colour head (ReLU, rgb.2, sigmoid) of the tile that has just finished, from TMEM
 //
 // Shared memory (bytes): E 2x32K | ring 4x40K | barriers | fp32 head weights.  TMEM: 2 x 256 columns.
 // Precision: operands are rounded to fp16 (11-bit significand), products/sums are fp32; measured
