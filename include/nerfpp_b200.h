@@ -223,6 +223,15 @@ int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, float cam_dep
                     float* ray_o, float* ray_d, float* depth, float* rgb, float* depth_sup, float* min_depth,
                     void* stream);
 
+/* ---- N2: pixel decode of the on-disk formats ------------------------------------------------ */
+/* RaySamplerSingleImage.set_resolution_level (nerf_sample_ray_split.py:73-102) turns the PNGs that load_data_split
+ * (data_loader_split.py:27-129) found into float arrays on the host: rgb/mask = u8/255, min depth = u8/255*max_depth+1e-4,
+ * depth{,_<type>} = depth_scale * (u16/256).  Here the raw pixels are uploaded as they are (1-2 bytes each) and decoded on
+ * the device: out[i] = ((src[i] / div) * mul) + add, each step rounded to fp32 in numpy's order (bit-exact).
+ * src: device, src_bits = 8 (uint8) or 16 (uint16); n elements. */
+int nerfpp_decode_pixels(const void* src, int src_bits, int64_t n, float div, float mul, float add, float* out,
+                         void* stream);
+
 /* ---- N3: image metrics of the test loop (ddp_train_nerf.py:556-600) -------------------- */
 /* out_metrics[8] (device) = mse, psnr = -10 log10(mse + 1e-6), #valid depth pixels, rmse, rmse_log, abs_diff, abs_rel,
  * sq_rel; depth metrics over pixels with 1e-3 < gt/depth_scale < cap (cap = 80 m in the reference), both sides clipped to

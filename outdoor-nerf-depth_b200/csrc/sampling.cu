@@ -291,3 +291,27 @@ extern "C" int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, fl
   NPP_CHECK_LAUNCH();
   return 0;
 }
+
+// ---- N2: pixel decode of the on-disk formats (nerf_sample_ray_split.py:73-102) -------------------------------------
+// out = ((x / div) * mul) + add with every step rounded to fp32, the order numpy evaluates
+//   rgb / mask  imread(...).astype(float32) / 255.                      (div 255, mul 1, add 0)      :73,80
+//   min depth   imread(...).astype(float32) / 255. * max_depth + 1e-4   (div 255, mul max, add 1e-4) :87
+//   depth       depth_scale * (imread(...).astype(float32) / 256.0)     (div 256, mul scale, add 0)  :94-102
+// (x * 1 and x + 0 are exact, so one kernel serves all three.)
+template <typename T>
+__global__ void decode_pixels_kernel(const T* __restrict__ src, long long n, float div, float mul, float add, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __fadd_rn(__fmul_rn(__fdiv_rn((float)src[i], div), mul), add);
+}
+
+extern "C" int nerfpp_decode_pixels(const void* src, int src_bits, int64_t n, float div, float mul, float add, float* out, void* stream) {
+  NPP_CHECK_ARG(src && out && n >= 0 && (src_bits == 8 || src_bits == 16) && div != 0.f, "bad argument");
+  if (n == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (src_bits == 8) decode_pixels_kernel<uint8_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, n, div, mul, add, out);
+  else decode_pixels_kernel<uint16_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, n, div, mul, add, out);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}

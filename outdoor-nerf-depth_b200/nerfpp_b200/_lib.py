@@ -66,6 +66,7 @@ SIGNATURES = {
     "nerfpp_depth_loss": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     "nerfpp_depth_loss_backward": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P]),
     "nerfpp_gen_rays": (c_int, [P, P, c_float, c_int, P, c_int64, P, P, P, P, P, P, P, P, P, P]),
+    "nerfpp_decode_pixels": (c_int, [P, c_int, c_int64, c_float, c_float, c_float, P, P]),
     "nerfpp_image_metrics": (c_int, [P, P, P, P, c_int64, c_float, c_float, P, P, P]),
     "mip360_sample_intervals": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, P, P]),
     "mip360_compute_alpha_weights": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),

@@ -26,7 +26,14 @@ def render_backward(params, inputs, outs, ws, tws, grads):
     ost = _lib.RenderOut()
     for k in RET_KEYS:
         setattr(ost, k, outs[k].data_ptr())
-    pgrads = [torch.zeros_like(p) for p in params]
+    # one zero-filled buffer for all 48 gradients (the wgrad kernels accumulate with red.global.add): one fill kernel
+    # instead of 48; every tensor starts on a 16-byte boundary
+    sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    pgrads, off = [], 0
+    for p, sz in zip(params, sizes):
+        pgrads.append(flat[off:off + p.numel()].view(p.shape))
+        off += sz
     gfg, gbg = _lib.NetGrads(), _lib.NetGrads()
     for l in range(_lib.NLAYERS):
         gfg.w[l], gfg.b[l] = pgrads[2 * l].data_ptr(), pgrads[2 * l + 1].data_ptr()
