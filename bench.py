@@ -87,8 +87,23 @@ class ClockSampler:
 
 
 def make_rays(n, seed):
-    import nerfpp_oracle as O   # synthetic workload generator only (inputs, not results)
-    return O.synthetic_rays(n, seed=seed, depth_scale=DEPTH_SCALE)
+    """SURVEY.md section 8(d) synthetic batch (host tensors): origins inside the ball of radius 0.5, un-normalised
+    directions, rgb ~ U[0,1], depth prior = far * U with every 5th ray invalid (0).  Same draws as the oracle's
+    ``synthetic_rays`` (the cpu_baseline leg uses that one), restated here so this arm never imports oracle/."""
+    g = torch.Generator().manual_seed(seed)
+    dirs = torch.randn(n, 3, generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    ray_o = dirs * (0.5 * torch.rand(n, 1, generator=g) ** (1.0 / 3.0))
+    d = torch.randn(n, 3, generator=g)
+    ray_d = d / d.norm(dim=-1, keepdim=True) * (1.0 + 0.2 * torch.rand(n, 1, generator=g))
+    rgb = torch.rand(n, 3, generator=g)
+    d1 = -(ray_d * ray_o).sum(-1) / (ray_d * ray_d).sum(-1)              # ddp_train_nerf.py:57-64
+    pm = ray_o + d1[:, None] * ray_d
+    far = d1 + torch.sqrt(1.0 - (pm * pm).sum(-1)) / ray_d.norm(dim=-1)
+    depth_sup = far * torch.rand(n, generator=g)
+    depth_sup[::5] = 0.0
+    return dict(ray_o=ray_o.contiguous(), ray_d=ray_d.contiguous(), min_depth=torch.full((n,), 1e-4), rgb=rgb,
+                depth_sup=depth_sup, depth_scale=DEPTH_SCALE)
 
 
 def make_models(device):
@@ -106,7 +121,7 @@ def make_models(device):
 
 def run_ours(args):
     import nerfpp_b200
-    from nerfpp_b200 import _lib, ops, render_rays
+    from nerfpp_b200 import GraphedRenderStep, _lib, ops, render_rays
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -123,21 +138,35 @@ def run_ours(args):
     host = make_rays(N_RAYS, seed=rank)                 # this rank's band of the global 4096*world batch
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    gathered = torch.empty(world * N_RAYS, 4, device=dev) if world > 1 else None
+    gathered = torch.empty(world * N_RAYS * 4, device=dev) if world > 1 else None   # per rank: rgb [n,3] | depth [n]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     pending_flag = [None]
+    step_kw = dict(cascade_samples=CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA)
+    graphed = not args.no_graph
+    g_dev = g_host = None
+    if graphed:
+        # the step captured once into a CUDA graph (nerfpp_b200.graph): one launch per step instead of ~14 through Python
+        g_dev = GraphedRenderStep(models, N_RAYS, depth_scale=DEPTH_SCALE, host_io=False, device=dev, **step_kw)
+        for k, v in g_dev.dev_in.items():
+            v.copy_(batch[k])
+        g_host = GraphedRenderStep(models, N_RAYS, depth_scale=DEPTH_SCALE, host_io=True, device=dev, **step_kw)
 
     def step(b):
+        """One pass over this rank's 4096 rays with the inputs resident in HBM."""
         with torch.no_grad():
+            if graphed:
+                out = g_dev()                            # inputs: g_dev.dev_in (filled once above)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, g_dev._packed[:4 * N_RAYS])
+                return out
             if pending_flag[0] is not None:          # the previous step's out-of-sphere flag (its work is long done)
                 pending_flag[0].raise_if_set()
-            res = render_rays(models, b, CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH,
-                              depth_sigma=DEPTH_SIGMA, defer_unbounded_check=True)
+            res = render_rays(models, b, defer_unbounded_check=True, **step_kw)
             pending_flag[0] = res["unbounded"]
             ret = res["levels"][-1][0]
             if world > 1:
-                tile = torch.cat((ret["rgb"], ret["depth"][:, None]), -1)
+                tile = torch.cat((ret["rgb"].reshape(-1), ret["depth"]))
                 dist.all_gather_into_tensor(gathered, tile)
         return res, ret
 
@@ -163,6 +192,8 @@ def run_ours(args):
         barrier()
         t_wall = time.perf_counter() - t_wall
     launches = ops.LAUNCHES[0]
+    if graphed:
+        g_dev.check_unbounded()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -173,6 +204,13 @@ def run_ours(args):
 
     # ---- e2e: pinned host buffers -> H2D -> path -> D2H of rgb/depth/loss, wall clock ----
     def e2e_step():
+        """The same pass from HOST buffers to HOST results: H2D of the batch, the path, D2H of rgb/depth/losses."""
+        if graphed:
+            out = g_host(host)                       # host -> pinned staging -> (graph: H2D, kernels, D2H) -> pinned -> sync
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, g_host._packed[:4 * N_RAYS])
+                return gathered.cpu(), out["losses"]
+            return out["rgb"], out["losses"]
         b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
         res, ret = step(b)
         out = torch.cat((ret["rgb"], ret["depth"][:, None]), -1) if world == 1 else gathered
@@ -194,6 +232,8 @@ def run_ours(args):
     e2e_value = world * N_RAYS * args.steps / float(t_e2e.item())
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     d2h = (world * N_RAYS * 4 * 4 if world > 1 else N_RAYS * 4 * 4) + 2 * 4 * 4
+    if graphed:   # the graph's one D2H (rgb, depth, 2 x 4 losses, flag), plus the gathered tiles when N > 1
+        d2h = g_host._n_out * 4 + (world * N_RAYS * 4 * 4 if world > 1 else 0)
 
     # ---- informational: one trainer step (ddp_train_nerf.py:432-498: per level forward, loss, backward, Adam) ----
     train = train_step_rate(models, batch, dev) if (world == 1 and not args.no_train) else None
@@ -210,7 +250,9 @@ def run_ours(args):
                        "cascade_samples": list(CASCADE), "unit_of_work": "U2 forward (SURVEY 8(d)): 2.512 TFLOP algorithmic per 4096 rays",
                        "l2": "flushed between timed steps (256 MiB write)", "field": "tcgen05" if ops.default_field_impl() == 0 else "simt",
                        "parallelism": "rays sharded in contiguous bands, %d rank(s), 1 NCCL all-gather/step" % world if world > 1 else "single GPU",
-                       "wall_s_timed_region": t_wall},
+                       "wall_s_timed_region": t_wall,
+                       "launch": ("one CUDA graph per step (%d library kernels + torch rand/cat nodes)" % g_dev.kernels_per_replay) if graphed
+                       else "eager: one Python call per kernel"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -364,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--no-train", action="store_true", help="skip the informational trainer-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":

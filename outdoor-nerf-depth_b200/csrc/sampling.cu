@@ -306,8 +306,9 @@ __global__ void decode_pixels_kernel(const T* __restrict__ src, long long n, flo
 }
 
 extern "C" int nerfpp_decode_pixels(const void* src, int src_bits, int64_t n, float div, float mul, float add, float* out, void* stream) {
-  NPP_CHECK_ARG(src && out && n >= 0 && (src_bits == 8 || src_bits == 16) && div != 0.f, "bad argument");
-  if (n == 0) return 0;
+  NPP_CHECK_ARG(n >= 0 && (src_bits == 8 || src_bits == 16) && div != 0.f, "bad argument");
+  if (n == 0) return 0;                         // an empty image: nothing to launch (the pointers may be null)
+  NPP_CHECK_ARG(src && out, "null pointer");
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (src_bits == 8) decode_pixels_kernel<uint8_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, n, div, mul, add, out);

@@ -1,6 +1,7 @@
 """Backward of NerfNet.forward through the CUDA library (nerfpp_backward): composite backward, then per net the
 tcgen05 data-gradient chain and the split-K weight-gradient GEMMs.  No PyTorch fallback."""
 import ctypes
+import os
 
 import torch
 
@@ -29,11 +30,14 @@ def render_backward(params, inputs, outs, ws, tws, grads):
     # one zero-filled buffer for all 48 gradients (the wgrad kernels accumulate with red.global.add): one fill kernel
     # instead of 48; every tensor starts on a 16-byte boundary
     sizes = [(p.numel() + 3) // 4 * 4 for p in params]
-    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-    pgrads, off = [], 0
-    for p, sz in zip(params, sizes):
-        pgrads.append(flat[off:off + p.numel()].view(p.shape))
-        off += sz
+    if os.environ.get("NERFPP_FLAT_GRADS", "1") == "1":
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        pgrads, off = [], 0
+        for p, sz in zip(params, sizes):
+            pgrads.append(flat[off:off + p.numel()].view(p.shape))
+            off += sz
+    else:
+        pgrads = [torch.zeros_like(p) for p in params]
     gfg, gbg = _lib.NetGrads(), _lib.NetGrads()
     for l in range(_lib.NLAYERS):
         gfg.w[l], gfg.b[l] = pgrads[2 * l].data_ptr(), pgrads[2 * l + 1].data_ptr()

@@ -1,0 +1,126 @@
+"""One pass of the hot path (render_rays: sampling -> field -> composite -> losses, every cascade level) captured once
+into a CUDA graph and replayed per step.
+
+The path is ~14 kernels of 3-460 us behind a Python caller: replaying one graph removes the per-launch host cost and the
+inter-kernel gaps, and with ``host_io=True`` the step's host->device and device->host transfers are graph nodes as well
+(ONE copy each way between pinned staging buffers and packed device buffers), so a step that starts and ends in host
+memory -- what the reference trainer's ``ray_batch[key].to(rank)`` / ``.item()`` lines amount to
+(ddp_train_nerf.py:423-427,474-496) -- costs one ``cudaGraphLaunch`` and one stream synchronisation.
+
+Nothing here adds arithmetic: the captured calls are exactly render.render_rays'.  Weights are read from the packed
+buffers of each model's PackedNet cache, whose addresses are stable; ``__call__`` re-packs (outside the graph) when an
+optimizer step has bumped a parameter's version."""
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from ._lib import NerfppError
+from .render import render_rays
+
+IN_KEYS = (("ray_o", 3), ("ray_d", 3), ("min_depth", 1), ("rgb", 3), ("depth_sup", 1))
+
+
+class GraphedRenderStep(object):
+    """step = GraphedRenderStep(models, n_rays, ...);  out = step(batch)  or  step.host_in[...] = ...; out = step()
+
+    ``host_io=True``:  ``batch`` (or ``step.host_in``) holds HOST tensors; returns HOST tensors (views of one pinned
+                       buffer, valid until the next call): rgb [n,3], depth [n], losses [levels,4].
+    ``host_io=False``: ``batch`` holds DEVICE tensors (copied into the graph's static inputs unless they already are
+                       ``step.dev_in``); returns device tensors, no synchronisation."""
+
+    def __init__(self, models, n_rays, cascade_samples=(64, 128), train=True, depth_loss_type="mse", lambda_depth=0.1,
+                 depth_sigma=0.01, depth_scale=1.0, with_rgb=True, with_depth_sup=True, host_io=True, device=None, warmup=2):
+        self.models, self.n, self.host_io = list(models), int(n_rays), bool(host_io)
+        dev = torch.device(device) if device is not None else next(models[0].parameters()).device
+        if dev.type != "cuda":
+            raise NerfppError("GraphedRenderStep: CUDA device required (there is no CPU path)")
+        self.device = dev
+        keys = [(k, w) for k, w in IN_KEYS if (k not in ("rgb",) or with_rgb) and (k != "depth_sup" or (with_rgb and with_depth_sup))]
+        n = self.n
+        total = sum(w for _, w in keys) * n
+        self._in_dev = torch.zeros(total, device=dev)
+        self._in_host = torch.zeros(total).pin_memory() if host_io else None
+
+        def views(flat):
+            out, off = OrderedDict(), 0
+            for k, w in keys:
+                out[k] = flat[off:off + n * w].view((n, w) if w > 1 else (n,))
+                off += n * w
+            return out
+        self.dev_in = views(self._in_dev)
+        self.host_in = views(self._in_host) if host_io else None
+        self.dev_in["ray_d"][:, 2] = 1.0            # a valid ray for the warm-up passes (origin 0, direction +z)
+        self.dev_in["min_depth"].fill_(1e-4)
+        if host_io:
+            self._in_host.copy_(self._in_dev)
+        nl = len(cascade_samples)
+        self._n_out = 4 * n + 4 * nl + 1            # rgb | depth | losses | out-of-sphere flag (as float)
+        self._out_host = torch.zeros(self._n_out).pin_memory() if host_io else None
+        kw = dict(cascade_samples=tuple(cascade_samples), train=train, depth_loss_type=depth_loss_type if with_depth_sup else None,
+                  lambda_depth=lambda_depth, depth_sigma=depth_sigma, defer_unbounded_check=True)
+        self._scale = float(depth_scale)
+
+        def body():
+            if host_io:
+                self._in_dev.copy_(self._in_host, non_blocking=True)
+            b = dict(self.dev_in)
+            b["depth_scale"] = self._scale
+            res = render_rays(self.models, b, **kw)
+            ret = res["levels"][-1][0]
+            flag = res["unbounded"].flag
+            parts = [ret["rgb"].reshape(-1), ret["depth"].reshape(-1)]
+            parts += [l.reshape(-1) for l in res.get("losses", [])] or [torch.zeros(4 * nl, device=dev)]
+            parts.append(flag.float())
+            packed = torch.cat(parts)
+            if host_io:
+                self._out_host.copy_(packed, non_blocking=True)
+            return res, packed
+
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up off the capture: library init, weight packing, allocator
+                for _ in range(max(int(warmup), 1)):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES[0]
+            with torch.cuda.graph(self.graph):
+                self.res, self._packed = body()
+            self.kernels_per_replay = ops.LAUNCHES[0] - before      # kernels of libnerfpp_b200.so in the graph
+        self.replays = 0
+
+    def _refresh_weights(self):
+        impl = ops.default_field_impl()
+        for m in self.models:
+            net = m.nerf_net if hasattr(m, "nerf_net") else m
+            net._packed[0].get(net.fg_net.tensors(), impl)
+            net._packed[1].get(net.bg_net.tensors(), impl)
+
+    def _split(self, flat):
+        n, nl = self.n, (self._n_out - 4 * self.n - 1) // 4
+        return OrderedDict(rgb=flat[:3 * n].view(n, 3), depth=flat[3 * n:4 * n], losses=flat[4 * n:4 * n + 4 * nl].view(nl, 4))
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            dst = self.host_in if self.host_io else self.dev_in
+            for k in dst:
+                if batch[k] is not dst[k]:
+                    dst[k].copy_(batch[k], non_blocking=True)
+        self._refresh_weights()
+        self.graph.replay()
+        self.replays += 1
+        ops.LAUNCHES[0] += self.kernels_per_replay
+        if not self.host_io:
+            return self._split(self._packed)
+        torch.cuda.current_stream(self.device).synchronize()
+        if self._out_host[-1] != 0:
+            raise Exception(ops.UNBOUNDED_MSG)
+        return self._split(self._out_host)
+
+    def check_unbounded(self):
+        """host_io=False only: reads the out-of-sphere flag of the last replay (one host sync)."""
+        if float(self._packed[-1]) != 0:
+            raise Exception(ops.UNBOUNDED_MSG)

@@ -77,6 +77,12 @@ class UnboundedFlag(object):
     _pinned, _next = [], [0]
 
     def __init__(self, flag):
+        self.flag = flag
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture (nerfpp_b200.graph.GraphedRenderStep) the owner of the graph copies the
+            # flag out with the step's other results and checks it after each replay
+            self.host = self.event = None
+            return
         # the flag travels to a pinned host word right behind the kernel that sets it, so reading it later waits for
         # that kernel only, not for whatever has been enqueued since
         if len(self._pinned) < 16:
@@ -88,6 +94,8 @@ class UnboundedFlag(object):
         self.event.record()
 
     def raise_if_set(self):
+        if self.event is None:
+            raise NerfppError("this flag belongs to a captured CUDA graph; GraphedRenderStep checks it after each replay")
         self.event.synchronize()
         if int(self.host[0]) != 0:
             raise Exception(UNBOUNDED_MSG)
@@ -391,17 +399,25 @@ class _NerfppFunction(torch.autograd.Function):
         packed_bg = model_cache[1].get(bg_t, impl)
         outs, ws, inputs, tws = render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, impl, keep_workspace=True,
                                                train=True)
-        ctx.impl, ctx.ws, ctx.tws, ctx.inputs, ctx.outs = impl, ws, tws, inputs, outs
-        ctx.save_for_backward(*params)
+        ctx.impl, ctx.ws, ctx.tws = impl, ws, tws
         vals = tuple(outs.values())
+        # the outputs go through save_for_backward, never a ctx attribute: an attribute would close the reference cycle
+        # node -> output -> grad_fn -> node, and the workspaces (2.5-7.5 GB per call) would then wait for Python's cycle
+        # collector instead of being returned to the allocator when the graph is freed
+        ctx.save_for_backward(*params, *inputs, *vals)
         ctx.mark_non_differentiable(outs["fg_dists"])
         return vals
 
     @staticmethod
     def backward(ctx, *grads):
         from . import backward as B   # CUDA backward (nerfpp_backward); raises if the library lacks it
-        params = ctx.saved_tensors
-        pg = B.render_backward(params, ctx.inputs, ctx.outs, ctx.ws, ctx.tws, grads)
+        saved = ctx.saved_tensors
+        if ctx.tws is None:
+            raise NerfppError("backward through this NerfNet.forward ran already; its training workspace is released after the "
+                              "first backward (retain_graph=True is not supported, the reference trainer never uses it)")
+        params, inputs, outs = saved[:48], saved[48:53], OrderedDict(zip(RET_KEYS, saved[53:]))
+        pg = B.render_backward(params, inputs, outs, ctx.ws, ctx.tws, grads)
+        ctx.ws = ctx.tws = None
         return (None, None, None, None, None, None, None) + tuple(pg)
 
 

@@ -406,3 +406,48 @@ def test_render_single_image_matches_oracle():
             want = ref[m][0][k].reshape(H, W, -1).squeeze()
             assert out[m][k].shape == want.shape and not out[m][k].is_cuda
             assert relerr(out[m][k].numpy(), want.numpy()) <= 1e-4, (m, k)
+
+
+def test_graphed_step_matches_eager():
+    """GraphedRenderStep replays exactly render_rays' calls: on the deterministic path (train=False) results are
+    bit-equal to the eager call, from host buffers and from device buffers; re-packed weights are picked up; the
+    out-of-sphere exception of ddp_train_nerf.py:62-63 survives the capture."""
+    from nerfpp_b200 import GraphedRenderStep, render_rays
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    n = 300
+    rays = O.synthetic_rays(n, seed=4)
+    dev = torch.device("cuda:0")
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in rays.items()}
+    kw = dict(cascade_samples=(64, 128), train=False, depth_loss_type="l1", lambda_depth=0.1, depth_sigma=0.01)
+    with torch.no_grad():
+        ref = render_rays(nets, batch, **kw)
+    want = ref["levels"][-1][0]
+    gh = GraphedRenderStep(nets, n, depth_scale=rays["depth_scale"], host_io=True, **kw)
+    gd = GraphedRenderStep(nets, n, depth_scale=rays["depth_scale"], host_io=False, **kw)
+    for rep in range(2):
+        out = gh(rays)
+        assert not out["rgb"].is_cuda
+        assert torch.equal(out["rgb"], want["rgb"].cpu()) and torch.equal(out["depth"], want["depth"].cpu())
+        assert torch.equal(out["losses"], torch.stack(ref["losses"]).cpu())
+        out = gd(batch)
+        assert torch.equal(out["rgb"], want["rgb"]) and torch.equal(out["losses"], torch.stack(ref["losses"]))
+    assert gd.kernels_per_replay >= 10 and gh.replays == 2
+    # an optimizer-style in-place update bumps the parameter version: the next replay must see the new weights
+    with torch.no_grad():
+        nets[1].nerf_net.fg_net.rgb_layers[2].bias += 0.25
+        ref2 = render_rays(nets, batch, **kw)
+    out = gd(batch)
+    assert torch.equal(out["rgb"], ref2["levels"][-1][0]["rgb"]) and not torch.equal(out["rgb"], want["rgb"])
+    # stochastic path: two replays draw different perturbations (the graph advances torch's Philox offset)
+    gt = GraphedRenderStep(nets, n, depth_scale=rays["depth_scale"], host_io=False, cascade_samples=(64, 128), train=True,
+                           depth_loss_type="mse")
+    a = gt(batch)["rgb"].clone()
+    b = gt(batch)["rgb"].clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    np.testing.assert_allclose(a.cpu().numpy(), want["rgb"].cpu().numpy(), atol=0.1)
+    bad = dict(rays)
+    bad["ray_o"] = rays["ray_o"].clone()
+    bad["ray_o"][7] = torch.tensor([2.0, 0.0, 0.0])
+    with pytest.raises(Exception, match="bounded by the unit sphere"):
+        gh(bad)
