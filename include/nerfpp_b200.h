@@ -96,6 +96,12 @@ int nerfpp_sample_cdf(const float* bins, int bins_ld, const float* cdf, int cdf_
  * z_prev, w_prev [n,Sp]; u [n,Ns] (u_ld 0 = shared row); out_z [n, Sp+Ns] ascending. */
 int nerfpp_resample_merge(const float* z_prev, const float* w_prev, const float* u, int u_ld,
                           int n_rays, int n_prev, int n_new, float* out_z, void* stream);
+/* The foreground (:452-457) and background (:460-465) refinements of one level in ONE launch: 4096 rays fill less than
+ * half of a B200's warp slots, the two nets' rays run side by side.  Same arithmetic as two nerfpp_resample_merge calls;
+ * fg_u / bg_u share u_ld (0 = one shared row each). */
+int nerfpp_resample_merge_pair(const float* fg_z_prev, const float* fg_w_prev, const float* fg_u, float* out_fg_z,
+                               const float* bg_z_prev, const float* bg_w_prev, const float* bg_u, float* out_bg_z,
+                               int u_ld, int n_rays, int n_prev, int n_new, void* stream);
 
 /* ---- packed weights ---------------------------------------------------------------------- */
 /* The field kernels read a repacked copy of one net's parameters (transposed / padded fp32

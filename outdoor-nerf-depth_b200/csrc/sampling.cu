@@ -140,39 +140,48 @@ sample_pdf_kernel(const float* __restrict__ bins, int bins_ld, const float* __re
 
 // ---- A4 + A5 fused ----------------------------------------------------------------------------
 // ddp_train_nerf.py:452-457: mids -> sample_pdf(w[1:-1]) -> sort(cat(z_prev, z_new)).
-// The sort is a stable rank computation (each element counts the elements ordered before it),
-// exact for any multiset; 192 values per ray make the O(S^2) form the cheapest one.
+// Only the sorted VALUES are returned (:457 drops torch.sort's indices), so any exact sorting network gives the
+// reference's result: a warp-wide bitonic sort in shared memory over the next power of two (padding = +inf),
+// 36 compare-exchange stages of 4 pairs per lane at 192 values, instead of the O(S^2) rank count it replaces.
+// One launch serves the foreground and the background net of a level (blockIdx.y): 4096 rays are 4096 warps, less
+// than half of the 9472 warps a B200 holds, so the two halves run side by side.
+struct ResampleJob { const float* z_prev; const float* w_prev; const float* u; float* out_z; };
 __global__ void __launch_bounds__(SAMP_WARPS * 32)
-resample_merge_kernel(const float* __restrict__ z_prev, const float* __restrict__ w_prev, const float* __restrict__ u,
-                      int u_ld, int n, int Sp, int Ns, float* __restrict__ out_z) {
+resample_merge_kernel(ResampleJob job0, ResampleJob job1, int u_ld, int n, int Sp, int Ns, int P) {
   extern __shared__ float smem[];
+  const ResampleJob job = blockIdx.y == 0 ? job0 : job1;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int r = blockIdx.x * SAMP_WARPS + warp;
   if (r >= n) return;
   const int M = Sp - 2, St = Sp + Ns;
-  float* cdf_s = smem + warp * (2 * Sp + St);   // M+1 = Sp-1 used
+  float* cdf_s = smem + warp * (2 * Sp + P);   // M+1 = Sp-1 used
   float* bins_s = cdf_s + Sp;
-  float* all_s = bins_s + Sp;                  // [Sp + Ns]
-  const float* zr = z_prev + (size_t)r * Sp;
+  float* all_s = bins_s + Sp;                  // [P]: Sp old, Ns new, padding
+  const float* zr = job.z_prev + (size_t)r * Sp;
   for (int j = lane; j < Sp; j += 32) all_s[j] = zr[j];
+  for (int j = St + lane; j < P; j += 32) all_s[j] = __int_as_float(0x7f800000);
   __syncwarp();
   for (int j = lane; j < Sp - 1; j += 32) bins_s[j] = __fmul_rn(0.5f, __fadd_rn(all_s[j + 1], all_s[j]));
-  warp_build_cdf(w_prev + (size_t)r * Sp + 1, M, cdf_s, lane);
+  warp_build_cdf(job.w_prev + (size_t)r * Sp + 1, M, cdf_s, lane);
   for (int i = lane; i < Ns; i += 32) {
-    float ui = u[(size_t)r * u_ld + i];
+    float ui = job.u[(size_t)r * u_ld + i];
     all_s[Sp + i] = cdf_interp(cdf_s, bins_s, cdf_above(cdf_s, M, ui), ui);
   }
   __syncwarp();
-  float* o = out_z + (size_t)r * St;
-  for (int i = lane; i < St; i += 32) {
-    float v = all_s[i];
-    int rank = 0;
-    for (int j = 0; j < St; ++j) {
-      float q = all_s[j];
-      rank += (q < v) || (q == v && j < i);
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // the pair's lower index: bit j clear
+        const int l = i | j;
+        const float a = all_s[i], b = all_s[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up && a != b) { all_s[i] = b; all_s[l] = a; }
+      }
+      __syncwarp();
     }
-    o[rank] = v;
   }
+  float* o = job.out_z + (size_t)r * St;
+  for (int i = lane; i < St; i += 32) o[i] = all_s[i];
 }
 
 // ---- N1: ray generation + batch gather (nerf_sample_ray_split.py:10-34, 155-221) ------------------------------------
@@ -264,17 +273,34 @@ extern "C" int nerfpp_sample_cdf(const float* bins, int bins_ld, const float* cd
   return sample_common(1, bins, bins_ld, cdf, cdf_ld, u, u_ld, n_rays, M, n_new, out_samples, out_above, nullptr, stream);
 }
 
-extern "C" int nerfpp_resample_merge(const float* z_prev, const float* w_prev, const float* u, int u_ld, int n_rays,
-                                     int n_prev, int n_new, float* out_z, void* stream) {
-  NPP_CHECK_ARG(n_rays >= 0 && n_prev >= 3 && n_new >= 1 && z_prev && w_prev && u && out_z, "bad argument");
+static int resample_launch(const ResampleJob& j0, const ResampleJob& j1, int jobs, int u_ld, int n_rays, int n_prev, int n_new,
+                           void* stream) {
+  NPP_CHECK_ARG(n_rays >= 0 && n_prev >= 3 && n_new >= 1, "bad argument");
   NPP_CHECK_ARG(n_prev + n_new <= 4096, "too many samples per ray");
   if (n_rays == 0) return 0;
-  size_t smem = (size_t)SAMP_WARPS * (3 * n_prev + n_new) * sizeof(float);
+  int P = 2;
+  while (P < n_prev + n_new) P <<= 1;
+  size_t smem = (size_t)SAMP_WARPS * (2 * n_prev + P) * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  resample_merge_kernel<<<(n_rays + SAMP_WARPS - 1) / SAMP_WARPS, SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      z_prev, w_prev, u, u_ld, n_rays, n_prev, n_new, out_z);
+  dim3 grid((n_rays + SAMP_WARPS - 1) / SAMP_WARPS, jobs);
+  resample_merge_kernel<<<grid, SAMP_WARPS * 32, smem, (cudaStream_t)stream>>>(j0, j1, u_ld, n_rays, n_prev, n_new, P);
   NPP_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int nerfpp_resample_merge(const float* z_prev, const float* w_prev, const float* u, int u_ld, int n_rays,
+                                     int n_prev, int n_new, float* out_z, void* stream) {
+  NPP_CHECK_ARG(z_prev && w_prev && u && out_z, "null argument");
+  ResampleJob j{z_prev, w_prev, u, out_z};
+  return resample_launch(j, j, 1, u_ld, n_rays, n_prev, n_new, stream);
+}
+
+extern "C" int nerfpp_resample_merge_pair(const float* fg_z_prev, const float* fg_w_prev, const float* fg_u, float* out_fg_z,
+                                          const float* bg_z_prev, const float* bg_w_prev, const float* bg_u, float* out_bg_z,
+                                          int u_ld, int n_rays, int n_prev, int n_new, void* stream) {
+  NPP_CHECK_ARG(fg_z_prev && fg_w_prev && fg_u && out_fg_z && bg_z_prev && bg_w_prev && bg_u && out_bg_z, "null argument");
+  ResampleJob j0{fg_z_prev, fg_w_prev, fg_u, out_fg_z}, j1{bg_z_prev, bg_w_prev, bg_u, out_bg_z};
+  return resample_launch(j0, j1, 2, u_ld, n_rays, n_prev, n_new, stream);
 }
 
 extern "C" int nerfpp_gen_rays(const float* kinv_host, const float* c2w_host, float cam_depth, int W, const int64_t* pixel_ids,

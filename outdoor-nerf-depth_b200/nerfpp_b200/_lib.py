@@ -45,6 +45,7 @@ SIGNATURES = {
     "nerfpp_sample_pdf": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     "nerfpp_sample_cdf": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P]),
     "nerfpp_resample_merge": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P]),
+    "nerfpp_resample_merge_pair": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "nerfpp_packed_bytes": (c_int64, [c_int, c_int]),
     "nerfpp_pack_weights": (c_int, [POINTER(NetParams), c_int, c_int, P, P]),
     "nerfpp_field_forward": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P]),

@@ -226,6 +226,33 @@ def resample_merge(z_prev, w_prev, N_samples, det=False, u=None):
     return out
 
 
+def resample_merge_pair(fg_z_prev, fg_w_prev, bg_z_prev, bg_w_prev, N_samples, det=False, u_fg=None, u_bg=None):
+    """Both refinements of one cascade level (ddp_train_nerf.py:452-457 foreground, :460-465 background) in one launch.
+    Random draws, when not supplied, come from ONE torch.rand call ([2, n, N_samples]: row 0 foreground, row 1 background)."""
+    fz, fw = _c(fg_z_prev, "fg_z_prev", 2), _c(fg_w_prev, "fg_w_prev", 2)
+    bz, bw = _c(bg_z_prev, "bg_z_prev", 2), _c(bg_w_prev, "bg_w_prev", 2)
+    n, sp = fz.shape
+    if fw.shape != fz.shape or bz.shape != fz.shape or bw.shape != fz.shape:
+        raise ValueError("foreground and background depths / weights must all be [n, S_prev]")
+    if (u_fg is None) != (u_bg is None):
+        raise ValueError("give both u_fg and u_bg or neither")
+    if u_fg is None:
+        if det:
+            u_fg = u_bg = linspace01(N_samples, fz.device)
+        else:
+            u_fg, u_bg = torch.rand(2, n, N_samples, device=fz.device).unbind(0)
+    uf, ld_f = _u_rows(u_fg, n, N_samples, fz.device)
+    ub, ld_b = _u_rows(u_bg, n, N_samples, fz.device)
+    if ld_f != ld_b:
+        raise ValueError("u_fg and u_bg must have the same layout")
+    out_f = torch.empty(n, sp + N_samples, device=fz.device, dtype=torch.float32)
+    out_b = torch.empty_like(out_f)
+    with torch.cuda.device(fz.device):
+        check(_lib.lib().nerfpp_resample_merge_pair(_p(fz), _p(fw), _p(uf), _p(out_f), _p(bz), _p(bw), _p(ub), _p(out_b), ld_f, n, sp,
+                                                    N_samples, _stream()), "resample_merge")
+    return out_f, out_b
+
+
 # ------------------------------------------------------------------------------------------------
 # packed weights
 # ------------------------------------------------------------------------------------------------

@@ -26,14 +26,17 @@ def cascade_forward(models, ray_o, ray_d, min_depth, cascade_samples=(64, 128), 
         if m == 0:
             t_fg = t_bg = None
             if train:
-                t_fg = rand["t_fg"] if rand else torch.rand(n, S, device=ray_o.device)
-                t_bg = rand["t_bg"] if rand else torch.rand(n, S, device=ray_o.device)
+                t_fg, t_bg = (rand["t_fg"], rand["t_bg"]) if rand else torch.rand(2, n, S, device=ray_o.device).unbind(0)
             fg_z, bg_z = ops.coarse_depths(min_depth, fg_far, S, t_fg, t_bg)
         else:
             u_fg = rand["u_fg_%d" % m] if (train and rand) else None
             u_bg = rand["u_bg_%d" % m] if (train and rand) else None
-            fg_z = ops.resample_merge(fg_z, ret["fg_weights"], S, det=not train, u=u_fg)
-            bg_z = ops.resample_merge(bg_z, ret["bg_weights"], S, det=not train, u=u_bg)
+            if fg_z.shape == bg_z.shape:
+                fg_z, bg_z = ops.resample_merge_pair(fg_z, ret["fg_weights"], bg_z, ret["bg_weights"], S, det=not train,
+                                                     u_fg=u_fg, u_bg=u_bg)
+            else:
+                fg_z = ops.resample_merge(fg_z, ret["fg_weights"], S, det=not train, u=u_fg)
+                bg_z = ops.resample_merge(bg_z, ret["bg_weights"], S, det=not train, u=u_bg)
         ret = models[m](ray_o, ray_d, fg_far, fg_z, bg_z) if impl is None else models[m](ray_o, ray_d, fg_far, fg_z, bg_z, impl=impl)
         out.append((ret, fg_z, bg_z))
     if flag is not None:

@@ -166,6 +166,21 @@ def test_merge_is_exact_sort_of_union():
         assert torch.equal(got, torch.sort(torch.cat((zg, new), -1), -1)[0])     # exact multiset + order
         close_frac, worst = sample_agreement(got.cpu().numpy(), ref.numpy())
         assert close_frac >= 0.995 and worst <= 2e-3, (n, close_frac, worst)
+        # the paired launch (fg + bg of a level in one kernel) == two single launches, bit for bit
+        z2 = torch.sort(torch.rand(n, 64, generator=gen), -1)[0].to(dev())
+        w2, u2 = torch.rand(n, 64, generator=gen).to(dev()), torch.rand(n, 128, generator=gen).to(dev())
+        pf, pb = ops.resample_merge_pair(zg, wg, z2, w2, 128, u_fg=ug, u_bg=u2)
+        assert torch.equal(pf, got) and torch.equal(pb, ops.resample_merge(z2, w2, 128, u=u2))
+        df, db = ops.resample_merge_pair(zg, wg, z2, w2, 128, det=True)
+        assert torch.equal(df, ops.resample_merge(zg, wg, 128, det=True)) and torch.equal(db, ops.resample_merge(z2, w2, 128, det=True))
+    # unsorted input depths and sample counts that are not powers of two: still the exact sort of the union
+    for sp, ns in ((64, 128), (17, 5), (192, 64), (3, 1), (100, 411)):
+        z = torch.rand(9, sp, generator=gen).to(dev())
+        w, u = torch.rand(9, sp, generator=gen).to(dev()), torch.rand(9, ns, generator=gen).to(dev())
+        got = ops.resample_merge(z, w, ns, u=u)
+        mids = (0.5 * (z[..., 1:] + z[..., :-1])).contiguous()
+        new = ops.sample_pdf(mids, w[..., 1:-1], ns, u=u)
+        assert torch.equal(got, torch.sort(torch.cat((z, new), -1), -1)[0]), (sp, ns)
 
 
 # ------------------------------------------------------------------------------------------------
