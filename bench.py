@@ -221,12 +221,15 @@ def run_ours(args):
     for _ in range(3):
         e2e_step()
     barrier()
-    t0 = time.perf_counter()
+    t_sum = 0.0
     for _ in range(args.steps):
         flush.zero_()
-        e2e_step()
+        torch.cuda.synchronize()             # the L2 flush is a measurement device, not part of a step
+        t0 = time.perf_counter()
+        e2e_step()                           # returns host tensors: the step's last D2H has completed
+        t_sum += time.perf_counter() - t0
     barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    t_e2e = torch.tensor([t_sum], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * N_RAYS * args.steps / float(t_e2e.item())
@@ -240,7 +243,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (field_tc_kernel), timed alone with CUDA events ----
     roof = field_roofline(models, batch, dev)
-    cpu = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu, parity = cpu_baseline(dev=dev) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else (None, None)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -262,6 +265,8 @@ def run_ours(args):
             line["train"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -349,11 +354,45 @@ def reference_step(levels, rays, O):
     with torch.no_grad():
         out, far = O.cascade_forward(levels, rays["ray_o"], rays["ray_d"], rays["min_depth"], CASCADE,
                                      O.synthetic_rand(rays["ray_o"].shape[0], CASCADE, seed=1))
-        for ret, fg_z, _ in out:
-            O.level_loss(ret, rays["rgb"], rays["depth_sup"], fg_z, far, True, "mse", LAMBDA_DEPTH, DEPTH_SIGMA * DEPTH_SCALE)
+        losses = [O.level_loss(ret, rays["rgb"], rays["depth_sup"], fg_z, far, True, "mse", LAMBDA_DEPTH, DEPTH_SIGMA * DEPTH_SCALE)
+                  for ret, fg_z, _ in out]
+    return out, losses
 
 
-def cpu_baseline(sample=4096, reps=4):
+def parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev):
+    """The checker half of the cpu_baseline leg: the CUDA path on the very rays, weights and random draws the oracle
+    has just been timed on.  Reports max relative error (normalised by the largest reference magnitude, as the tests
+    do) of the finest level's rgb / depth, of each level's total loss, and the PSNR of our rgb against the oracle's."""
+    from types import SimpleNamespace
+    import math
+    import ddp_model
+    from nerfpp_b200 import render_rays
+    args = SimpleNamespace(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True)
+    nets = []
+    for p in levels:
+        net = ddp_model.NerfNetWithAutoExpo(args)
+        net.load_state_dict(p)
+        nets.append(net.to(dev))
+    n = rays["ray_o"].shape[0]
+    rand = {k: v.to(dev) for k, v in O.synthetic_rand(n, CASCADE, seed=1).items()}
+    b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in rays.items()}
+    with torch.no_grad():
+        res = render_rays(nets, b, CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA, rand=rand)
+    got, want = res["levels"][-1][0], ref_out[-1][0]
+    rel = lambda a, w: float((a.cpu().double() - w.double()).abs().max() / w.double().abs().max())
+    mse = float(((got["rgb"].cpu().double() - want["rgb"].double()) ** 2).mean())
+    loss_rel = max(abs(float(res["losses"][m][2]) - float(ref_losses[m][0])) / abs(float(ref_losses[m][0])) for m in range(len(CASCADE)))
+    coarse = {}
+    for name, idx in (("fg", 1), ("bg", 2)):      # stratified + perturbed depths of level 0: integer-exact work, expected 0 / 0
+        a, w = res["levels"][0][idx].cpu(), ref_out[0][idx]
+        coarse[name] = {"mismatched": int((a != w).sum()), "of": a.numel(), "max_abs": float((a - w).abs().max())}
+    return {"rays": n, "rgb_max_rel": rel(got["rgb"], want["rgb"]), "depth_max_rel": rel(got["depth"], want["depth"]),
+            "loss_max_rel": loss_rel, "psnr_vs_oracle_db": (-10.0 * math.log10(mse) if mse > 0 else float("inf")),
+            "coarse_depths": coarse, "tolerance": 1e-4,
+            "against": "oracle/nerfpp_oracle.py on the same rays, weights and random draws (train path, both levels)"}
+
+
+def cpu_baseline(sample=4096, reps=4, dev=None):
     import nerfpp_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -362,11 +401,13 @@ def cpu_baseline(sample=4096, reps=4):
     rays = make_rays(sample, 6)
     t0 = time.perf_counter()
     for _ in range(reps):
-        reference_step(levels, rays, O)
+        ref_out, ref_losses = reference_step(levels, rays, O)
     dt = time.perf_counter() - t0
-    return {"value": reps * sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+    base = {"value": reps * sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": "%d x %d rays of the same workload (oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference, "
                       "all host threads), %.1f s" % (reps, sample, dt)}
+    parity = parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev) if dev is not None else None
+    return base, parity
 
 
 def run_reference(args):
