@@ -6,8 +6,9 @@
 How the drop-in works:
   * ``ddp_model`` and ``depth_loss`` are resolved by name through ``sys.path``: this directory is put AHEAD of the
     reference directory, so the trainer's ``from ddp_model import NerfNetWithAutoExpo`` / ``from depth_loss import *``
-    (ddp_train_nerf.py:9,18) bind the B200 modules; its own ``utils``, ``data_loader_split`` ... still come from the
-    reference.
+    (ddp_train_nerf.py:9,18) bind the B200 modules, and ``from data_loader_split import load_data_split`` (:11) binds
+    the device-resident loader (set NERFPP_REFERENCE_LOADER=1 to keep the reference's host
+    loader); its own ``utils``, ``nerf_sample_ray_split`` ... still come from the reference.
   * ``intersect_sphere``, ``perturb_samples`` and ``sample_pdf`` are defined INSIDE the trainer module
     (ddp_train_nerf.py:51-130) and children are started with the ``spawn`` method (fresh import per child,
     :742-745), so they are patched inside each child before ``ddp_train_nerf.ddp_train_nerf(rank, args)`` runs.
@@ -35,9 +36,27 @@ def patch_trainer_module(mod):
     return mod
 
 
+def _use_reference_loader(reference_dir):
+    """NERFPP_REFERENCE_LOADER=1: bind ``data_loader_split`` to the reference's own file although this directory, which
+    holds a module of the same name, comes first on sys.path."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("data_loader_split", os.path.join(reference_dir, "data_loader_split.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["data_loader_split"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def _child(rank, args, reference_dir, entry):
     _paths(reference_dir)
     import importlib
+    import torch
+    # the trainer loads the data (ddp_train_nerf.py:389) before create_nerf() selects the device (:310); the device-
+    # resident loader must already see this rank's GPU as the current one
+    if torch.cuda.is_available():
+        torch.cuda.set_device(rank)
+    if os.environ.get("NERFPP_REFERENCE_LOADER") == "1":
+        _use_reference_loader(reference_dir)
     trainer = patch_trainer_module(importlib.import_module("ddp_train_nerf"))
     if entry == "train":
         trainer.ddp_train_nerf(rank, args)
@@ -60,6 +79,8 @@ def main(argv=None):
         entry = "test"
     _paths(reference_dir)
     import torch
+    if os.environ.get("NERFPP_REFERENCE_LOADER") == "1":
+        _use_reference_loader(reference_dir)
     import ddp_train_nerf as trainer          # the reference's module, unmodified
     parser = trainer.config_parser()
     args = parser.parse_args(argv)

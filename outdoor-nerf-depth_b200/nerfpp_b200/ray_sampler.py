@@ -85,15 +85,28 @@ class DeviceRaySampler(object):
         s.depth_gt_path, s.depth_sup_path = depth_gt_path, depth_sup_path
         return s
 
-    # accessors of the reference class (:108-129); device tensors instead of numpy arrays
+    # accessors of the reference class (:108-129).  The unmodified trainer does numpy arithmetic on what they return
+    # (ddp_train_nerf.py:557-570, ddp_test_nerf.py:82-91), so they hand out HOST arrays like the reference; the
+    # device-resident copies are ``self.img`` / ``self.depth_gt`` / ``self.depth_sup`` (flat, row-major).
+    resolution_level = 1                      # ddp_train_nerf.py:421 logs it; the trainer never changes it
+
+    def _host(self, name, shape):
+        t = getattr(self, name)
+        if t is None:
+            return None
+        cache = self.__dict__.setdefault("_host_cache", {})
+        if name not in cache:
+            cache[name] = t.reshape(shape).cpu().numpy()
+        return cache[name]
+
     def get_img(self):
-        return None if self.img is None else self.img.reshape(self.H, self.W, 3)
+        return self._host("img", (self.H, self.W, 3))
 
     def get_gt_depth_img(self):
-        return None if self.depth_gt is None else self.depth_gt.reshape(self.H, self.W)
+        return self._host("depth_gt", (self.H, self.W))
 
     def get_sup_depth_img(self):
-        return None if self.depth_sup is None else self.depth_sup.reshape(self.H, self.W)
+        return self._host("depth_sup", (self.H, self.W))
 
     def _rays(self, ids, n):
         dev = self.device

@@ -139,3 +139,22 @@ def test_launcher_patches_trainer_functions():
     assert stub.intersect_sphere is ops.intersect_sphere
     assert stub.perturb_samples is ops.perturb_samples
     assert stub.sample_pdf is ops.sample_pdf
+
+
+def test_launcher_can_keep_the_reference_loader(tmp_path):
+    """NERFPP_REFERENCE_LOADER=1: the name ``data_loader_split`` resolves to the reference directory's file although the
+    drop-in directory (which holds a module of the same name) is first on sys.path."""
+    import sys
+    import launch_ddp_train_nerf as LN
+    (tmp_path / "data_loader_split.py").write_text("WHO = 'reference stub'\ndef load_data_split(*a, **k):\n    return WHO\n")
+    saved = sys.modules.pop("data_loader_split", None)
+    try:
+        mod = LN._use_reference_loader(str(tmp_path))
+        import data_loader_split as again
+        assert again is mod and again.load_data_split() == "reference stub"
+    finally:
+        sys.modules.pop("data_loader_split", None)
+        if saved is not None:
+            sys.modules["data_loader_split"] = saved
+    import data_loader_split as ours
+    assert ours.__file__.endswith(os.path.join("outdoor-nerf-depth_b200", "data_loader_split.py"))

@@ -36,7 +36,11 @@ def test_loader_matches_reference_golden(scene, golden_dir):
                 assert np.array_equal(ret[k].cpu().numpy(), g["%s_%d_%s" % (tag, i, k)]), (tag, i, k)
             np.testing.assert_allclose(ret["ray_d"].cpu().numpy(), g["%s_%d_ray_d" % (tag, i)], rtol=2e-6, atol=1e-7)
             np.testing.assert_allclose(ret["depth"].cpu().numpy(), g["%s_%d_depth" % (tag, i)], rtol=1e-6)
-            assert tuple(s.get_img().shape) == (s.H, s.W, 3) and tuple(s.get_gt_depth_img().shape) == (s.H, s.W)
+            # the accessors the trainer's numpy metric code reads (ddp_train_nerf.py:557-570): host arrays, like the reference
+            img, dgt = s.get_img(), s.get_gt_depth_img()
+            assert isinstance(img, np.ndarray) and img.shape == (s.H, s.W, 3) and dgt.shape == (s.H, s.W)
+            assert np.array_equal(img.reshape(-1, 3), g["%s_%d_rgb" % (tag, i)]) and s.resolution_level == 1
+            assert np.array_equal(s.get_sup_depth_img().reshape(-1), g["%s_%d_depth_sup" % (tag, i)])
         if tag == "a":
             np.random.seed(3)
             r = samplers[1].random_sample(64, center_crop=False)       # same numpy draw as the reference (:178)
