@@ -5,7 +5,7 @@
 
 size_t npp_dgrad_packed_bytes();
 int npp_pack_dgrad(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
-int npp_field_dgrad(const void* packed, const void* act, const float* rgb, const float* raw_sigma, const float* d_sigma,
+int npp_field_dgrad(const void* packed, const void* act, const void* mask, const float* rgb, const float* raw_sigma, const float* d_sigma,
                     const float* d_rgb, const float* scale, long long total, void* dz, float* d_raw_sigma, float* d_raw_rgb,
                     cudaStream_t st);
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
@@ -111,7 +111,7 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
     const float* raw_sigma = (const float*)(tw + tc::train_ws_sigma_off(tiles));
     rc = npp_pack_dgrad(bg ? params_bg : params_fg, bg != 0, b.packed, st);
     if (rc) return rc;
-    rc = npp_field_dgrad(b.packed, act, bg ? f.bg_rgb : f.fg_rgb, raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma,
+    rc = npp_field_dgrad(b.packed, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb, raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma,
                          bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + bg, total, b.dz, b.d_raw_sigma, b.d_raw_rgb, st);
     if (rc) return rc;
     rc = npp_field_wgrad(bg != 0, act, etiles, b.dz, b.d_raw_sigma, b.d_raw_rgb, b.scale + bg, total, bg ? grads_bg : grads_fg, st);

@@ -54,7 +54,7 @@ constexpr int T_W2 = 0, T_WSIG = 3 * RGB_HID, T_TOTAL = T_WSIG + W;
 
 __global__ void __launch_bounds__(THREADS, 1)
 field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const uint8_t* __restrict__ act,
-                   const float* __restrict__ rgb, const float* __restrict__ raw_sigma, const float* __restrict__ d_sigma,
+                   const uint8_t* __restrict__ mask, const float* __restrict__ rgb, const float* __restrict__ raw_sigma, const float* __restrict__ d_sigma,
                    const float* __restrict__ d_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
                    uint8_t* __restrict__ dz, float* __restrict__ d_raw_sigma, float* __restrict__ d_raw_rgb) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -218,19 +218,20 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
 #pragma unroll 1
       for (int t = 0; t < NUM_LAYERS; ++t) {
         const uint32_t buf = (t + tile_i) & 1;
+        const int l = target_act(t);
+        // ReLU mask of the forward activation this layer's output is the gradient of (base_remap, t == 0, had none):
+        // the training forward left it as bits (MASK layout, tc_common.cuh), one 16-byte word group per thread and
+        // layer.  It is fetched HERE, before the wait for the layer's accumulator, so the load flies while the tensor
+        // pipe still runs this layer's MMAs.
+        uint4 mb4 = make_uint4(0u, 0u, 0u, 0u);
+        if (t != 0) mb4 = __ldg(reinterpret_cast<const uint4*>(mask + mask_off(l, (size_t)num_tiles, (size_t)tile, hh, row)));
+        const uint32_t mb[4] = {mb4.x, mb4.y, mb4.z, mb4.w};
         mbar_wait(bar(B_ACC + buf), (acc_par >> buf) & 1u);
         acc_par ^= 1u << buf;
         tc_fence_after();
-        const int l = target_act(t);
         const uint32_t acc_addr = lane_addr + buf * 256u + 32u * hh;
         uint32_t v[2][32];
         tmem_ld32(acc_addr, v[0]);
-        uint4 hm[4];                                      // saved forward activation of this row, chunk 0 (ReLU mask)
-        if (t != 0) {
-          const uint8_t* ach = act + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, 0) + roff;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) hm[u] = *reinterpret_cast<const uint4*>(ach + (((4 * hh + u) ^ (row & 7)) << 4));
-        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t (&cur)[32] = v[j & 1];
@@ -249,28 +250,16 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) pk[e] = pack_f16x2_sat(cur[2 * e], cur[2 * e + 1]);
-          if (t != 0) {       // ReLU mask of the forward activation (base_remap had no activation)
-            const uint32_t* hw = reinterpret_cast<const uint32_t*>(hm);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const __half2 m2 = __hgt2(*reinterpret_cast<const __half2*>(&hw[e]), __float2half2_rn(0.f));
-              const __half2 r2 = __hmul2(*reinterpret_cast<const __half2*>(&pk[e]), m2);
-              pk[e] = *reinterpret_cast<const uint32_t*>(&r2);
-            }
-            if (j + 1 < 4) {  // next chunk's mask
-              const uint8_t* ach = act + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j + 1) + roff;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) hm[u] = *reinterpret_cast<const uint4*>(ach + (((4 * hh + u) ^ (row & 7)) << 4));
-            }
-          }
-          if (t != NUM_LAYERS - 1) tmem_st16(acc_addr + 64u * j, pk);      // next layer's A operand, in place
-          store_act_chunk(dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
+          if (t != 0) apply_relu_mask(pk, mb[j]);
           if (t != NUM_LAYERS - 1) {
+            tmem_st16(acc_addr + 64u * j, pk);      // next layer's A operand, in place
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_AREADY + j));
           }
+          // the copy for the weight-gradient kernel leaves behind the arrive, off the chain the tensor pipe waits for
+          store_act_chunk(dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
         }
       }
     }
@@ -318,8 +307,8 @@ int npp_pack_dgrad(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st
   return 0;
 }
 
-// act / dz: ACT-layout buffers (tc_common.cuh) of the same tiling as the forward's training workspace
-int npp_field_dgrad(const void* packed, const void* act, const float* rgb, const float* raw_sigma, const float* d_sigma,
+// act / dz: ACT-layout buffers (tc_common.cuh) of the same tiling as the forward's training workspace; mask: its MASK region
+int npp_field_dgrad(const void* packed, const void* act, const void* mask, const float* rgb, const float* raw_sigma, const float* d_sigma,
                     const float* d_rgb, const float* scale, long long total, void* dz, float* d_raw_sigma, float* d_raw_rgb,
                     cudaStream_t st) {
   static int num_sms = 0;
@@ -334,7 +323,7 @@ int npp_field_dgrad(const void* packed, const void* act, const float* rgb, const
   const uint8_t* blobs = (const uint8_t*)packed;
   const float* tail = (const float*)(blobs + tcb::h_tab.total);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  tcb::field_dgrad_kernel<<<grid, tcb::THREADS, tcb::SMEM_BYTES, st>>>(blobs, tail, (const uint8_t*)act, rgb, raw_sigma, d_sigma, d_rgb,
+  tcb::field_dgrad_kernel<<<grid, tcb::THREADS, tcb::SMEM_BYTES, st>>>(blobs, tail, (const uint8_t*)act, (const uint8_t*)mask, rgb, raw_sigma, d_sigma, d_rgb,
                                                                         scale, total, num_tiles, (uint8_t*)dz, d_raw_sigma, d_raw_rgb);
   NPP_CHECK_LAUNCH();
   return 0;

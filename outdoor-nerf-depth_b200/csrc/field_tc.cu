@@ -132,9 +132,10 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 //   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
 template <int KIND, bool SAVE>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
-                                               const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
+                                               const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, float& sig_part,
                                                long long* probe_slot) {
   uint32_t v[2][32];
+  uint32_t mbits[4];
   tmem_ld32(acc_addr, v[0]);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {       // 64-column chunks of the layer output
@@ -145,7 +146,10 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
 #pragma unroll
     for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
     tmem_st16(acc_addr + 64u * j, pk);
-    if (SAVE) store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
+    if (SAVE) {
+      store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
+      if (KIND != 2) mbits[j] = relu_mask_bits(pk);      // the ReLU mask the dgrad chain reads instead of the fp16 values
+    }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
@@ -164,15 +168,16 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
       sig_part += (s[0] + s[1]) + (s[2] + s[3]);
     }
   }
+  if (SAVE && KIND != 2) *mask_dst = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
 }
 
 template <bool SAVE>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
-                                                  const float* __restrict__ tail, uint8_t* act_chunk0, float& sig_part,
+                                                  const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, float& sig_part,
                                                   long long* probe_slot) {
-  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
-  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
-  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, sig_part, probe_slot);
+  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
+  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
+  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
 }
 
 // Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
@@ -225,7 +230,9 @@ __device__ __forceinline__ void rgb_head(uint32_t acc_addr, uint32_t free_bar, i
 
 // CLUSTER > 1: the CTAs of a cluster walk their tiles in lock step and share every weight tile: each
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
-template <bool BG, int CLUSTER>
+// TRAIN: the training-mode forward (saves activations / masks / E tiles for the backward) is a separate instantiation so
+// that the inference kernel's register allocation never sees the save code.
+template <bool BG, int CLUSTER, bool TRAIN>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
@@ -336,7 +343,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
         const uint32_t one_lo = sw128_lo(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
         mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
-        if (save.e && lane == 0) bulk_s2g(save.e + (size_t)(grp * CLUSTER + (int)cta_rank) * E_BYTES, e_addr, E_BYTES);   // training: keep the E operand
+        if (TRAIN && lane == 0) bulk_s2g(save.e + (size_t)(grp * CLUSTER + (int)cta_rank) * E_BYTES, e_addr, E_BYTES);   // training: keep the E operand
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
         // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
         if (tile_i > 0) mbar_wait(bar(B_ACC + 1), (tile_i - 1) & 1);
@@ -363,7 +370,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
               }
             }
             if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
-              if (save.e && lane == 0) bulk_s2g_wait_read();
+              if (TRAIN && lane == 0) bulk_s2g_wait_read();
               __syncwarp();
               wait_stage();
               if (elect_one()) {
@@ -428,7 +435,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       tc_fence_after();
       const long long hg = (long long)tile * TILE + hrow;
       float* const dst = hg < total ? out_rgb + 3 * hg : nullptr;
-      if (save.act) rgb_head<true>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0), dst);
+      if (TRAIN) rgb_head<true>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0), dst);
       else rgb_head<false>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, nullptr, dst);
     };
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
@@ -484,7 +491,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     auto flush_pending = [&]() {
       if (pend_g >= 0) {
         out_sigma[pend_g] = fabsf(pend);
-        if (save.raw_sigma) save.raw_sigma[pend_g] = pend;
+        if (TRAIN) save.raw_sigma[pend_g] = pend;
         pend_g = -1;
       }
     };
@@ -494,7 +501,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       const bool valid = g < total;
       float sig_part = 0.f;
       long long* const probe_base = (probing && (int)tid_pinned == 0 && grp == group0 + 5 * group_step) ? dbg + 14 * 148 + 16 * (int)cta_pinned : nullptr;
-      uint8_t* const act_tile = save.act ? save.act + act_chunk_off(0, (size_t)num_tiles, (size_t)tile, 0) : nullptr;
+      uint8_t* const act_tile = TRAIN ? save.act + act_chunk_off(0, (size_t)num_tiles, (size_t)tile, 0) : nullptr;
       const size_t act_layer_stride = act_layer_off(1, (size_t)num_tiles);
 #pragma unroll 1
       for (int m = 0; m < NUM_MMA_LAYERS - 1; ++m) {       // rgb.0 (layer 9) is read by the colour head, not here
@@ -508,8 +515,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (probe) probe_base[1] = clock64();
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 10 + m] = clock64();
         const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
-        if (act_tile) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride, sig_part, probe);
-        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, sig_part, probe);
+        if (TRAIN) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
+                                              reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)), sig_part, probe);
+        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, sig_part, probe);
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
         if (m == 0) flush_pending();
       }
@@ -636,10 +644,10 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
   return 0;
 }
 
-template <bool BG, int CLUSTER>
+template <bool BG, int CLUSTER, bool TRAIN>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, tc::TrainSave save, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER>;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER, TRAIN>;
   static bool configured = false;
   static int max_clusters = 0;
   if (!configured) {
@@ -685,13 +693,17 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;
   const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
-  tc::TrainSave save{nullptr, nullptr, nullptr};
+  tc::TrainSave save{nullptr, nullptr, nullptr, nullptr};
   if (train_ws) {
     uint8_t* w = (uint8_t*)train_ws;
     save.act = w; save.e = w + tc::train_ws_e_off((size_t)num_tiles); save.raw_sigma = (float*)(w + tc::train_ws_sigma_off((size_t)num_tiles));
+    save.mask = w + tc::train_ws_mask_off((size_t)num_tiles);
   }
-#define NPP_TC_LAUNCH(BG, C) launch_tc<BG, C>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
-  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1) : NPP_TC_LAUNCH(true, 2);
-  return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1) : NPP_TC_LAUNCH(false, 2);
+#define NPP_TC_LAUNCH(BG, C, T) launch_tc<BG, C, T>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
+  if (train_ws) {     // the training forward always runs unclustered (the cluster variant is an inference experiment)
+    return bg ? NPP_TC_LAUNCH(true, 1, true) : NPP_TC_LAUNCH(false, 1, true);
+  }
+  if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, false) : NPP_TC_LAUNCH(true, 2, false);
+  return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, false) : NPP_TC_LAUNCH(false, 2, false);
 #undef NPP_TC_LAUNCH
 }

@@ -199,10 +199,45 @@ __device__ __forceinline__ void store_act_chunk(uint8_t* chunk, int row, int hh,
 // What a training-mode forward saves for the backward (all NULL = inference): the fp16 activations of every layer
 // (ACT layout above; layers 0..7 = base outputs after ReLU, 8 = base_remap output, 9 = rgb hidden after ReLU), the
 // E operand tile of every sample tile ([tile][2 chunks]) and the sigma head's output before the abs().
-struct TrainSave { uint8_t* act; uint8_t* e; float* raw_sigma; };
+// ... and the ReLU masks of base layers 0..7 as bits (MASK layout below): the data-gradient chain needs only the sign of
+// those activations, 4 KB per layer and tile instead of the 64 KB of fp16 it would otherwise re-read.
+struct TrainSave { uint8_t* act; uint8_t* e; float* raw_sigma; uint8_t* mask; };
 __host__ __device__ inline size_t train_ws_e_off(size_t n_tiles) { return act_bytes(n_tiles); }
 __host__ __device__ inline size_t train_ws_sigma_off(size_t n_tiles) { return act_bytes(n_tiles) + n_tiles * 2 * (size_t)CHUNK_BYTES; }
-__host__ __device__ inline size_t train_ws_bytes(size_t n_tiles) { return train_ws_sigma_off(n_tiles) + n_tiles * TILE * sizeof(float); }
+__host__ __device__ inline size_t train_ws_mask_off(size_t n_tiles) { return train_ws_sigma_off(n_tiles) + n_tiles * TILE * sizeof(float); }
+// MASK layout: [layer 0..7][tile][hh 0..1][row 0..127] uint4 = the four chunk words of one epilogue thread (row, column
+// half hh of every 64-column chunk), written and read as one coalesced 16-byte access per thread
+constexpr int MASK_LAYERS = 8;
+__host__ __device__ inline size_t mask_off(int layer, size_t n_tiles, size_t tile, int hh, int row) {
+  return (((size_t)layer * n_tiles + tile) * 2 + (size_t)hh) * (TILE * 16) + (size_t)row * 16;
+}
+__host__ __device__ inline size_t train_ws_bytes(size_t n_tiles) { return train_ws_mask_off(n_tiles) + MASK_LAYERS * n_tiles * 2 * (size_t)(TILE * 16); }
+
+// One chunk's ReLU mask as a word: the bit of packed pair e's low / high half sits where  (word << (e >> 1))  exposes it
+// as the sign bit of byte 0 / 2 (e even) or byte 1 / 3 (e odd), so that ONE prmt with sign replication per pair turns it
+// back into a 0xffff / 0x0000 mask per half (apply_relu_mask).
+__device__ __forceinline__ uint32_t relu_mask_bits(const uint32_t (&pk)[16]) {
+  uint32_t m = 0u;
+  const __half2 zero2 = __float2half2_rn(0.f);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int sft = e >> 1;
+    const uint32_t pos = (e & 1) ? ((1u << (15 - sft)) | (1u << (31 - sft))) : ((1u << (7 - sft)) | (1u << (23 - sft)));
+    m |= __hgt2_mask(*reinterpret_cast<const __half2*>(&pk[e]), zero2) & pos;
+  }
+  return m;
+}
+__device__ __forceinline__ void apply_relu_mask(uint32_t (&pk)[16], uint32_t bits) {
+#pragma unroll
+  for (int e2 = 0; e2 < 8; ++e2) {
+    const uint32_t sh = bits << e2;
+    uint32_t m0, m1;
+    asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(m0) : "r"(sh));
+    asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m1) : "r"(sh));
+    pk[2 * e2] &= m0;
+    pk[2 * e2 + 1] &= m1;
+  }
+}
 
 }  // namespace tc
 }  // namespace npp
