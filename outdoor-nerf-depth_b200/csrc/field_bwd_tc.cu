@@ -24,7 +24,9 @@ constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = 32768;          // one [256 N x 64 K] SW128 tile of W^T
 constexpr int G_BYTES = 2 * CHUNK_BYTES;    // dG operand: 128 columns; double-buffered
 constexpr int OFF_G = 0, OFF_W = 2 * G_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_W2 = OFF_BAR + 512;
-constexpr int SMEM_BYTES = OFF_W2 + 3 * RGB_HID * 4;
+constexpr int OFF_STG = OFF_W2 + 3 * RGB_HID * 4;   // staging of the DZ store (tc_common.cuh: stage_store_chunk), 1024-aligned
+constexpr int SMEM_BYTES = OFF_STG + STG_BYTES;
+static_assert(OFF_STG % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, PRO_WARP0 = 10, NUM_PRO_WARPS = 4, THREADS = 448;
 constexpr int NUM_LAYERS = 9;               // t = 0: rgb.0 (remap part), 1: base_remap, 2..8: base 7..1
 
@@ -210,7 +212,8 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t roff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-    uint32_t acc_par = 0, tile_i = 0;
+    uint32_t acc_par = 0, tile_i = 0, stg_flip = 0;
+    uint8_t* const stg = smem + OFF_STG;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_i) {
       const long long g = (long long)tile * TILE + row;
       float dsr = 0.f;
@@ -258,11 +261,13 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_AREADY + j));
           }
-          // the copy for the weight-gradient kernel leaves behind the arrive, off the chain the tensor pipe waits for
-          store_act_chunk(dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), row, hh, pk);
+          // the copy for the weight-gradient kernel leaves behind the arrive, off the chain the tensor pipe waits for,
+          // through shared memory and one bulk copy per warp pair
+          stage_store_chunk(stg, stg_flip, dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), q, lane, hh, pk);
         }
       }
     }
+    stage_store_drain();
   }
   tc_fence_before();
   __syncthreads();

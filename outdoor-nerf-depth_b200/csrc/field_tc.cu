@@ -52,7 +52,12 @@ constexpr int T_WRGB2 = 256;                 // 3 x 128
 constexpr int T_BSIG = 256 + 384;
 constexpr int T_BRGB2 = T_BSIG + 1;
 constexpr int T_TOTAL = T_BRGB2 + 3;
-constexpr int SMEM_BYTES = OFF_TAIL + T_TOTAL * 4;   // the fp32 head weights live in shared memory for the whole kernel
+constexpr int SMEM_BYTES = OFF_TAIL + T_TOTAL * 4;
+// The training instantiation runs the weight ring with 3 slots and stages its activation stores (tc_common.cuh:
+// stage_store_chunk, 32 KB) in the fourth slot.
+constexpr int NSTAGE_TRAIN = 3;
+constexpr int OFF_STG_TRAIN = OFF_W + NSTAGE_TRAIN * STAGE_BYTES;
+static_assert(STG_BYTES <= STAGE_BYTES && OFF_STG_TRAIN % 1024 == 0, "staging fits the spare ring slot");   // the fp32 head weights live in shared memory for the whole kernel
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 
 __host__ __device__ constexpr int param_layer(int m) { return m < 8 ? m : m == 8 ? L_REMAP : L_RGB0; }
@@ -132,8 +137,8 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 //   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
 template <int KIND, bool SAVE>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
-                                               const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, float& sig_part,
-                                               long long* probe_slot) {
+                                               const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
+                                               uint32_t& stg_flip, float& sig_part, long long* probe_slot) {
   uint32_t v[2][32];
   uint32_t mbits[4];
   tmem_ld32(acc_addr, v[0]);
@@ -146,15 +151,16 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
 #pragma unroll
     for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
     tmem_st16(acc_addr + 64u * j, pk);
-    if (SAVE) {
-      store_act_chunk(act_chunk0 + (size_t)j * CHUNK_BYTES, row, hh, pk);
-      if (KIND != 2) mbits[j] = relu_mask_bits(pk);      // the ReLU mask the dgrad chain reads instead of the fp16 values
-    }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(aready_bar + 8u * j);
     if (probe_slot) probe_slot[j] = clock64();
+    if (SAVE) {   // training, behind the arrive: the fp16 activations leave through shared memory and one bulk copy per warp
+                  // pair (tc_common.cuh), and their ReLU mask is kept as bits for the dgrad chain
+      stage_store_chunk(stg, stg_flip, act_chunk0 + (size_t)j * CHUNK_BYTES, row >> 5, lane, hh, pk);
+      if (KIND != 2) mbits[j] = relu_mask_bits(pk);
+    }
     if (KIND == 1) {
       float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -173,11 +179,11 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
 
 template <bool SAVE>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
-                                                  const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, float& sig_part,
-                                                  long long* probe_slot) {
-  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
-  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
-  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, sig_part, probe_slot);
+                                                  const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
+                                                  uint32_t& stg_flip, float& sig_part, long long* probe_slot) {
+  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
+  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
+  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
 }
 
 // Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
@@ -296,12 +302,13 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       uint32_t it = 0;
       for (int grp = group0; grp < n_groups; grp += group_step) {
         for (int i = 0; i < tab.n; ++i, ++it) {
-          const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
+          constexpr uint32_t NS = TRAIN ? NSTAGE_TRAIN : NSTAGE;
+          const uint32_t st = it % NS, ph = (it / NS) & 1;
           const uint32_t bytes = (uint32_t)tab.s[i].blob_bytes;
           // a stage without bias tile lands straight on the weight area of the slot
           const uint32_t dst = s_base + OFF_W + st * STAGE_BYTES + (tab.s[i].bias ? (uint32_t)(AUX_BYTES - tab.s[i].n * BIAS_ROW_BYTES) : (uint32_t)AUX_BYTES);
           mbar_wait(bar(B_WEMPTY + st), ph ^ 1);          // every CTA of the cluster has consumed this stage
-          if ((flags & 8) && it >= NSTAGE) { mbar_arrive(bar(B_WFULL + st)); continue; }   // timing experiment: no refill (wrong results)
+          if ((flags & 8) && it >= NS) { mbar_arrive(bar(B_WFULL + st)); continue; }   // timing experiment: no refill (wrong results)
           mbar_expect_tx(bar(B_WFULL + st), bytes);
           if (CLUSTER == 1) {
             bulk_g2s(dst, blobs + tab.s[i].blob_off, bytes, bar(B_WFULL + st));
@@ -330,7 +337,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       auto release = [&](uint32_t wempty_bar) { if (CLUSTER == 1) tc_commit(wempty_bar); else tc_commit_mcast(wempty_bar, kMask); };
       auto advance = [&]() {
         ++st; slot += STAGE_BYTES; wfull += 8; wempty += 8;
-        if (st == NSTAGE) { st = 0; ph ^= 1; slot = ring0; wfull = wfull0; wempty = wempty0; }
+        if (st == (TRAIN ? NSTAGE_TRAIN : NSTAGE)) { st = 0; ph ^= 1; slot = ring0; wfull = wfull0; wempty = wempty0; }
       };
       auto ts4 = [&](uint32_t d, uint32_t a0, uint32_t blo, uint32_t idesc) {   // one 64-column A chunk from TMEM
         mma_ts<1>(d, a0, blo, idesc);
@@ -484,7 +491,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0, stg_flip = 0;
     long long e_wait = 0, e_t0 = clock64(), ett = 0;
     float pend = 0.f;            // raw sigma of the previous tile's row, written out under the next tile's layer-1 MMAs
     long long pend_g = -1;
@@ -516,8 +523,9 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 10 + m] = clock64();
         const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
         if (TRAIN) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
-                                              reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)), sig_part, probe);
-        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, sig_part, probe);
+                                              reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)),
+                                              smem + OFF_STG_TRAIN, stg_flip, sig_part, probe);
+        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe);
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
         if (m == 0) flush_pending();
       }
@@ -543,6 +551,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       }
     }
     flush_pending();
+    if (TRAIN) stage_store_drain();
     if (timing && (int)tid_pinned == 0) {
       dbg[8 * (int)cta_pinned + 5] = clock64() - e_t0; dbg[8 * (int)cta_pinned + 6] = e_wait;
     }
