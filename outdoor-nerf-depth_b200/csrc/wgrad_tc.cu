@@ -8,7 +8,8 @@
 // adds its partial into the fp32 gradient with red.global.add (the caller zero-fills or accumulates).
 // This kernel is HBM-bound by construction (128 KB of operands per 2048 tensor-pipe cycles).
 //
-// wgrad_small_kernel: the column sums (bias gradients) and the two tiny heads (sigma 256->1, rgb.2 128->3) on CUDA cores.
+// The bias gradients (column sums of DZ) are taken by wgrad_tc_kernel's otherwise idle epilogue warps from the A tiles in
+// shared memory.  wgrad_small_kernel: the two tiny heads (sigma 256->1, rgb.2 128->3) on CUDA cores.
 #include "tc_common.cuh"
 
 namespace npp {
@@ -31,20 +32,21 @@ struct Job {
   int ncols;          // weight columns written
   int w_index;        // NerfppNetGrads.w index
   int ld, col0;       // row stride (in-features of the layer) and first column in dW
+  int bias;           // this job also sums DZ[a_layer] over the samples = the layer's bias gradient (one job per layer)
 };
 struct JobTable { Job j[12]; int n; };
 __host__ __device__ constexpr JobTable make_jobs(bool bg) {
   JobTable t{};
   const int emb = emb_dim(bg), ech = bg ? 2 : 1;
   int i = 0;
-  t.j[i++] = Job{0, 2, 1, 0, 0, ech, 0, emb, 0, emb, 0};                                  // base 0: embedding
+  t.j[i++] = Job{0, 2, 1, 0, 0, ech, 0, emb, 0, emb, 0, 1};                               // base 0: embedding
   for (int l = 1; l < 8; ++l) {
-    if (l == 5) t.j[i++] = Job{5, 2, 1, 0, 0, ech, 0, emb, 5, emb + W, 0};                // base 5: [embedding | h4]
-    t.j[i++] = Job{l, 2, 0, l - 1, 0, 4, 0, W, l, l == 5 ? emb + W : W, l == 5 ? emb : 0};
+    if (l == 5) t.j[i++] = Job{5, 2, 1, 0, 0, ech, 0, emb, 5, emb + W, 0, 0};             // base 5: [embedding | h4]
+    t.j[i++] = Job{l, 2, 0, l - 1, 0, 4, 0, W, l, l == 5 ? emb + W : W, l == 5 ? emb : 0, 1};
   }
-  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0};                                  // base_remap
-  t.j[i++] = Job{9, 1, 0, 8, 0, 4, 0, W, L_RGB0, W + VIEW_DIM, 0};                        // rgb.0: remap part
-  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W};                // rgb.0: view-direction part
+  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0, 1};                               // base_remap
+  t.j[i++] = Job{9, 1, 0, 8, 0, 4, 0, W, L_RGB0, W + VIEW_DIM, 0, 1};                     // rgb.0: remap part
+  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W, 0};             // rgb.0: view-direction part
   t.n = i;
   return t;
 }
@@ -72,7 +74,8 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
   const size_t nt = (size_t)num_tiles;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_XEMPTY + i), 1); mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
+    // an A half is released by the MMAs' commit and, in a bias job, also by each of the four column-sum warps
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_XEMPTY + i), 1); mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), jb.bias ? 5 : 1); }
     mbar_init(bar(B_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -133,6 +136,47 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
     }
   } else {
     // ================= epilogue: TMEM -> red.global.add into dW =================
+    // While the MMAs run these four warps are idle, and every DZ tile of the layer passes through shared memory as the
+    // A operand: in a bias job they add it up over the samples (the bias gradient) instead of a second kernel reading
+    // all of DZ from HBM again.  Thread = one pair of adjacent features x one half of the 128 sample rows; a warp reads
+    // one 128-byte row of the swizzled image per step (conflict-free).
+    if (jb.bias && t_end > t_begin) {
+      const int t = threadIdx.x, p = t & 63, rh = t >> 6;
+      const int col = 2 * (p & 31);
+      const uint32_t coff = (uint32_t)((p >> 5) * CHUNK_BYTES + (col & 7) * 2);
+      float bsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      uint32_t ia = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h < jb.m_halves) {
+            const uint32_t ab = ia & 1;
+            mbar_wait(bar(B_AFULL + ab), (ia >> 1) & 1);
+            const uint8_t* ah = smem + OFF_A + ab * AH_BYTES + coff;
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) {
+              const int r = rh * 64 + k;
+              const __half2 v = *reinterpret_cast<const __half2*>(ah + (r >> 3) * 1024 + (r & 7) * 128 + (((col >> 3) ^ (r & 7)) << 4));
+              const float2 f = __half22float2(v);
+              bsum[h][0] += f.x;
+              bsum[h][1] += f.y;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_AEMPTY + ab));
+            ++ia;
+          }
+        }
+      }
+      const float inv_scale_b = 1.f / *scale_ptr;
+      float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (h < jb.m_halves) {
+          const int f0 = 128 * h + 64 * (p >> 5) + col;
+          atomicAdd(db + f0, bsum[h][0] * inv_scale_b);
+          atomicAdd(db + f0 + 1, bsum[h][1] * inv_scale_b);
+        }
+    }
     if (t_end > t_begin) {
       mbar_wait(bar(B_DONE), 0);
       tc_fence_after();
@@ -222,7 +266,7 @@ wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ 
                    const float* __restrict__ d_raw_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
                    NerfppNetGrads grads) {
   __shared__ float s_acc[3 * RGB_HID + W];
-  const int what = blockIdx.y;
+  const int what = 10 + blockIdx.y;     // the bias gradients (what 0..9) are summed inside wgrad_tc_kernel now
   const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
   const float inv_scale = 1.f / *scale_ptr;
   const size_t nt = (size_t)num_tiles;
@@ -271,8 +315,8 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
                                                                                (const uint8_t*)dz, scale, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
-  int sx = num_tiles < 48 ? num_tiles : 48;         // 12 x 48 CTAs ~ 4 per SM
-  tcw::wgrad_small_kernel<<<dim3(sx, 12), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
+  int sx = num_tiles < num_sms ? num_tiles : num_sms;      // 2 x 148 CTAs; 96 KB of activations per tile, read once
+  tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
                                                         num_tiles, *grads);
   NPP_CHECK_LAUNCH();
   return 0;

@@ -432,6 +432,7 @@ class _NerfppFunction(torch.autograd.Function):
         # node -> output -> grad_fn -> node, and the workspaces (2.5-7.5 GB per call) would then wait for Python's cycle
         # collector instead of being returned to the allocator when the graph is freed
         ctx.save_for_backward(*params, *inputs, *vals)
+        ctx.set_materialize_grads(False)      # outputs the loss does not use arrive as None, not as zero-filled tensors
         ctx.mark_non_differentiable(outs["fg_dists"])
         return vals
 
