@@ -268,7 +268,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if parity is not None:
             line["parity"] = parity
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -428,22 +428,41 @@ def run_reference(args):
     sample = 512
     levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
     rays = make_rays(sample, 6)
-    for _ in range(max(min(args.warmup, 1), 1)):
-        reference_step(levels, make_rays(64, 5), O)
-    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 5))          # K and W as asked, bounded so the arm always ends within a minute or two
+    for _ in range(warm):
+        reference_step(levels, rays, O)
+    steps = max(1, min(args.steps, 40))
     t0 = time.perf_counter()
     for _ in range(steps):
         reference_step(levels, rays, O)
     dt = (time.perf_counter() - t0) / steps
     v = sample / dt
     world = int(os.environ.get("WORLD_SIZE", 1))
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": 1,
+    emit(({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_rays_per_step": sample},
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "%d rays/step of the same workload, torch-CPU fp32, %d threads" % (sample, cores)},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+RESULT_OUT = [None]
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner through C
+    stdio when a communicator is created): from here on file descriptor 1 points at stderr, and the JSON line goes to
+    a private duplicate of the real stdout."""
+    sys.stdout.flush()
+    RESULT_OUT[0] = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = RESULT_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -456,6 +475,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--no-train", action="store_true", help="skip the informational trainer-step measurement")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
