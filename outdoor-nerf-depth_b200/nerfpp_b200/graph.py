@@ -91,6 +91,7 @@ class GraphedRenderStep(object):
                 self.res, self._packed = body()
             self.kernels_per_replay = ops.LAUNCHES[0] - before      # kernels of libnerfpp_b200.so in the graph
         self.replays = 0
+        self._done = torch.cuda.Event() if host_io else None
 
     def _refresh_weights(self):
         impl = ops.default_field_impl()
@@ -103,7 +104,9 @@ class GraphedRenderStep(object):
         n, nl = self.n, (self._n_out - 4 * self.n - 1) // 4
         return OrderedDict(rgb=flat[:3 * n].view(n, 3), depth=flat[3 * n:4 * n], losses=flat[4 * n:4 * n + 4 * nl].view(nl, 4))
 
-    def __call__(self, batch=None):
+    def launch(self, batch=None):
+        """Enqueues one step on the CURRENT stream without waiting for it: stage the inputs (``batch`` or whatever the
+        caller wrote into ``host_in`` / ``dev_in``), re-pack weights if an optimizer touched them, replay the graph."""
         if batch is not None:
             dst = self.host_in if self.host_io else self.dev_in
             for k in dst:
@@ -113,14 +116,70 @@ class GraphedRenderStep(object):
         self.graph.replay()
         self.replays += 1
         ops.LAUNCHES[0] += self.kernels_per_replay
+        if self.host_io:
+            self._done.record()
+
+    def fetch(self):
+        """The results of the last ``launch``.  host_io: waits for that replay (its D2H node is its last node), raises
+        the reference's out-of-sphere exception if the flag is set, returns views of the pinned result buffer."""
         if not self.host_io:
             return self._split(self._packed)
-        torch.cuda.current_stream(self.device).synchronize()
+        self._done.synchronize()
         if self._out_host[-1] != 0:
             raise Exception(ops.UNBOUNDED_MSG)
         return self._split(self._out_host)
+
+    def __call__(self, batch=None):
+        self.launch(batch)
+        return self.fetch()
 
     def check_unbounded(self):
         """host_io=False only: reads the out-of-sphere flag of the last replay (one host sync)."""
         if float(self._packed[-1]) != 0:
             raise Exception(ops.UNBOUNDED_MSG)
+
+
+class PipelinedRenderStep(object):
+    """``depth`` host-to-host GraphedRenderSteps on their own streams, used round-robin: while step i computes, step
+    i+1's inputs are staged and copied (copy engine) and step i-1's results are read on the host, so the GPU never waits
+    for the host between steps -- the prefetching a trainer's data loader does.
+
+        pipe.submit(batch_0)
+        for b in batches[1:]:
+            pipe.submit(b); out = pipe.result()      # result of the OLDEST outstanding step (host views, valid until
+        out = pipe.result()                          # that slot is submitted to again)
+
+    ``after_launch(slot_index, step)`` (optional) runs on the slot's stream right behind the replay -- bench.py issues the
+    N > 1 all-gather of the rendered tile there."""
+
+    def __init__(self, models, n_rays, depth=2, device=None, after_launch=None, **kw):
+        kw["host_io"] = True
+        self.slots = [GraphedRenderStep(models, n_rays, device=device, **kw) for _ in range(int(depth))]
+        self.device = self.slots[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.slots]
+        self.after_launch = after_launch
+        self._next, self._pending = 0, []
+
+    @property
+    def kernels_per_replay(self):
+        return self.slots[0].kernels_per_replay
+
+    def submit(self, batch=None):
+        if len(self._pending) == len(self.slots):
+            raise NerfppError("PipelinedRenderStep: %d steps outstanding; fetch a result() first" % len(self.slots))
+        i = self._next
+        self._next = (i + 1) % len(self.slots)
+        st = self.streams[i]
+        st.wait_stream(torch.cuda.current_stream(self.device))     # behind whatever the caller has enqueued (weight updates)
+        with torch.cuda.stream(st):
+            self.slots[i].launch(batch)
+            if self.after_launch is not None:
+                self.after_launch(i, self.slots[i])
+                self.slots[i]._done.record()
+        self._pending.append(i)
+        return i
+
+    def result(self):
+        if not self._pending:
+            raise NerfppError("PipelinedRenderStep: nothing submitted")
+        return self.slots[self._pending.pop(0)].fetch()

@@ -466,3 +466,36 @@ def test_graphed_step_matches_eager():
     bad["ray_o"][7] = torch.tensor([2.0, 0.0, 0.0])
     with pytest.raises(Exception, match="bounded by the unit sphere"):
         gh(bad)
+
+
+def test_pipelined_step_is_fifo_and_matches_eager():
+    """PipelinedRenderStep: two host-to-host graphs on two streams used alternately; results come back in submission
+    order and equal the eager path bit for bit (deterministic cascade), whatever is in flight meanwhile."""
+    from nerfpp_b200 import NerfppError, PipelinedRenderStep, render_rays
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    n = 200
+    dev = torch.device("cuda:0")
+    kw = dict(cascade_samples=(64, 128), train=False, depth_loss_type="mse", lambda_depth=0.1, depth_sigma=0.01)
+    batches = [O.synthetic_rays(n, seed=10 + i) for i in range(5)]
+    want = []
+    with torch.no_grad():
+        for b in batches:
+            res = render_rays(nets, {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}, **kw)
+            want.append((res["levels"][-1][0]["rgb"].cpu(), res["levels"][-1][0]["depth"].cpu(), torch.stack(res["losses"]).cpu()))
+    pipe = PipelinedRenderStep(nets, n, depth=2, depth_scale=batches[0]["depth_scale"], **kw)
+    with pytest.raises(NerfppError):
+        pipe.result()
+    got = []
+    pipe.submit(batches[0])
+    for b in batches[1:]:
+        pipe.submit(b)
+        out = pipe.result()
+        got.append((out["rgb"].clone(), out["depth"].clone(), out["losses"].clone()))
+    out = pipe.result()
+    got.append((out["rgb"].clone(), out["depth"].clone(), out["losses"].clone()))
+    for (a0, a1, a2), (b0, b1, b2) in zip(got, want):
+        assert torch.equal(a0, b0) and torch.equal(a1, b1) and torch.equal(a2, b2)
+    pipe.submit(batches[0]); pipe.submit(batches[1])
+    with pytest.raises(NerfppError):
+        pipe.submit(batches[2])
