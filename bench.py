@@ -310,8 +310,7 @@ def train_step_rate(models, batch, dev, steps=5):
             if m == 0:
                 fg_z, bg_z = ops.coarse_depths(batch["min_depth"], far, S, torch.rand(n, S, device=dev), torch.rand(n, S, device=dev))
             else:
-                fg_z = ops.resample_merge(fg_z, ret["fg_weights"].detach(), S)
-                bg_z = ops.resample_merge(bg_z, ret["bg_weights"].detach(), S)
+                fg_z, bg_z = ops.resample_merge_pair(fg_z, ret["fg_weights"].detach(), bg_z, ret["bg_weights"].detach(), S)
             opts[m].zero_grad()
             ret = nets[m](batch["ray_o"], batch["ray_d"], far, fg_z, bg_z)
             loss = torch.mean((ret["rgb"] - batch["rgb"]) ** 2) + LAMBDA_DEPTH * DL.depth_mse(batch["depth_sup"], ret["depth"])

@@ -209,8 +209,7 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
 
 // Weighted column sums over all samples of a chunked [tiles][nch][128 rows][64 cols] fp16 operand buffer:
 //   out[ch][col] += inv_scale * sum_rows wgt[row][ch] * X[row][col]        (wgt == nullptr: plain column sums)
-// This is the bias gradient (X = DZ[l], no weights), the sigma head (X = h7, wgt = d raw sigma) and rgb.2 (X = rgb
-// hidden, wgt = d raw rgb, NCH = 3).  blockIdx.x = sample-range split; one thread owns one 16-byte unit (8 columns) of
+// This is the sigma head (X = h7, wgt = d raw sigma) and rgb.2 (X = rgb hidden, wgt = d raw rgb, NCH = 3).  blockIdx.x = sample-range split; one thread owns one 16-byte unit (8 columns) of
 // four rows of every chunk, so all loads are 16-byte and a warp reads 512 contiguous bytes; the 8-column partials meet in
 // shared memory and leave with one atomicAdd per column per CTA.  HBM-bound: every operand byte is read exactly once.
 template <int NCH>
@@ -258,23 +257,17 @@ __device__ __forceinline__ void weighted_colsum(const uint8_t* __restrict__ laye
   }
 }
 
-// blockIdx.y = what: 0..9 bias gradient of the layer whose pre-activation gradient is DZ[y];
-//              10 = sigma head weights, 11 = rgb.2 weights; their two bias gradients (plain sums of 1 / 3 numbers per sample)
-//              are done by the y = 10 / 11 CTAs as well.
+// blockIdx.y: 0 = sigma head weights (X = h7, weights d raw sigma), 1 = rgb.2 weights (X = rgb hidden, weights d raw rgb);
+// the heads' bias gradients (plain sums of 1 / 3 numbers per sample) are done by the same CTAs.
 __global__ void __launch_bounds__(256)
 wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ dz, const float* __restrict__ d_raw_sigma,
                    const float* __restrict__ d_raw_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
                    NerfppNetGrads grads) {
   __shared__ float s_acc[3 * RGB_HID + W];
-  const int what = 10 + blockIdx.y;     // the bias gradients (what 0..9) are summed inside wgrad_tc_kernel now
+  const int what = 10 + blockIdx.y;     // (the layers' bias gradients are summed inside wgrad_tc_kernel)
   const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
   const float inv_scale = 1.f / *scale_ptr;
   const size_t nt = (size_t)num_tiles;
-  if (what < 10) {
-    const int pl = what < 8 ? what : what == 8 ? L_REMAP : L_RGB0;
-    weighted_colsum<1>(dz + act_layer_off(what, nt), what == 9 ? 2 : 4, nullptr, total, t_begin, t_end, inv_scale, s_acc, grads.b[pl], 0);
-    return;
-  }
   if (what == 10) weighted_colsum<1>(act + act_layer_off(7, nt), 4, d_raw_sigma, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_SIGMA], 0);
   else weighted_colsum<3>(act + act_layer_off(9, nt), 2, d_raw_rgb, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_RGB2], RGB_HID);
   // bias of the head: sum over the CTA's samples of d raw sigma / d raw rgb

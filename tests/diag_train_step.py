@@ -24,8 +24,7 @@ def step(timers=None):
         if m == 0:
             fg_z, bg_z = ops.coarse_depths(rays["min_depth"], far, S, torch.rand(n, S, device=dev), torch.rand(n, S, device=dev))
         else:
-            fg_z = ops.resample_merge(fg_z, ret["fg_weights"].detach(), S)
-            bg_z = ops.resample_merge(bg_z, ret["bg_weights"].detach(), S)
+            fg_z, bg_z = ops.resample_merge_pair(fg_z, ret["fg_weights"].detach(), bg_z, ret["bg_weights"].detach(), S)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         opts[m].zero_grad()
         ev[0].record()
