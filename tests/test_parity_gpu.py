@@ -466,6 +466,16 @@ def test_graphed_step_matches_eager():
     bad["ray_o"][7] = torch.tensor([2.0, 0.0, 0.0])
     with pytest.raises(Exception, match="bounded by the unit sphere"):
         gh(bad)
+    # configs[0] (depth_sup_type=rgbonly): no prior in the batch, rgb loss only; and a render-only step without targets
+    g_rgb = GraphedRenderStep(nets, n, host_io=False, with_depth_sup=False, cascade_samples=(64, 128), train=False)
+    assert list(g_rgb.dev_in.keys()) == ["ray_o", "ray_d", "min_depth", "rgb"]
+    out = g_rgb(batch)
+    assert torch.equal(out["rgb"], want["rgb"]) and torch.equal(out["losses"][:, 0], torch.stack(ref["losses"])[:, 0])
+    assert float(out["losses"][:, 1].abs().max()) == 0.0
+    g_r = GraphedRenderStep(nets, n, host_io=True, with_rgb=False, cascade_samples=(64, 128), train=False)
+    assert list(g_r.host_in.keys()) == ["ray_o", "ray_d", "min_depth"]
+    out = g_r(rays)
+    assert torch.equal(out["depth"], want["depth"].cpu()) and float(out["losses"].abs().max()) == 0.0
 
 
 def test_pipelined_step_is_fifo_and_matches_eager():
