@@ -84,6 +84,46 @@ RENDER_KEYS = ("rgb", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth", "b
 _KEY_WIDTH = dict(rgb=3, fg_rgb=3, bg_rgb=3, fg_depth=1, bg_depth=1, bg_lambda=1, depth=1)   # fg_dists: the level's sample count
 
 
+class _LazyRenderDict(OrderedDict):
+    """The per-level result of render_single_image: an OrderedDict with the reference's keys in the reference's order,
+    whose bulky entries (``fg_dists``: one float per SAMPLE, 93 % of the bytes, read by nothing in the trainer or the
+    tester) stay on the device until somebody asks for them.  Any access that could see the value -- ``d[k]``, ``get``,
+    ``values()``, ``items()``, ``pop`` -- copies it to the host first, so it behaves like the plain dict of CPU tensors."""
+
+    def __init__(self, eager, lazy):
+        super().__init__(eager)
+        self._lazy = dict(lazy)
+
+    def _force(self, k=None):
+        for key in ([k] if k is not None else list(self._lazy)):
+            if key in self._lazy:
+                super().__setitem__(key, self._lazy.pop(key)())
+
+    def __getitem__(self, k):
+        self._force(k)
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        self._force(k)
+        return super().get(k, default)
+
+    def pop(self, k, *a):
+        self._force(k)
+        return super().pop(k, *a)
+
+    def values(self):
+        self._force()
+        return super().values()
+
+    def items(self):
+        self._force()
+        return super().items()
+
+    def copy(self):
+        self._force()
+        return OrderedDict(super().items())
+
+
 def band_sizes(n_rays, world_size):
     """ddp_train_nerf.py:137-143: contiguous row-major bands, pixel count must divide by the world size."""
     if (n_rays // world_size) * world_size != n_rays:
@@ -124,7 +164,9 @@ def render_single_image(rank, world_size, models, ray_sampler, chunk_size, rende
     What changed underneath: each rank renders its band chunk by chunk straight into ONE packed device buffer
     [rays_of_rank, channels_of_all_levels] (no per-chunk device->host copies, no empty_cache()), and the ranks are
     merged by ONE all-gather of that buffer (NCCL over NVLink when the process group is NCCL) instead of one CPU
-    gloo gather per key per level (:229-243).  ``render_chunk(models, chunk_dict) -> [ret per level]`` is the
+    gloo gather per key per level (:229-243).  Rank 0 copies the narrow keys (rgb, depths, lambda: 20 floats per ray
+    and level) to the host at once; ``fg_dists`` (one float per sample -- 93 % of the bytes, read by nothing downstream)
+    is fetched when first accessed (_LazyRenderDict).  ``render_chunk(models, chunk_dict) -> [ret per level]`` is the
     per-chunk renderer (default: the CUDA cascade); tests inject a stub to exercise the sharding logic on CPU."""
     import torch.distributed as dist
     ray_batch = ray_sampler.get_all()
@@ -150,11 +192,20 @@ def render_single_image(rank, world_size, models, ray_sampler, chunk_size, rende
         gathered = packed
     if rank != 0:
         return None
-    host = gathered.cpu()
+    # one D2H of the narrow keys (20 floats per ray and level); fg_dists stays on the device until it is read
     out = []
+    H, W = ray_sampler.H, ray_sampler.W
+    small = [(k, off, w) for cols in layout for k, (off, w) in cols.items() if k != "fg_dists"]
+    host = torch.cat([gathered[:, off:off + w] for _, off, w in small], dim=1).cpu()
+    pos = 0
     for cols in layout:
-        d = OrderedDict()
+        eager, lazy = [], {}
         for k, (off, w) in cols.items():
-            d[k] = host[:, off:off + w].reshape(ray_sampler.H, ray_sampler.W, -1).squeeze()
-        out.append(d)
+            if k == "fg_dists":
+                eager.append((k, None))
+                lazy[k] = (lambda o=off, ww=w: gathered[:, o:o + ww].cpu().reshape(H, W, -1).squeeze())
+            else:
+                eager.append((k, host[:, pos:pos + w].reshape(H, W, -1).squeeze()))
+                pos += w
+        out.append(_LazyRenderDict(eager, lazy))
     return out

@@ -116,6 +116,13 @@ def test_no_cpu_fallback():
             net(torch.zeros(n, 3), torch.ones(n, 3), torch.ones(n), torch.rand(n, S), torch.rand(n, S))
     with pytest.raises(NerfppError):
         depth_loss.depth_mse(torch.ones(4), torch.ones(4))
+    # the graph-captured step and the device-resident sampler refuse a CPU device as well
+    from nerfpp_b200 import GraphedRenderStep
+    from nerfpp_b200.ray_sampler import decode_pixels
+    with pytest.raises(NerfppError):
+        GraphedRenderStep([net, net], 16, device="cpu")
+    with pytest.raises(NerfppError):
+        decode_pixels(np.zeros((2, 2), np.uint8), 255.0, device="cpu")
 
 
 def test_product_does_not_import_oracle():
