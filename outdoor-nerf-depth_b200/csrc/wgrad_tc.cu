@@ -308,7 +308,9 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
                                                                                (const uint8_t*)dz, scale, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
-  int sx = num_tiles < num_sms ? num_tiles : num_sms;      // 2 x 148 CTAs; 96 KB of activations per tile, read once
+  // 96 KB of activations per tile, read once.  A thread's loop over its tiles is a chain of dependent round trips to HBM
+  // (4 x 16 B in flight per thread), so the sample range is cut fine enough for ~8 CTAs per SM to cover the latency.
+  int sx = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
   tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
                                                         num_tiles, *grads);
   NPP_CHECK_LAUNCH();
