@@ -71,7 +71,7 @@ class GraphedRenderStep(object):
             flag = res["unbounded"].flag
             parts = [ret["rgb"].reshape(-1), ret["depth"].reshape(-1)]
             parts += [l.reshape(-1) for l in res.get("losses", [])] or [torch.zeros(4 * nl, device=dev)]
-            parts.append(flag.float())
+            parts.append(flag.view(torch.float32))       # the int32 flag's bits ride along (read back as int32): no convert kernel
             packed = torch.cat(parts)
             if host_io:
                 self._out_host.copy_(packed, non_blocking=True)
@@ -125,7 +125,7 @@ class GraphedRenderStep(object):
         if not self.host_io:
             return self._split(self._packed)
         self._done.synchronize()
-        if self._out_host[-1] != 0:
+        if int(self._out_host[-1:].view(torch.int32)[0]) != 0:
             raise Exception(ops.UNBOUNDED_MSG)
         return self._split(self._out_host)
 
@@ -135,7 +135,7 @@ class GraphedRenderStep(object):
 
     def check_unbounded(self):
         """host_io=False only: reads the out-of-sphere flag of the last replay (one host sync)."""
-        if float(self._packed[-1]) != 0:
+        if int(self._packed[-1:].view(torch.int32)[0]) != 0:
             raise Exception(ops.UNBOUNDED_MSG)
 
 
@@ -159,6 +159,8 @@ class PipelinedRenderStep(object):
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.slots]
         self.after_launch = after_launch
         self._next, self._pending = 0, []
+        self._params = [p for m in models for p in m.parameters()]
+        self._wkey = None
 
     @property
     def kernels_per_replay(self):
@@ -167,6 +169,13 @@ class PipelinedRenderStep(object):
     def submit(self, batch=None):
         if len(self._pending) == len(self.slots):
             raise NerfppError("PipelinedRenderStep: %d steps outstanding; fetch a result() first" % len(self.slots))
+        # the slots share the packed weight buffers, which launch() re-packs IN PLACE after an optimizer step: steps
+        # still in flight must have finished reading them first
+        wkey = tuple(p._version for p in self._params)
+        if wkey != self._wkey:
+            for j in self._pending:
+                self.slots[j]._done.synchronize()
+            self._wkey = wkey
         i = self._next
         self._next = (i + 1) % len(self.slots)
         st = self.streams[i]

@@ -22,15 +22,24 @@ def cascade_forward(models, ray_o, ray_d, min_depth, cascade_samples=(64, 128), 
     out = []
     fg_z = bg_z = ret = None
     n = ray_o.shape[0]
+    draws = None
+    if train and not rand:
+        # every uniform draw of the step from ONE torch.rand call (one launch instead of one per level): per level a
+        # contiguous [2, n, S] block, row 0 foreground, row 1 background
+        flat = torch.rand(2 * n * sum(cascade_samples), device=ray_o.device)
+        draws, off = [], 0
+        for S in cascade_samples:
+            draws.append(flat[off:off + 2 * n * S].view(2, n, S))
+            off += 2 * n * S
     for m, S in enumerate(cascade_samples):
         if m == 0:
             t_fg = t_bg = None
             if train:
-                t_fg, t_bg = (rand["t_fg"], rand["t_bg"]) if rand else torch.rand(2, n, S, device=ray_o.device).unbind(0)
+                t_fg, t_bg = (rand["t_fg"], rand["t_bg"]) if rand else draws[0].unbind(0)
             fg_z, bg_z = ops.coarse_depths(min_depth, fg_far, S, t_fg, t_bg)
         else:
-            u_fg = rand["u_fg_%d" % m] if (train and rand) else None
-            u_bg = rand["u_bg_%d" % m] if (train and rand) else None
+            u_fg = rand["u_fg_%d" % m] if (train and rand) else (draws[m][0] if draws is not None else None)
+            u_bg = rand["u_bg_%d" % m] if (train and rand) else (draws[m][1] if draws is not None else None)
             if fg_z.shape == bg_z.shape:
                 fg_z, bg_z = ops.resample_merge_pair(fg_z, ret["fg_weights"], bg_z, ret["bg_weights"], S, det=not train,
                                                      u_fg=u_fg, u_bg=u_bg)
