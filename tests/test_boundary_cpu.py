@@ -165,3 +165,26 @@ def test_launcher_can_keep_the_reference_loader(tmp_path):
             sys.modules["data_loader_split"] = saved
     import data_loader_split as ours
     assert ours.__file__.endswith(os.path.join("outdoor-nerf-depth_b200", "data_loader_split.py"))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference's algorithm on the host cores; the one leg that needs no GPU): stdout
+    carries exactly one JSON line with the contract's keys, whatever libraries print."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, WORLD_SIZE="1", RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    # a rank other than 0 does no work and prints nothing
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert p.returncode == 0 and p.stdout.strip() == ""
