@@ -49,42 +49,115 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+NVML_CHILD = r"""
+import sys, time
+import pynvml
+pynvml.nvmlInit()
+key = sys.argv[1]
+try:
+    h = pynvml.nvmlDeviceGetHandleByUUID(key) if key.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(key))
+except Exception:
+    h = pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+out = sys.stdout
+sys.stdin.readline()            # the parent says when the timed region starts: no polling before that
+while True:
+    out.write("%.6f,%d,%d,%d" % (time.time(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, int(reasons(h))) + chr(10))
+    out.flush()
+    time.sleep(0.004)
+"""
+
+
 class ClockSampler:
-    """Samples nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of this rank's GPU, sampled WHILE the timed region runs (B200_PROFILING.md recipe).
+
+    Default: an `nvidia-smi -lms 100` child, started when the process starts (eight ranks starting one each need more
+    than the 40 ms region just to print their first row) and read until 150 ms after the region; rows are stamped on
+    arrival and only those from the region on count.  NERFPP_BENCH_CLOCKS=nvml selects the denser sampler below.
+
+    The region is 20 steps of ~1.9 ms: a `nvidia-smi -lms 100` child delivers zero to two rows in 40 ms (and none at all
+    when eight ranks start one each).  So the numbers nvidia-smi prints are read from NVML (nvidia_ml_py, the library
+    nvidia-smi itself is built on) every ~4 ms by a CHILD process, like nvidia-smi: started early (NVML init takes a
+    moment), told on its stdin when the region starts, killed when it ends.  Polling is confined to the region because
+    seconds of 500 Hz NVML queries before it left the GPU measurably slower afterwards (the e2e leg lost 5-8 %), from a
+    thread of this process as well as from a child.  Rows carry the child's wall-clock time; only rows inside the
+    region count.  Without pynvml: the nvidia-smi child."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.index, self.rows, self.proc, self.source, self.t0, self.t1 = index, [], None, None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            if os.environ.get("NERFPP_BENCH_CLOCKS") != "nvml":
+                raise RuntimeError("default: the nvidia-smi child")
+            import pynvml  # noqa: F401  (only to know the child can import it)
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                key = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            except Exception:
+                key = str(index)
+            self.proc = subprocess.Popen([sys.executable, "-c", NVML_CHILD, key, str(index)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "NVML (nvidia_ml_py) polled by a child process every ~4 ms, inside the timed region only"
+            self.nvml = True
+        except Exception:
+            self.nvml = False
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                self.source = "nvidia-smi -lms 100"
+            except Exception:
+                self.proc = None
+        if self.proc is not None:
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            f = [x.strip() for x in line.split(",")]
+            if self.nvml:
+                try:
+                    r = int(f[3])
+                    self.rows.append((float(f[0]), [f[1], f[2]] + ["Active" if r & b else "Not Active" for b in self.BITS]))
+                except Exception:
+                    pass
+            else:
+                self.rows.append((time.time(), f))
 
-    def __exit__(self, *a):
+    def __enter__(self):          # the timed region starts
+        if self.nvml and self.proc is not None:
+            try:
+                self.proc.stdin.write("go\n")
+                self.proc.stdin.flush()
+            except Exception:
+                pass
+        self.t0 = time.time()
+        return self
+
+    def __exit__(self, *a):       # ... and ends
+        self.t1 = time.time()
         if self.proc is not None:
-            time.sleep(0.15)
+            if not self.nvml:
+                time.sleep(0.15)
+                self.t1 = time.time()
             self.proc.terminate()
             self.t.join(timeout=2)
 
+    def close(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        rows = [f for (t, f) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "source": self.source}
+        mx = max(int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit())
+        reasons = [nm for i, nm in enumerate(self.NAMES) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def make_rays(n, seed):
@@ -134,6 +207,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    clk = ClockSampler(local)          # its child process needs a moment to come up: started before the warm-up
     _lib.lib()
     models = make_models(dev)
     host = make_rays(N_RAYS, seed=rank)                 # this rank's band of the global 4096*world batch
@@ -154,13 +228,13 @@ def run_ours(args):
         # host -> host: two such graphs on their own streams, used alternately, so that step i+1's H2D and step i-1's host
         # read-back overlap step i's kernels (nerfpp_b200.graph.PipelinedRenderStep); for N > 1 the all-gather of the
         # rendered tile and the D2H of the gathered image ride on the slot's stream right behind the replay
-        gath_dev = [torch.empty(world * N_RAYS * 4, device=dev) for _ in range(2)] if world > 1 else None
-        gath_host = [torch.empty(world * N_RAYS * 4).pin_memory() for _ in range(2)] if world > 1 else None
+        gath_dev = [torch.empty(world * N_RAYS * 4, device=dev) for _ in range(args.e2e_depth)] if world > 1 else None
+        gath_host = [torch.empty(world * N_RAYS * 4).pin_memory() for _ in range(args.e2e_depth)] if world > 1 else None
 
         def gather_tiles(i, st):
             dist.all_gather_into_tensor(gath_dev[i], st._packed[:4 * N_RAYS])
             gath_host[i].copy_(gath_dev[i], non_blocking=True)
-        g_host = PipelinedRenderStep(models, N_RAYS, depth=2, depth_scale=DEPTH_SCALE, device=dev,
+        g_host = PipelinedRenderStep(models, N_RAYS, depth=args.e2e_depth, depth_scale=DEPTH_SCALE, device=dev,
                                      after_launch=gather_tiles if world > 1 else None, **step_kw)
 
     # N > 1: the step's rendered tile (rgb | depth) is copied aside and all-gathered on a SIDE stream, so the collective of
@@ -212,7 +286,7 @@ def run_ours(args):
     # ---- timed: K steps, device time per step by CUDA events, L2 flushed between steps ----
     ops.LAUNCHES[0] = 0
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clk:
+    with clk:
         barrier()
         t_wall = time.perf_counter()
         for a, b in evs:
@@ -254,13 +328,16 @@ def run_ours(args):
         the measurement protocol is enqueued before every step and is INSIDE the timed region."""
         t0 = time.perf_counter()
         if graphed:
-            flush.zero_()
-            g_host.submit(host)
-            for _ in range(k - 1):
+            ahead = min(args.e2e_depth - 1, k)
+            for _ in range(ahead):               # fill the pipeline
                 flush.zero_()
-                g_host.submit(host)              # step i+1 is staged and enqueued ...
+                g_host.submit(host)
+            for _ in range(k - ahead):
+                flush.zero_()
+                g_host.submit(host)              # step i+depth-1 is staged and enqueued ...
                 g_host.result()                  # ... before step i's results are read on the host
-            g_host.result()
+            for _ in range(ahead):
+                g_host.result()
         else:
             for _ in range(k):
                 flush.zero_()
@@ -301,8 +378,9 @@ def run_ours(args):
                        else "eager: one Python call per kernel"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": ("PipelinedRenderStep: host batch -> pinned staging -> graph (H2D, kernels, D2H) -> host results, two "
-                            "graphs on two streams so step i+1's copies overlap step i's kernels; wall clock over all steps, L2 "
+                    "steps_in_flight": args.e2e_depth if graphed else 1,
+                    "how": ("PipelinedRenderStep: host batch -> pinned staging -> graph (H2D, kernels, D2H) -> host results, one "
+                            "graph and stream per step in flight so step i+1's copies overlap step i's kernels; wall clock over all steps, L2 "
                             "flush included") if graphed else "eager, one step at a time, wall clock, L2 flush included"},
             "gpu_launches": launches,
             "roofline": roof,
@@ -517,6 +595,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="host-to-host steps in flight in the e2e leg (PipelinedRenderStep)")
     ap.add_argument("--no-train", action="store_true", help="skip the informational trainer-step measurement")
     args = ap.parse_args()
     claim_stdout()
