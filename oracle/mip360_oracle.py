@@ -182,3 +182,69 @@ def synthetic_level(batch, n_bins, seed=0):
     prior = (g.random(batch, dtype=F32) * 0.8 + 0.1).astype(F32)
     prior[::5] = 0
     return dict(t=t, logits=logits, density=density, rgbs=rgbs, dirs=dirs, prior=prior)
+
+
+# ----------------------------------------------------------------------------------------------
+# N4: the two regularisers of the mipnerf360 trainer (train_utils.py:160-180)
+# pinned by the reference's own tests, ported in tests/test_mip360_oracle.py:
+#   stepfun_test.py:588-622 (lossfun_outer: same / ablated point sets), :624-655 (inner <= w <= outer),
+#   :657-681 (invariance to monotonic maps of t), :683-697 (self loss ~ 0), :699-735 (brute-force outer / inner),
+#   :227-250 (interval_distortion vs brute force), :252-275 (lossfun_distortion == sum of interval distortions)
+# ----------------------------------------------------------------------------------------------
+def searchsorted(a, v):
+    """stepfun.py:30-53: (idx_lo, idx_hi) with a[idx_lo] <= v < a[idx_hi]; both clamp to the first / last index outside."""
+    a, v = np.asarray(a, F32), np.asarray(v, F32)
+    i = np.arange(a.shape[-1])
+    v_ge_a = v[..., None, :] >= a[..., :, None]
+    idx_lo = np.max(np.where(v_ge_a, i[:, None], i[:1, None]), -2)
+    idx_hi = np.min(np.where(~v_ge_a, i[:, None], i[-1:, None]), -2)
+    return idx_lo, idx_hi
+
+
+def inner_outer(t0, t1, y1):
+    """stepfun.py:64-79: inner and outer measures of the step function (t1, y1) on the intervals of t0."""
+    y1 = np.asarray(y1, F32)
+    cy1 = np.concatenate([np.zeros_like(y1[..., :1]), np.cumsum(y1, axis=-1, dtype=F32)], axis=-1)
+    idx_lo, idx_hi = searchsorted(t1, t0)
+    cy1_lo = np.take_along_axis(cy1, idx_lo, axis=-1)
+    cy1_hi = np.take_along_axis(cy1, idx_hi, axis=-1)
+    y0_outer = cy1_hi[..., 1:] - cy1_lo[..., :-1]
+    y0_inner = np.where(idx_hi[..., :-1] <= idx_lo[..., 1:], cy1_lo[..., 1:] - cy1_hi[..., :-1], F32(0))
+    return y0_inner.astype(F32), y0_outer.astype(F32)
+
+
+def lossfun_outer(t, w, t_env, w_env, eps=EPS):
+    """stepfun.py:82-89: max(0, w - w_outer)^2 / (w + eps) per interval of t."""
+    w = np.asarray(w, F32)
+    _, w_outer = inner_outer(t, t_env, w_env)
+    return (np.maximum(F32(0), w - w_outer) ** 2 / (w + F32(eps))).astype(F32)
+
+
+def lossfun_distortion(t, w):
+    """stepfun.py:266-276: iint w_i w_j |t_i - t_j| over the step function, per ray."""
+    t, w = np.asarray(t, F32), np.asarray(w, F32)
+    ut = (t[..., 1:] + t[..., :-1]) / F32(2)
+    dut = np.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = np.sum(w * np.sum(w[..., None, :] * dut, axis=-1, dtype=F32), axis=-1, dtype=F32)
+    loss_intra = np.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), axis=-1, dtype=F32) / F32(3)
+    return (loss_inter + loss_intra).astype(F32)
+
+
+def interval_distortion(t0_lo, t0_hi, t1_lo, t1_hi):
+    """stepfun.py:279-297: mean |x - y| for x in [t0_lo, t0_hi], y in [t1_lo, t1_hi] (float64: a test reference)."""
+    t0_lo, t0_hi, t1_lo, t1_hi = (np.asarray(x, np.float64) for x in (t0_lo, t0_hi, t1_lo, t1_hi))
+    d_disjoint = np.abs((t1_lo + t1_hi) / 2 - (t0_lo + t0_hi) / 2)
+    d_overlap = (2 * (np.minimum(t0_hi, t1_hi) ** 3 - np.maximum(t0_lo, t1_lo) ** 3)
+                 + 3 * (t1_hi * t0_hi * np.abs(t1_hi - t0_hi) + t1_lo * t0_lo * np.abs(t1_lo - t0_lo)
+                        + t1_hi * t0_lo * (t0_lo - t1_hi) + t1_lo * t0_hi * (t1_lo - t0_hi))) / (6 * (t0_hi - t0_lo) * (t1_hi - t1_lo))
+    return np.where((t0_lo > t1_hi) | (t1_lo > t0_hi), d_disjoint, d_overlap)
+
+
+def interlevel_loss(c, w, proposals, mult=1.0):
+    """train_utils.py:160-171: sum over proposal levels of mean(lossfun_outer(c, w, cp, wp))."""
+    return F32(mult) * sum(F32(np.mean(lossfun_outer(c, w, cp, wp))) for cp, wp in proposals)
+
+
+def distortion_loss(c, w, mult=0.01):
+    """train_utils.py:174-180."""
+    return F32(mult) * F32(np.mean(lossfun_distortion(c, w)))

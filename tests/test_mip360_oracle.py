@@ -86,3 +86,81 @@ def test_volumetric_rendering_and_losses_shapes():
     np.testing.assert_allclose(r["acc"] + np.maximum(0, 1 - r["acc"]), np.maximum(1, r["acc"]), rtol=1e-6)
     assert np.isfinite(M.depth_loss_kl(w, lv["t"], lv["prior"], 0.01 * 0.05, lv["dirs"]))
     assert M.depth_loss_mse(r["distance_mean"], lv["prior"]) >= 0 and M.depth_loss_l1(r["distance_mean"], lv["prior"]) >= 0
+
+
+# ---- N4: the interlevel / distortion regularisers, pinned by the reference's own property tests ----------------------
+def _brute_outer(t0, t1, w1):        # stepfun_test.py:40-50
+    return np.array([sum(w1[j] for j in range(len(t1) - 1) if t1[j + 1] >= t0[i] and t1[j] <= t0[i + 1]) for i in range(len(t0) - 1)])
+
+
+def _brute_inner(t0, t1, w1):        # stepfun_test.py:27-37
+    return np.array([sum(w1[j] for j in range(len(t1) - 1) if t1[j] >= t0[i] and t1[j + 1] < t0[i + 1]) for i in range(len(t0) - 1)])
+
+
+@pytest.mark.parametrize("num_ablate,is_all_zero", [(0, True), (2, False)])
+def test_lossfun_outer_same_and_ablated_point_sets(num_ablate, is_all_zero):
+    """stepfun_test.py:588-622: histograms of the same points bound each other (loss 0); drop points from one and it does not."""
+    rng = np.random.default_rng(0)
+    all_zero = True
+    for _ in range(10):
+        num_pts, d0, d1 = rng.integers(10, 20, 3)
+        t0, t1 = np.sort(rng.random(d0 + 1)).astype(np.float32), np.sort(rng.random(d1 + 1)).astype(np.float32)
+        lo, hi = max(t0.min(), t1.min()) + 0.1, min(t0.max(), t1.max()) - 0.1
+        pts = rng.uniform(lo, hi, num_pts)
+        pts_ablate = pts[:-num_ablate] if num_ablate > 0 else pts
+        w0 = np.array([np.mean((pts_ablate >= t0[i]) & (pts_ablate < t0[i + 1])) for i in range(d0)], np.float32)
+        w1 = np.array([np.mean((pts >= t1[i]) & (pts < t1[i + 1])) for i in range(d1)], np.float32)
+        all_zero &= bool(np.all(M.lossfun_outer(t0, w0, t1, w1) < 1e-12))
+    assert all_zero == is_all_zero
+
+
+def test_inner_outer_bound_and_match_brute_force():
+    """stepfun_test.py:624-655 (inner <= w <= outer for histograms of the same points) and :699-735 (brute-force measures)."""
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        d0, d1, num_pts = rng.integers(10, 20, 3)
+        t0, t1 = np.sort(rng.random(d0 + 1)).astype(np.float32), np.sort(rng.random(d1 + 1)).astype(np.float32)
+        lo, hi = max(t0.min(), t1.min()) + 0.1, min(t0.max(), t1.max()) - 0.1
+        pts = rng.uniform(lo, hi, num_pts)
+        w0 = np.array([np.sum((pts >= t0[i]) & (pts < t0[i + 1])) for i in range(d0)], np.float32)
+        w1 = np.array([np.sum((pts >= t1[i]) & (pts < t1[i + 1])) for i in range(d1)], np.float32)
+        w0_in, w0_out = M.inner_outer(t0, t1, w1)
+        w1_in, w1_out = M.inner_outer(t1, t0, w0)
+        assert np.all(w0_in <= w0) and np.all(w0 <= w0_out) and np.all(w1_in <= w1) and np.all(w1 <= w1_out)
+        wr = np.exp(rng.normal(size=d0)).astype(np.float32)
+        inn, out = M.inner_outer(t1, t0, wr)
+        np.testing.assert_allclose(out, _brute_outer(t1, t0, wr), atol=1e-5, rtol=1e-5)
+        np.testing.assert_allclose(inn, _brute_inner(t1, t0, wr), atol=1e-5, rtol=1e-5)
+
+
+def test_lossfun_outer_monotonic_invariance_and_self_zero():
+    """stepfun_test.py:657-697."""
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        d0, d1 = rng.integers(10, 20, 2)
+        t0, t1 = np.sort(rng.random(d0 + 1)).astype(np.float32), np.sort(rng.random(d1 + 1)).astype(np.float32)
+        w0, w1 = np.exp(rng.normal(size=d0)).astype(np.float32), np.exp(rng.normal(size=d1)).astype(np.float32)
+        curve = lambda x: (1 + x ** 3).astype(np.float32)
+        assert np.array_equal(M.lossfun_outer(t0, w0, t1, w1), M.lossfun_outer(curve(t0), w0, curve(t1), w1))
+        assert np.all(M.lossfun_outer(t0, w0, t0, w0) < 1e-10)
+
+
+def test_distortion_loss_matches_interval_distortion():
+    """stepfun_test.py:227-275: interval_distortion vs brute force, and lossfun_distortion == sum_ij w_i w_j d_ij."""
+    rng = np.random.default_rng(0)
+    n, d = 3, 7
+    t0 = np.sort(rng.uniform(-3, 3, (n, d + 1)), -1)
+    t1 = np.sort(rng.uniform(-3, 3, (n, d + 1)), -1)
+    dist = M.interval_distortion(t0[..., :-1], t0[..., 1:], t1[..., :-1], t1[..., 1:])
+    brute = np.zeros_like(dist)
+    for i in range(n):
+        for j in range(d):
+            brute[i, j] = np.mean(np.abs(np.linspace(t0[i, j], t0[i, j + 1], 2001)[:, None] - np.linspace(t1[i, j], t1[i, j + 1], 2001)[None, :]))
+    np.testing.assert_allclose(dist, brute, atol=1e-6, rtol=1e-3)
+    n, d = 3, 8
+    t = np.sort(rng.uniform(-3, 3, (n, d + 1)), -1).astype(np.float32)
+    w = M.softmax((2 * rng.normal(size=(n, d))).astype(np.float32))
+    losses = M.lossfun_distortion(t, w)
+    dd = M.interval_distortion(t[..., :-1, None], t[..., 1:, None], t[..., None, :-1], t[..., None, 1:])
+    alt = np.sum(w[:, None, :] * w[:, :, None] * dd, axis=(-1, -2))
+    np.testing.assert_allclose(losses, alt, atol=1e-6, rtol=1e-4)
