@@ -277,6 +277,20 @@ int mip360_depth_loss(const float* weights, const float* tdist, const float* ter
                       const float* predicted_depth, const float* dirs, int n_rays, int n_samples,
                       int depth_loss_type, float sigma, float* out_loss, void* workspace, void* stream);
 
+/* ---- N4 (partial): the regularisers of the mipnerf360 trainer (train_utils.py:160-180) ---------- */
+/* stepfun.lossfun_outer (stepfun.py:82-89; inner_outer :64-79, searchsorted :30-53): the proposal histogram (t_env
+ * [n,P+1], w_env [n,P]) must be an upper envelope of the NeRF histogram (t [n,S+1], w [n,S]):
+ * out_loss [n,S] = max(0, w - w_outer)^2 / (w + eps).  interlevel_loss is the mean of it, summed over proposal levels.
+ * With grad_loss [n,S] (d/d out_loss) also out_grad_w_env [n,P] -- the only input interlevel_loss differentiates
+ * (c and w pass through stop_gradient).  out_loss may be NULL in a backward-only call.  S, P <= 256. */
+int mip360_lossfun_outer(const float* t, const float* w, const float* t_env, const float* w_env, int n_rays, int n_bins,
+                         int n_env_bins, float eps, const float* grad_loss, float* out_loss, float* out_grad_w_env,
+                         void* stream);
+/* stepfun.lossfun_distortion (stepfun.py:266-276): out_loss [n] = sum_ij w_i w_j |u_i - u_j| + sum_i w_i^2 (t_i+1 - t_i)/3,
+ * u = interval midpoints; distortion_loss is its mean.  With grad_loss [n]: out_grad_t [n,S+1], out_grad_w [n,S]. */
+int mip360_lossfun_distortion(const float* t, const float* w, int n_rays, int n_bins, const float* grad_loss,
+                              float* out_loss, float* out_grad_t, float* out_grad_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

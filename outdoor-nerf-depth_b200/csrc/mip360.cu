@@ -216,6 +216,110 @@ __global__ void depth_loss_final_kernel(const double* __restrict__ partial, int 
   if (threadIdx.x == 0) out[0] = (float)(s[0] / denom);
 }
 
+
+// ---- N4: the regularisers of the mipnerf360 trainer (train_utils.py:160-180) -----------------
+// stepfun.lossfun_outer (stepfun.py:82-89) on top of inner_outer (:64-79) and searchsorted (:30-53), one warp per ray:
+//   cy = [0, cumsum(w_env)];  for every fencepost v = t[i]:  c = #{j : t_env[j] <= v},  lo = max(c-1, 0),  hi = min(c, P)
+//   w_outer[i] = cy[hi[i+1]] - cy[lo[i]] = sum of w_env[k] for k in [lo[i], hi[i+1]);   loss[i] = max(0, w[i]-w_outer[i])^2 / (w[i]+eps)
+// Backward (g = d/d loss, may be NULL for the forward alone): the only differentiable input of interlevel_loss is w_env
+// (c and w come through stop_gradient, the indices are piecewise constant):
+//   d w_env[k] = sum_i [lo[i] <= k < hi[i+1]] * g[i] * (-2 max(0, w[i]-w_outer[i]) / (w[i]+eps))
+__global__ void __launch_bounds__(WARPS * 32)
+lossfun_outer_kernel(const float* __restrict__ t, const float* __restrict__ w, const float* __restrict__ t_env,
+                     const float* __restrict__ w_env, int B, int S, int P, float eps, const float* __restrict__ g,
+                     float* __restrict__ out_loss, float* __restrict__ out_dwenv) {
+  __shared__ float s_te[WARPS][MAX_BINS + 1], s_cy[WARPS][MAX_BINS + 1], s_go[WARPS][MAX_BINS];
+  __shared__ short s_lo[WARPS][MAX_BINS + 1], s_hi[WARPS][MAX_BINS + 1];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS + wl;
+  if (r >= B) return;
+  float* te = s_te[wl]; float* cy = s_cy[wl]; float* go = s_go[wl];
+  short* lo = s_lo[wl]; short* hi = s_hi[wl];
+  for (int j = lane; j <= P; j += 32) te[j] = t_env[(size_t)r * (P + 1) + j];
+  // cy[0] = 0, cy[k+1] = w_env[0] + ... + w_env[k]   (fp32 inclusive scan, 32 at a time with a running carry)
+  float carry = 0.f;
+  if (lane == 0) cy[0] = 0.f;
+  for (int base = 0; base < P; base += 32) {
+    const int k = base + lane;
+    float v = k < P ? w_env[(size_t)r * P + k] : 0.f;
+    v = warp_incl_scan(v, lane) + carry;
+    if (k < P) cy[k + 1] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  __syncwarp();
+  for (int i = lane; i <= S; i += 32) {
+    const float v = t[(size_t)r * (S + 1) + i];
+    int a = 0, b = P + 1;                       // c = number of t_env[j] <= v
+    while (a < b) { const int mid = (a + b) >> 1; if (te[mid] <= v) a = mid + 1; else b = mid; }
+    lo[i] = (short)(a > 0 ? a - 1 : 0);
+    hi[i] = (short)(a < P + 1 ? a : P);
+  }
+  __syncwarp();
+  for (int i = lane; i < S; i += 32) {
+    const float wi = w[(size_t)r * S + i];
+    const float w_outer = cy[hi[i + 1]] - cy[lo[i]];
+    const float ex = fmaxf(0.f, wi - w_outer);
+    if (out_loss) out_loss[(size_t)r * S + i] = ex * ex / (wi + eps);
+    go[i] = g ? g[(size_t)r * S + i] * (-2.f * ex / (wi + eps)) : 0.f;
+  }
+  __syncwarp();
+  if (g && out_dwenv) {
+    for (int k = lane; k < P; k += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < S; ++i) acc += (lo[i] <= k && k < hi[i + 1]) ? go[i] : 0.f;
+      out_dwenv[(size_t)r * P + k] = acc;
+    }
+  }
+}
+
+// stepfun.lossfun_distortion (stepfun.py:266-276), one warp per ray, O(S^2):
+//   u_i = (t_i + t_{i+1}) / 2,  A_i = sum_j w_j |u_i - u_j|,  loss = sum_i w_i A_i + sum_i w_i^2 (t_{i+1} - t_i) / 3
+// Backward (g = d/d loss [B], NULL for the forward alone), with B_i = sum_j w_j sign(u_i - u_j):
+//   d w_i = g (2 A_i + (2/3) w_i (t_{i+1} - t_i)),   d u_i = 2 g w_i B_i,
+//   d t_k = (d u_{k-1} + d u_k) / 2 + g (w_{k-1}^2 - w_k^2) / 3      (terms with an index outside [0, S) dropped)
+__global__ void __launch_bounds__(WARPS * 32)
+lossfun_distortion_kernel(const float* __restrict__ t, const float* __restrict__ w, int B, int S, const float* __restrict__ g,
+                          float* __restrict__ out_loss, float* __restrict__ out_dt, float* __restrict__ out_dw) {
+  __shared__ float s_t[WARPS][MAX_BINS + 1], s_u[WARPS][MAX_BINS], s_w[WARPS][MAX_BINS], s_du[WARPS][MAX_BINS];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS + wl;
+  if (r >= B) return;
+  float* st = s_t[wl]; float* su = s_u[wl]; float* sw = s_w[wl]; float* du = s_du[wl];
+  for (int i = lane; i <= S; i += 32) st[i] = t[(size_t)r * (S + 1) + i];
+  for (int i = lane; i < S; i += 32) sw[i] = w[(size_t)r * S + i];
+  __syncwarp();
+  for (int i = lane; i < S; i += 32) su[i] = (st[i + 1] + st[i]) / 2.f;
+  __syncwarp();
+  const float gr = g ? g[r] : 0.f;
+  float part = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    const float ui = su[i], wi = sw[i];
+    float A = 0.f, Bs = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float d = ui - su[j];
+      A += sw[j] * fabsf(d);
+      Bs += sw[j] * (d > 0.f ? 1.f : d < 0.f ? -1.f : 0.f);
+    }
+    const float delta = st[i + 1] - st[i];
+    part += wi * A + wi * wi * delta / 3.f;
+    if (g) {
+      if (out_dw) out_dw[(size_t)r * S + i] = gr * (2.f * A + (2.f / 3.f) * wi * delta);
+      du[i] = 2.f * gr * wi * Bs;
+    }
+  }
+  part = warp_sum(part);
+  if (lane == 0 && out_loss) out_loss[r] = part;
+  __syncwarp();
+  if (g && out_dt) {
+    for (int k = lane; k <= S; k += 32) {
+      float v = 0.f;
+      if (k > 0) v += 0.5f * du[k - 1] + gr * sw[k - 1] * sw[k - 1] / 3.f;
+      if (k < S) v += 0.5f * du[k] - gr * sw[k] * sw[k] / 3.f;
+      out_dt[(size_t)r * (S + 1) + k] = v;
+    }
+  }
+}
+
 }  // namespace mip
 }  // namespace npp
 
@@ -272,6 +376,31 @@ extern "C" int mip360_depth_loss(const float* weights, const float* tdist, const
   NPP_CHECK_LAUNCH();
   const double denom = depth_loss_type == NERFPP_DEPTH_KL ? (double)n_rays * n_samples : (double)n_rays;
   mip::depth_loss_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)workspace, nb, denom, out_loss);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mip360_lossfun_outer(const float* t, const float* w, const float* t_env, const float* w_env, int n_rays, int n_bins,
+                                    int n_env_bins, float eps, const float* grad_loss, float* out_loss, float* out_grad_w_env,
+                                    void* stream) {
+  NPP_CHECK_ARG(t && w && t_env && w_env && (out_loss || (grad_loss && out_grad_w_env)), "null argument");
+  NPP_CHECK_ARG(!out_grad_w_env || grad_loss, "out_grad_w_env needs grad_loss");
+  NPP_CHECK_ARG(n_rays >= 0 && n_bins >= 1 && n_bins <= mip::MAX_BINS && n_env_bins >= 1 && n_env_bins <= mip::MAX_BINS, "bad shape");
+  if (n_rays == 0) return 0;
+  mip::lossfun_outer_kernel<<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, w, t_env, w_env, n_rays, n_bins, n_env_bins, eps, grad_loss, out_loss, out_grad_w_env);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mip360_lossfun_distortion(const float* t, const float* w, int n_rays, int n_bins, const float* grad_loss,
+                                         float* out_loss, float* out_grad_t, float* out_grad_w, void* stream) {
+  NPP_CHECK_ARG(t && w && (out_loss || grad_loss), "null argument");
+  NPP_CHECK_ARG((!out_grad_t && !out_grad_w) || grad_loss, "gradients need grad_loss");
+  NPP_CHECK_ARG(n_rays >= 0 && n_bins >= 1 && n_bins <= mip::MAX_BINS, "bad shape");
+  if (n_rays == 0) return 0;
+  mip::lossfun_distortion_kernel<<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, w, n_rays, n_bins, grad_loss, out_loss, out_grad_t, out_grad_w);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -123,3 +123,94 @@ def depth_point_loss(distance_mean, disps_sup, depth_loss_type):
     """The mse / l1 branch of train_utils.compute_data_loss (train_utils.py:109-121)."""
     typ = {"mse": DEPTH_MSE, "l1": DEPTH_L1}[depth_loss_type]
     return _loss(typ, None, None, disps_sup, distance_mean, None, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 (SURVEY.md section 8(f), partial): the two regularisers of the trainer (train_utils.py:160-180), with autograd
+# ------------------------------------------------------------------------------------------------
+class _LossfunOuter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, w, t_env, w_env, eps):
+        S, Pn = w.shape[-1], w_env.shape[-1]
+        lead = tuple(w.shape[:-1])
+        tt, ww = _c(t, "t").reshape(-1, S + 1), _c(w, "w").reshape(-1, S)
+        te, we = _c(t_env, "t_env").reshape(-1, Pn + 1), _c(w_env, "w_env").reshape(-1, Pn)
+        n = ww.shape[0]
+        if te.shape[0] != n or tt.shape[0] != n:
+            raise ValueError("lossfun_outer: leading dimensions of t, w, t_env, w_env must agree")
+        out = torch.empty(n, S, device=ww.device, dtype=torch.float32)
+        with torch.cuda.device(ww.device):
+            check(_lib.lib().mip360_lossfun_outer(_p(tt), _p(ww), _p(te), _p(we), n, S, Pn, float(eps), None, _p(out), None,
+                                                  _stream()), "mip360_lossfun_outer")
+        ctx.save_for_backward(tt, ww, te, we)
+        ctx.eps, ctx.env_shape = float(eps), tuple(w_env.shape)
+        return out.reshape(lead + (S,))
+
+    @staticmethod
+    def backward(ctx, g):
+        tt, ww, te, we = ctx.saved_tensors
+        n, S = ww.shape
+        Pn = we.shape[1]
+        gg = g.contiguous().float().reshape(n, S)
+        dwe = torch.empty(n, Pn, device=ww.device, dtype=torch.float32)
+        with torch.cuda.device(ww.device):
+            check(_lib.lib().mip360_lossfun_outer(_p(tt), _p(ww), _p(te), _p(we), n, S, Pn, ctx.eps, _p(gg), None, _p(dwe),
+                                                  _stream()), "mip360_lossfun_outer")
+        # interlevel_loss stops the gradient into (t, w) (train_utils.py:164-165) and the indices are piecewise constant
+        # in t_env: w_env is the one differentiable input
+        return None, None, None, dwe.reshape(ctx.env_shape), None
+
+
+def lossfun_outer(t, w, t_env, w_env, eps=EPS):
+    """stepfun.lossfun_outer (stepfun.py:82-89): [..., S] excess of the NeRF histogram (t, w) over the outer measure of the
+    proposal histogram (t_env, w_env).  Differentiable w.r.t. ``w_env``."""
+    return _LossfunOuter.apply(t, w, t_env, w_env, eps)
+
+
+class _LossfunDistortion(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, w):
+        S = w.shape[-1]
+        lead = tuple(w.shape[:-1])
+        tt, ww = _c(t, "t").reshape(-1, S + 1), _c(w, "w").reshape(-1, S)
+        n = ww.shape[0]
+        out = torch.empty(n, device=ww.device, dtype=torch.float32)
+        with torch.cuda.device(ww.device):
+            check(_lib.lib().mip360_lossfun_distortion(_p(tt), _p(ww), n, S, None, _p(out), None, None, _stream()),
+                  "mip360_lossfun_distortion")
+        ctx.save_for_backward(tt, ww)
+        ctx.shapes = (tuple(t.shape), tuple(w.shape))
+        return out.reshape(lead)
+
+    @staticmethod
+    def backward(ctx, g):
+        tt, ww = ctx.saved_tensors
+        n, S = ww.shape
+        gg = g.contiguous().float().reshape(n)
+        dt = torch.empty(n, S + 1, device=ww.device, dtype=torch.float32)
+        dw = torch.empty(n, S, device=ww.device, dtype=torch.float32)
+        with torch.cuda.device(ww.device):
+            check(_lib.lib().mip360_lossfun_distortion(_p(tt), _p(ww), n, S, _p(gg), None, _p(dt), _p(dw), _stream()),
+                  "mip360_lossfun_distortion")
+        return dt.reshape(ctx.shapes[0]), dw.reshape(ctx.shapes[1])
+
+
+def lossfun_distortion(t, w):
+    """stepfun.lossfun_distortion (stepfun.py:266-276): [...] = iint w_i w_j |t_i - t_j|.  Differentiable w.r.t. t and w."""
+    return _LossfunDistortion.apply(t, w)
+
+
+def interlevel_loss(ray_history, interlevel_loss_mult=1.0):
+    """train_utils.interlevel_loss (train_utils.py:160-171): ``ray_history`` is the list of per-level dicts with 'sdist' and
+    'weights'; the last level is the NeRF, the others the proposals."""
+    c, w = ray_history[-1]["sdist"].detach(), ray_history[-1]["weights"].detach()
+    loss = 0.
+    for rr in ray_history[:-1]:
+        loss = loss + lossfun_outer(c, w, rr["sdist"], rr["weights"]).mean()
+    return interlevel_loss_mult * loss
+
+
+def distortion_loss(ray_history, distortion_loss_mult=0.01):
+    """train_utils.distortion_loss (train_utils.py:174-180)."""
+    last = ray_history[-1]
+    return distortion_loss_mult * lossfun_distortion(last["sdist"], last["weights"]).mean()

@@ -98,3 +98,76 @@ def test_mip360_errors():
         mip360.compute_alpha_weights(torch.zeros(2, 4), torch.zeros(2, 5), torch.zeros(2, 3))
     with pytest.raises(NotImplementedError):
         mip360.depth_loss(None, None, None, None, 1.0, None, "urf")
+
+
+# ---- N4 (partial): interlevel / distortion regularisers -------------------------------------------------------------
+def _torch_lossfun_outer(t, w, t_env, w_env, eps):
+    """stepfun.py:30-89 restated with torch ops (autograd reference for the CUDA backward)."""
+    i = torch.arange(t_env.shape[-1], device=t.device)
+    v_ge_a = t[..., None, :] >= t_env[..., :, None]
+    idx_lo = torch.where(v_ge_a, i[:, None], i[:1, None]).amax(-2)
+    idx_hi = torch.where(~v_ge_a, i[:, None], i[-1:, None]).amin(-2)
+    cy = torch.cat([torch.zeros_like(w_env[..., :1]), torch.cumsum(w_env, -1)], -1)
+    w_outer = torch.gather(cy, -1, idx_hi)[..., 1:] - torch.gather(cy, -1, idx_lo)[..., :-1]
+    return torch.clamp(w - w_outer, min=0) ** 2 / (w + eps)
+
+
+def _torch_lossfun_distortion(t, w):
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = (ut[..., :, None] - ut[..., None, :]).abs()
+    return (w * (w[..., None, :] * dut).sum(-1)).sum(-1) + (w ** 2 * (t[..., 1:] - t[..., :-1])).sum(-1) / 3
+
+
+def _histograms(n, S, Pn, seed, temp=2.0):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.random((n, S + 1)), -1).astype(np.float32)
+    t[:, 0], t[:, -1] = 0.0, 1.0
+    te = np.sort(rng.random((n, Pn + 1)), -1).astype(np.float32)
+    te[:, 0], te[:, -1] = 0.0, 1.0
+    te[::7, 3] = t[::7, 2]                        # ties between a fencepost and an envelope edge
+    te = np.sort(te, -1)
+    w = M.softmax((temp * rng.normal(size=(n, S))).astype(np.float32))
+    we = M.softmax((temp * rng.normal(size=(n, Pn))).astype(np.float32))
+    return t, w, te, we
+
+
+@pytest.mark.parametrize("S,Pn", [(32, 64), (64, 64), (5, 9), (200, 33)])
+def test_lossfun_outer_matches_oracle_and_autograd(S, Pn):
+    from nerfpp_b200 import mip360
+    # Conditioning: the excess w - w_outer carries the few-ulp (of 1) differences between two fp32 cumsums, and the gradient
+    # divides it by w: mildly peaked weights (temperature 0.5, w >~ 1e-3) keep that at ~1e-4 while any indexing error
+    # (a range off by one bin) is an O(1) difference.
+    t, w, te, we = _histograms(1000 if S <= 64 else 50, S, Pn, seed=S + Pn, temp=0.5)
+    ref = M.lossfun_outer(t, w, te, we)
+    we_g = G(we).requires_grad_(True)
+    got = mip360.lossfun_outer(G(t), G(w), G(te), we_g)
+    # w_outer is a difference of two entries of a cumsum (<= 1): absolute error ~ a few ulp of 1, squared excess / w
+    np.testing.assert_allclose(N(got), ref, rtol=1e-4, atol=2e-6)
+    g = torch.rand_like(got)
+    (got * g).sum().backward()
+    we_r = G(we).requires_grad_(True)
+    (_torch_lossfun_outer(G(t), G(w), G(te), we_r, M.EPS) * g).sum().backward()
+    np.testing.assert_allclose(N(we_g.grad), N(we_r.grad), rtol=1e-3, atol=5e-4)
+    # self loss ~ 0 (stepfun_test.py:683-697: excess = cumsum rounding, squared) and the trainer-level wrapper
+    assert float(mip360.lossfun_outer(G(t), G(w), G(t), G(w)).max()) < 1e-8
+    hist = [dict(sdist=G(te), weights=we_g), dict(sdist=G(t), weights=G(w))]
+    want = M.interlevel_loss(t, w, [(te, we)])
+    assert abs(float(mip360.interlevel_loss(hist)) - float(want)) <= 1e-4 * abs(float(want)) + 1e-8
+
+
+@pytest.mark.parametrize("S", [32, 64, 7, 130])
+def test_lossfun_distortion_matches_oracle_and_autograd(S):
+    from nerfpp_b200 import mip360
+    t, w, _, _ = _histograms(1000 if S <= 64 else 40, S, 8, seed=S)
+    ref = M.lossfun_distortion(t, w)
+    tg, wg = G(t).requires_grad_(True), G(w).requires_grad_(True)
+    got = mip360.lossfun_distortion(tg, wg)
+    np.testing.assert_allclose(N(got), ref, rtol=1e-4, atol=1e-7)
+    g = torch.rand_like(got)
+    (got * g).sum().backward()
+    tr, wr = G(t).requires_grad_(True), G(w).requires_grad_(True)
+    (_torch_lossfun_distortion(tr, wr) * g).sum().backward()
+    np.testing.assert_allclose(N(wg.grad), N(wr.grad), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(N(tg.grad), N(tr.grad), rtol=2e-4, atol=2e-6)
+    want = M.distortion_loss(t, w)
+    assert abs(float(mip360.distortion_loss([dict(sdist=tg, weights=wg)])) - float(want)) <= 1e-4 * abs(float(want))
