@@ -10,7 +10,7 @@ Differences from the reference, on purpose:
     list to ``depth_files`` but reads ``depth_gt_files``, data_loader_split.py:83-89);
   * only resolution_level 1 (the only level the trainer uses, ddp_train_nerf.py never calls set_resolution_level).
 """
-import glob
+import fnmatch
 import logging
 import os
 
@@ -22,29 +22,34 @@ from nerfpp_b200.ray_sampler import DeviceRaySampler
 logger = logging.getLogger(__package__)
 
 
-def find_files(dir, exts):
-    if os.path.isdir(dir):
-        files_grabbed = []
-        for ext in exts:
-            files_grabbed.extend(glob.glob(os.path.join(dir, ext)))
-        return sorted(files_grabbed)
-    return []
+def find_files(dir, exts):                        # noqa: A002  (the reference's parameter names: callers pass exts=...)
+    """Sorted paths of the directory entries matching any of the shell patterns ([] when the directory is missing) --
+    what data_loader_split.py:14-24 returns."""
+    try:
+        names = os.listdir(dir)
+    except (FileNotFoundError, NotADirectoryError):
+        return []
+    # (like glob, a leading-dot name is not matched by '*')
+    return sorted(os.path.join(dir, nm) for nm in names if not nm.startswith('.') and any(fnmatch.fnmatch(nm, pat) for pat in exts))
 
 
 def read_image(path):
-    """Raw pixels as imageio.imread returns them: HxWx3 uint8 RGB, HxW uint8 or uint16."""
-    a = cv2.imread(path, cv2.IMREAD_UNCHANGED)
-    if a is None:
+    """Raw pixels in the layout imageio.imread gives the reference: HxWx3 uint8 RGB, HxW uint8 or uint16."""
+    px = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if px is None:
         raise IOError("cannot read image %s" % path)
-    if a.ndim == 3:
-        a = a[:, :, ::-1] if a.shape[2] == 3 else a[:, :, [2, 1, 0, 3]]
-    return np.ascontiguousarray(a)
+    if px.ndim == 3:                              # OpenCV decodes to BGR(A)
+        px = px[:, :, ::-1] if px.shape[2] == 3 else px[:, :, [2, 1, 0, 3]]
+    return np.ascontiguousarray(px)
 
 
 def parse_txt(filename):
-    assert os.path.isfile(filename)
-    nums = open(filename).read().split()
-    return np.array([float(x) for x in nums]).reshape([4, 4]).astype(np.float32)
+    """A 4x4 matrix stored as 16 whitespace-separated numbers, row-major (data_loader_split.py:29-32) -> float32."""
+    with open(filename) as f:
+        vals = np.array(f.read().split(), dtype=np.float64)
+    if vals.size != 16:
+        raise ValueError("%s: expected 16 numbers, found %d" % (filename, vals.size))
+    return vals.reshape(4, 4).astype(np.float32)
 
 
 def list_split(basedir, scene, split, skip=1, try_load_min_depth=True, depth_sup_type='gt'):
