@@ -194,7 +194,6 @@ def make_models(device):
 
 
 def run_ours(args):
-    import nerfpp_b200
     from nerfpp_b200 import GraphedRenderStep, PipelinedRenderStep, _lib, ops, render_rays
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))

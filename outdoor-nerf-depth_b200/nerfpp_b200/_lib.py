@@ -6,7 +6,7 @@ There is no fallback: if the library is missing or a call fails this raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NERFPP_B200_LIB") or os.path.join(HERE, "libnerfpp_b200.so")   # override: A/B diagnostics only

@@ -1,10 +1,9 @@
 """Autograd nodes for the depth-prior losses (CUDA forward + backward, no torch maths)."""
-import ctypes
 
 import torch
 
 from . import _lib
-from ._lib import DEPTH_KL, DEPTH_L1, DEPTH_MSE, NerfppError, check
+from ._lib import DEPTH_KL, DEPTH_L1, DEPTH_MSE, NerfppError, check  # noqa: F401  (the constants are re-exported: depth_loss.py uses them)
 from .ops import _c, _p, _stream
 
 

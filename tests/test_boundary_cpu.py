@@ -1,7 +1,6 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the
 header declares, the shim modules mirror the reference's import surface / state dict / RNG
 stream, and the product path refuses to run without CUDA (no fallback)."""
-import ctypes
 import hashlib
 import os
 import re
