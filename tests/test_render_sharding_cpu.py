@@ -87,3 +87,28 @@ def test_two_ranks_gloo_match_single_process():
     for m in range(2):
         for k in R.RENDER_KEYS:
             assert torch.equal(torch.from_numpy(got[m][k]), ref[m][k]), (m, k)
+
+
+def test_lazy_render_dict_behaves_like_the_plain_dict():
+    """The per-level result of render_single_image keeps the reference's keys and order; a deferred entry is fetched by
+    any access that could see its value, exactly once."""
+    from collections import OrderedDict
+    import torch
+    from nerfpp_b200.render import _LazyRenderDict
+    calls = []
+
+    def fetch():
+        calls.append(1)
+        return torch.arange(6.).reshape(2, 3)
+    d = _LazyRenderDict([("rgb", torch.zeros(2)), ("fg_dists", None), ("depth", torch.ones(2))], {"fg_dists": fetch})
+    assert list(d.keys()) == ["rgb", "fg_dists", "depth"] and len(d) == 3 and "fg_dists" in d and not calls
+    assert torch.equal(d["rgb"], torch.zeros(2)) and not calls
+    assert d["fg_dists"].shape == (2, 3) and len(calls) == 1
+    assert d.get("fg_dists").shape == (2, 3) and len(calls) == 1
+    d2 = _LazyRenderDict([("a", torch.zeros(1)), ("fg_dists", None)], {"fg_dists": fetch})
+    assert [tuple(v.shape) for v in d2.values()] == [(1,), (2, 3)] and len(calls) == 2
+    d3 = _LazyRenderDict([("fg_dists", None)], {"fg_dists": fetch})
+    assert dict(d3.items())["fg_dists"].shape == (2, 3)
+    d4 = _LazyRenderDict([("fg_dists", None), ("b", torch.zeros(1))], {"fg_dists": fetch})
+    c = d4.copy()
+    assert isinstance(c, OrderedDict) and c["fg_dists"].shape == (2, 3) and d4.pop("fg_dists").shape == (2, 3)
