@@ -248,3 +248,35 @@ def interlevel_loss(c, w, proposals, mult=1.0):
 def distortion_loss(c, w, mult=0.01):
     """train_utils.py:174-180."""
     return F32(mult) * F32(np.mean(lossfun_distortion(c, w)))
+
+
+# ---- proposal dilation (models.py:150-169 calls max_dilate_weights between levels) -- pinned by stepfun_test.py:277-300
+def query(tq, t, y, outside_value=0):
+    """stepfun.py:56-61: value of the step function (t, y) at tq."""
+    idx_lo, idx_hi = searchsorted(t, tq)
+    y = np.asarray(y, F32)       # (jnp clamps the out-of-range gather index of a query at/after the last edge; that value is masked)
+    return np.where(idx_lo == idx_hi, F32(outside_value), np.take_along_axis(y, np.minimum(idx_lo, y.shape[-1] - 1), axis=-1))
+
+
+def max_dilate(t, w, dilation, domain=(-np.inf, np.inf)):
+    """stepfun.py:99-113: max-pool a non-negative step function over +-dilation.  t [..., M+1], w [..., M] ->
+    t_dilate [..., 3M+1], w_dilate [..., 3M]."""
+    t, w = np.asarray(t, F32), np.asarray(w, F32)
+    t0 = t[..., :-1] - F32(dilation)
+    t1 = t[..., 1:] + F32(dilation)
+    t_dilate = np.sort(np.concatenate([t, t0, t1], axis=-1), axis=-1)
+    t_dilate = np.clip(t_dilate, F32(domain[0]), F32(domain[1]))
+    inside = (t0[..., None, :] <= t_dilate[..., None]) & (t1[..., None, :] > t_dilate[..., None])
+    w_dilate = np.max(np.where(inside, w[..., None, :], F32(0)), axis=-1)[..., :-1]
+    return t_dilate.astype(F32), w_dilate.astype(F32)
+
+
+def max_dilate_weights(t, w, dilation, domain=(-np.inf, np.inf), renormalize=False, eps=EPS ** 2):
+    """stepfun.py:116-128: the same on weights (through the pdf), optionally renormalised to sum 1."""
+    t, w = np.asarray(t, F32), np.asarray(w, F32)
+    p = w / np.maximum(F32(eps), t[..., 1:] - t[..., :-1])                     # weight_to_pdf :89-91
+    t_dilate, p_dilate = max_dilate(t, p, dilation, domain)
+    w_dilate = p_dilate * (t_dilate[..., 1:] - t_dilate[..., :-1])               # pdf_to_weight :94-96
+    if renormalize:
+        w_dilate = w_dilate / np.maximum(F32(eps), np.sum(w_dilate, axis=-1, keepdims=True, dtype=F32))
+    return t_dilate, w_dilate.astype(F32)

@@ -320,6 +320,68 @@ lossfun_distortion_kernel(const float* __restrict__ t, const float* __restrict__
   }
 }
 
+
+// stepfun.max_dilate / max_dilate_weights (stepfun.py:99-128; models.py:150-169 dilates the proposal histogram between
+// levels), one warp per ray.  The 3M+1 fenceposts  sort(cat(t, t[:-1]-d, t[1:]+d))  come from a warp bitonic sort in
+// shared memory (values only, padded with +inf), are clipped to the domain, and every dilated interval takes the max of
+// the values whose widened interval [t_j - d, t_j+1 + d) contains its left fencepost.  weights_mode: the values are the
+// pdf w / max(eps, dt) going in and are multiplied by the dilated interval widths coming out (weight_to_pdf /
+// pdf_to_weight :89-96), optionally renormalised to sum 1.
+constexpr int DIL_MAX_BINS = 85;              // 3 M + 1 <= 256
+__global__ void __launch_bounds__(WARPS * 32)
+max_dilate_kernel(const float* __restrict__ t, const float* __restrict__ w, int B, int M, float dilation, float dmin, float dmax,
+                  int weights_mode, int renormalize, float eps, float* __restrict__ out_t, float* __restrict__ out_w) {
+  __shared__ float s_all[WARPS][256], s_t0[WARPS][DIL_MAX_BINS], s_t1[WARPS][DIL_MAX_BINS], s_v[WARPS][DIL_MAX_BINS], s_wd[WARPS][256];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS + wl;
+  if (r >= B) return;
+  float* all = s_all[wl]; float* t0 = s_t0[wl]; float* t1 = s_t1[wl]; float* v = s_v[wl]; float* wd = s_wd[wl];
+  const int n_out = 3 * M + 1;
+  int P = 2;
+  while (P < n_out) P <<= 1;
+  const float* tr = t + (size_t)r * (M + 1);
+  for (int j = lane; j <= M; j += 32) all[j] = tr[j];
+  for (int j = n_out + lane; j < P; j += 32) all[j] = INFINITY;
+  __syncwarp();
+  for (int j = lane; j < M; j += 32) {
+    const float a = all[j], b = all[j + 1];
+    const float lo = __fsub_rn(a, dilation), hi = __fadd_rn(b, dilation);
+    t0[j] = lo; t1[j] = hi;
+    all[M + 1 + j] = lo; all[2 * M + 1 + j] = hi;
+    const float wj = w[(size_t)r * M + j];
+    v[j] = weights_mode ? __fdiv_rn(wj, fmaxf(eps, __fsub_rn(b, a))) : wj;
+  }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = lane; q < (P >> 1); q += 32) {
+        const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int l = i | j;
+        const float a = all[i], b = all[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up && a != b) { all[i] = b; all[l] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  for (int k = lane; k < n_out; k += 32) all[k] = fminf(fmaxf(all[k], dmin), dmax);      // jnp.clip(t_dilate, *domain)
+  __syncwarp();
+  float part = 0.f;
+  for (int k = lane; k < n_out - 1; k += 32) {
+    const float tk = all[k];
+    float m = 0.f;
+    for (int j = 0; j < M; ++j) if (t0[j] <= tk && t1[j] > tk) m = fmaxf(m, v[j]);
+    if (weights_mode) m = __fmul_rn(m, __fsub_rn(all[k + 1], tk));
+    wd[k] = m;
+    part += m;
+  }
+  part = warp_sum(part);
+  const float inv = (weights_mode && renormalize) ? fmaxf(eps, part) : 1.f;
+  __syncwarp();
+  for (int k = lane; k < n_out; k += 32) out_t[(size_t)r * n_out + k] = all[k];
+  for (int k = lane; k < n_out - 1; k += 32) out_w[(size_t)r * (n_out - 1) + k] = (weights_mode && renormalize) ? __fdiv_rn(wd[k], inv) : wd[k];
+}
+
 }  // namespace mip
 }  // namespace npp
 
@@ -401,6 +463,18 @@ extern "C" int mip360_lossfun_distortion(const float* t, const float* w, int n_r
   if (n_rays == 0) return 0;
   mip::lossfun_distortion_kernel<<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
       t, w, n_rays, n_bins, grad_loss, out_loss, out_grad_t, out_grad_w);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mip360_max_dilate(const float* t, const float* w, int n_rays, int n_bins, float dilation, float domain_min,
+                                 float domain_max, int weights_mode, int renormalize, float eps, float* out_t, float* out_w,
+                                 void* stream) {
+  NPP_CHECK_ARG(t && w && out_t && out_w, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && n_bins >= 1 && n_bins <= mip::DIL_MAX_BINS, "bad shape (at most 85 bins: 3 M + 1 <= 256 fenceposts)");
+  if (n_rays == 0) return 0;
+  mip::max_dilate_kernel<<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, w, n_rays, n_bins, dilation, domain_min, domain_max, weights_mode, renormalize, eps, out_t, out_w);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -71,6 +71,7 @@ SIGNATURES = {
     "nerfpp_image_metrics": (c_int, [P, P, P, P, c_int64, c_float, c_float, P, P, P]),
     "mip360_sample_intervals": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, P, P]),
     "mip360_lossfun_outer": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P]),
+    "mip360_max_dilate": (c_int, [P, P, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, P, P, P]),
     "mip360_lossfun_distortion": (c_int, [P, P, c_int, c_int, P, P, P, P, P]),
     "mip360_compute_alpha_weights": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P]),
     "mip360_volumetric_rendering": (c_int, [P, P, P, P, c_int, P, c_int, c_int, P, P, P]),

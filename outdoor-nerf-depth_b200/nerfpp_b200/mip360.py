@@ -214,3 +214,29 @@ def distortion_loss(ray_history, distortion_loss_mult=0.01):
     """train_utils.distortion_loss (train_utils.py:174-180)."""
     last = ray_history[-1]
     return distortion_loss_mult * lossfun_distortion(last["sdist"], last["weights"]).mean()
+
+
+def _max_dilate(t, w, dilation, domain, weights_mode, renormalize, eps):
+    ww = _c(w, "w")
+    lead = tuple(ww.shape[:-1])
+    M = ww.shape[-1]
+    ww = ww.reshape(-1, M)
+    tt = _c(t, "t").reshape(-1, M + 1)
+    n = ww.shape[0]
+    out_t = torch.empty(n, 3 * M + 1, device=ww.device, dtype=torch.float32)
+    out_w = torch.empty(n, 3 * M, device=ww.device, dtype=torch.float32)
+    with torch.cuda.device(ww.device):
+        check(_lib.lib().mip360_max_dilate(_p(tt), _p(ww), n, M, float(dilation), float(domain[0]), float(domain[1]), int(weights_mode),
+                                           int(bool(renormalize)), float(eps), _p(out_t), _p(out_w), _stream()), "mip360_max_dilate")
+    return out_t.reshape(lead + (3 * M + 1,)), out_w.reshape(lead + (3 * M,))
+
+
+def max_dilate(t, w, dilation, domain=(-math.inf, math.inf)):
+    """stepfun.max_dilate (stepfun.py:99-113): dilate (max-pool) a non-negative step function.  No gradient (the proposal
+    resampling path is not differentiated)."""
+    return _max_dilate(t, w, dilation, domain, 0, False, EPS ** 2)
+
+
+def max_dilate_weights(t, w, dilation, domain=(-math.inf, math.inf), renormalize=False, eps=EPS ** 2):
+    """stepfun.max_dilate_weights (stepfun.py:116-128), as models.py:150-169 applies it between proposal levels."""
+    return _max_dilate(t, w, dilation, domain, 1, renormalize, eps)

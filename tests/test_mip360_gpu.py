@@ -171,3 +171,31 @@ def test_lossfun_distortion_matches_oracle_and_autograd(S):
     np.testing.assert_allclose(N(tg.grad), N(tr.grad), rtol=2e-4, atol=2e-6)
     want = M.distortion_loss(t, w)
     assert abs(float(mip360.distortion_loss([dict(sdist=tg, weights=wg)])) - float(want)) <= 1e-4 * abs(float(want))
+
+
+@pytest.mark.parametrize("M_bins", [64, 8, 85, 1])
+def test_max_dilate_matches_oracle(M_bins):
+    """stepfun.max_dilate / max_dilate_weights (stepfun.py:99-128): fenceposts bit-exact (sort + clip), values bit-exact
+    without renormalisation (max, one division, one product), 1e-5 with it (one fp32 sum)."""
+    from nerfpp_b200 import mip360
+    rng = np.random.default_rng(M_bins)
+    n = 500
+    t = np.sort(rng.random((n, M_bins + 1)), -1).astype(np.float32)
+    t[::5, 1:2] = t[::5, 0:1]                                   # an empty interval now and then
+    w = M.softmax((2 * rng.normal(size=(n, M_bins))).astype(np.float32))
+    for dil, dom in ((0.0123, (-np.inf, np.inf)), (0.05, (0.0, 1.0)), (0.5 / 64, (0.1, 0.9))):
+        rt, rw = M.max_dilate(t, w, dil, dom)
+        gt, gw = mip360.max_dilate(G(t), G(w), dil, dom)
+        assert np.array_equal(N(gt), rt) and np.array_equal(N(gw), rw), (M_bins, dil)
+        rt, rw = M.max_dilate_weights(t, w, dil, dom, renormalize=False)
+        gt, gw = mip360.max_dilate_weights(G(t), G(w), dil, dom, renormalize=False)
+        assert np.array_equal(N(gt), rt)
+        np.testing.assert_allclose(N(gw), rw, rtol=1e-6, atol=0)
+        rt, rw = M.max_dilate_weights(t, w, dil, dom, renormalize=True)
+        gt, gw = mip360.max_dilate_weights(G(t), G(w), dil, dom, renormalize=True)
+        np.testing.assert_allclose(N(gw), rw, rtol=1e-5, atol=1e-12)
+        # sums to one wherever the dilated histogram has mass (a zero-width histogram clipped to nothing stays all zero)
+        np.testing.assert_allclose(N(gw).sum(-1), rw.sum(-1), rtol=1e-5, atol=1e-12)
+        assert np.all((np.abs(rw.sum(-1) - 1) < 1e-4) | (rw.sum(-1) == 0))
+    with pytest.raises(Exception):
+        mip360.max_dilate(G(np.zeros((2, 100), np.float32)), G(np.zeros((2, 99), np.float32)), 0.1)

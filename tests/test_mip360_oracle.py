@@ -164,3 +164,23 @@ def test_distortion_loss_matches_interval_distortion():
     dd = M.interval_distortion(t[..., :-1, None], t[..., 1:, None], t[..., None, :-1], t[..., None, 1:])
     alt = np.sum(w[:, None, :] * w[:, :, None] * dd, axis=(-1, -2))
     np.testing.assert_allclose(losses, alt, atol=1e-6, rtol=1e-4)
+
+
+def test_max_dilate_against_brute_force_queries():
+    """stepfun_test.py:277-300: a query of the dilated step function is the max of the original over +-dilation."""
+    rng = np.random.default_rng(0)
+    n, d, dilation = 20, 8, 0.53
+    t = (np.cumsum(rng.integers(1, 10, (n, d + 1)), -1) / 10).astype(np.float32)
+    w = M.softmax(rng.normal(size=(n, d)).astype(np.float32))
+    td, wd = M.max_dilate(t, w, dilation)
+    assert td.shape == (n, 3 * d + 1) and wd.shape == (n, 3 * d)
+    tq = ((np.arange((d + 4) * 10) - 2.5) / 10).astype(np.float32)
+    wq = M.query(np.broadcast_to(tq, (n, tq.size)), t, w)
+    wdq = M.query(np.broadcast_to(tq, (n, tq.size)), td, wd)
+    mask = np.abs(tq[None, :] - tq[:, None]) <= dilation
+    for i in range(n):
+        np.testing.assert_array_equal(wdq[i], np.max(mask * wq[i], axis=-1))
+    # weights variant: renormalised output sums to one, the domain clips the fenceposts
+    td, wd = M.max_dilate_weights(t, w, 0.2, domain=(0.5, 4.0), renormalize=True)
+    np.testing.assert_allclose(wd.sum(-1), 1.0, rtol=1e-5)
+    assert td.min() >= 0.5 and td.max() <= 4.0 and np.all(np.diff(td, axis=-1) >= 0) and np.all(wd >= 0)
