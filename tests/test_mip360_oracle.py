@@ -184,3 +184,21 @@ def test_max_dilate_against_brute_force_queries():
     td, wd = M.max_dilate_weights(t, w, 0.2, domain=(0.5, 4.0), renormalize=True)
     np.testing.assert_allclose(wd.sum(-1), 1.0, rtol=1e-5)
     assert td.min() >= 0.5 and td.max() <= 4.0 and np.all(np.diff(td, axis=-1) >= 0) and np.all(wd >= 0)
+
+
+def test_searchsorted_contract():
+    """stepfun_test.py:55-146: a[lo] <= v < a[hi] inside the range, both indices clamp to the first / last edge outside
+    it, and idx_hi equals numpy's searchsorted(side='right') for in-range queries."""
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        n, m = rng.integers(10, 100, 2)
+        v = rng.uniform(1e-7, 1 - 1e-7, n).astype(np.float32)
+        a = np.sort(np.concatenate([[0.0, 1.0], rng.random(m)])).astype(np.float32)
+        lo, hi = M.searchsorted(a, v)
+        assert np.all(a[lo] <= v) and np.all(v < a[hi])
+        assert np.array_equal(hi, np.searchsorted(a, v, side="right"))
+        below, above = (a[0] - 0.1 - rng.random(5)).astype(np.float32), (a[-1] + 0.1 + rng.random(5)).astype(np.float32)
+        lo, hi = M.searchsorted(a, below)
+        assert np.all(lo == 0) and np.all(hi == 0)
+        lo, hi = M.searchsorted(a, above)
+        assert np.all(lo == len(a) - 1) and np.all(hi == len(a) - 1)
