@@ -187,3 +187,22 @@ def test_bench_reference_arm_prints_one_json_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                        capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_missing_library_fails_loudly():
+    """No silent fallback: with the shared library absent, the first call through the binding raises NerfppError that
+    says how to build it (checked in a child process so this process's loaded library is left alone)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from nerfpp_b200 import _lib\n"
+        "_lib.LIB_PATH = '/nonexistent/libnerfpp_b200.so'\n"
+        "_lib._lib = None\n"
+        "try:\n"
+        "    _lib.lib()\n"
+        "except _lib.NerfppError as e:\n"
+        "    assert 'not built' in str(e) and 'no CPU or PyTorch fallback' in str(e), str(e)\n"
+        "    print('raised')\n" % os.path.join(ROOT, "outdoor-nerf-depth_b200"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == "raised", p.stderr[-1500:]
