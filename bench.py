@@ -519,52 +519,74 @@ def parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev):
             "against": "oracle/nerfpp_oracle.py on the same rays, weights and random draws (train path, both levels)"}
 
 
-def cpu_baseline(sample=4096, reps=4, dev=None):
+def reference_cpu_arm():
+    """The CPU arm's step function and what it is.  When the reference's own files are present (the git-ignored copy
+    ``baseline/_ref/nerfplusplus`` made by oracle/install_reference.py, or /root/reference in the build container) the step
+    calls the UNMODIFIED reference functions wired as the trainer's cascade loop (oracle/ref_harness.py): kind
+    "reference".  Otherwise the oracle port (kind "port")."""
+    try:
+        import ref_harness as RH
+        if RH.available():
+            nets = RH.build_nets(len(CASCADE), sigma_bias=5.0)
+            step = lambda rays: RH.reference_step(nets, rays, CASCADE, "mse", LAMBDA_DEPTH, DEPTH_SIGMA)
+            return step, "reference", ("the reference's own functions, unmodified (intersect_sphere / perturb_samples / sample_pdf, "
+                                       "NerfNetWithAutoExpo.forward, img2mse, depth_mse) wired as ddp_train_nerf.py:432-493, torch-CPU fp32")
+    except Exception as e:   # noqa: BLE001  (fall back to the port, say why)
+        sys.stderr.write("reference files unusable (%r): timing the oracle port instead\n" % (e,))
+    import nerfpp_oracle as O
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    return (lambda rays: reference_step(levels, rays, O)), "port", "oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference"
+
+
+def cpu_baseline(sample=N_RAYS, reps=4, dev=None):
+    """cpu_baseline leg of the product arm: the reference's CPU implementation on all host cores on ``reps`` batches of
+    the SAME 4096-ray workload, and -- the same leg, as the checker -- the parity of the CUDA path against the oracle."""
     import nerfpp_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
-    reference_step(levels, make_rays(64, 5), O)     # warm-up
+    step, kind, what = reference_cpu_arm()
     rays = make_rays(sample, 6)
+    step(make_rays(64, 5))     # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
-        ref_out, ref_losses = reference_step(levels, rays, O)
+        step(rays)
     dt = time.perf_counter() - t0
-    base = {"value": reps * sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d x %d rays of the same workload (oracle/nerfpp_oracle.py: torch-CPU fp32 restatement of the reference, "
-                      "all host threads), %.1f s" % (reps, sample, dt)}
-    parity = parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev) if dev is not None else None
+    base = {"value": reps * sample / dt, "unit": "rays/s", "cores": cores, "kind": kind,
+            "sample": "%d x %d rays of the same workload (%s, all host threads), %.1f s" % (reps, sample, what, dt)}
+    parity = None
+    if dev is not None:
+        levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+        ref_out, ref_losses = reference_step(levels, rays, O)
+        parity = parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev)
     return base, parity
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm for the path on the host cores (the oracle port;
-    /root/reference is Python+torch and does not travel to the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, on this arm's config
+    (4096 rays per step, cascade 64 -> +128, mse): baseline/_ref when the reference files travelled, else the oracle port."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    import nerfpp_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 512
-    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
-    rays = make_rays(sample, 6)
-    warm = max(1, min(args.warmup, 5))          # K and W as asked, bounded so the arm always ends within a minute or two
+    step, kind, what = reference_cpu_arm()
+    rays = make_rays(N_RAYS, 6)
+    warm, steps = max(1, args.warmup), max(1, args.steps)
     for _ in range(warm):
-        reference_step(levels, rays, O)
-    steps = max(1, min(args.steps, 40))
+        step(rays)
     t0 = time.perf_counter()
     for _ in range(steps):
-        reference_step(levels, rays, O)
+        step(rays)
     dt = (time.perf_counter() - t0) / steps
-    v = sample / dt
+    v = N_RAYS / dt
     world = int(os.environ.get("WORLD_SIZE", 1))
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_rays_per_step": sample},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": "%d rays/step of the same workload, torch-CPU fp32, %d threads" % (sample, cores)},
+        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "global_rays": N_RAYS, "cascade_samples": list(CASCADE),
+                   "unit_of_work": "U2 forward (SURVEY 8(d)): 2.512 TFLOP algorithmic per 4096 rays", "where": "host cores of the GPU box"},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": "%d rays/step of the same workload (%s), %d threads" % (N_RAYS, what, cores)},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 

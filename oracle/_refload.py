@@ -2,17 +2,25 @@
 
 The reference (``/root/reference/nerf-methods/nerfplusplus``) imports a few non-numeric packages at
 module scope that are not installed here (matplotlib, tensorboardX, imageio, configargparse;
-``utils.py:37-41``, ``ddp_train_nerf.py:13,17``).  They are replaced by empty stub modules; no
-arithmetic goes through them.  Used ONLY by ``oracle/gen_golden.py`` to
-produce ``tests/golden/*.npz``; nothing under tests/, bench.py or the product imports this at run
-time on the GPU box (the reference tree does not travel).
+``utils.py:37-41``, ``ddp_train_nerf.py:13,17``).  They are replaced by the import-only stand-ins of
+``outdoor-nerf-depth_b200/compat``; no arithmetic goes through them.  Used by
+``oracle/gen_golden.py`` (from ``/root/reference``, build container only) to produce ``tests/golden/*.npz`` and by
+``bench.py``'s CPU legs / ``oracle/ref_harness.py``, which on the GPU box find the git-ignored copy
+``baseline/_ref/nerfplusplus`` made by ``oracle/install_reference.py`` (and fall back to the oracle port without it).
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("NERFPP_REFERENCE", "/root/reference/nerf-methods/nerfplusplus")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = (os.environ.get("NERFPP_REFERENCE"), "/root/reference/nerf-methods/nerfplusplus",
+               os.path.join(_ROOT, "baseline", "_ref", "nerfplusplus"))      # the copy oracle/install_reference.py makes
+REF_ROOT = next((p for p in _CANDIDATES if p and os.path.isdir(p)), _CANDIDATES[1])
+
+
+def available():
+    return os.path.isdir(REF_ROOT)
 
 
 def _stub(name, **attrs):
@@ -22,34 +30,42 @@ def _stub(name, **attrs):
     return m
 
 
-def load_reference():
-    """Returns (ddp_train_nerf, ddp_model, depth_loss, utils) reference modules."""
+_NAMES = ("ddp_model", "depth_loss", "utils", "nerf_network", "ddp_train_nerf", "data_loader_split", "nerf_sample_ray_split")
+_COMPAT = os.path.join(_ROOT, "outdoor-nerf-depth_b200", "compat")
+_loaded = None
+
+
+def load_reference(isolated=True):
+    """Returns (ddp_train_nerf, ddp_model, depth_loss, utils) -- the reference's modules, unmodified.
+
+    The product ships drop-in modules with the SAME names (``ddp_model``, ``depth_loss``, ``data_loader_split``).  With
+    ``isolated`` (default) the reference is imported while those names are taken out of ``sys.modules`` / its directory is
+    first on ``sys.path``, and both are restored afterwards: the returned module objects keep working (their globals are
+    bound), while ``import ddp_model`` elsewhere in the process still means the product's module."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
     if not os.path.isdir(REF_ROOT):
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
-    if "matplotlib" not in sys.modules:
-        mpl = _stub("matplotlib", use=lambda *a, **k: None)
-        _stub("matplotlib.backends")
-        _stub("matplotlib.backends.backend_agg", FigureCanvasAgg=object)
-        _stub("matplotlib.figure", Figure=object)
-        _stub("matplotlib.cm")
-        _stub("matplotlib.pyplot")
-        mpl.cm = sys.modules["matplotlib.cm"]
-        mpl.colors = _stub("matplotlib.colors")
-        mpl.colorbar = _stub("matplotlib.colorbar")
-    for name in ("tensorboardX", "imageio", "configargparse"):
-        if name not in sys.modules:
-            try:
-                importlib.import_module(name)
-            except Exception:
-                _stub(name, SummaryWriter=object)
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
-    # make sure we do not pick up the drop-in shim modules of the same name
-    for name in ("ddp_model", "depth_loss", "utils", "nerf_network", "ddp_train_nerf"):
-        mod = sys.modules.get(name)
-        if mod is not None and not getattr(mod, "__file__", "").startswith(REF_ROOT):
-            del sys.modules[name]
-    import ddp_train_nerf, ddp_model, depth_loss, utils  # noqa: E401
-    for m in (ddp_train_nerf, ddp_model, depth_loss, utils):
-        assert m.__file__.startswith(REF_ROOT), m.__file__
-    return ddp_train_nerf, ddp_model, depth_loss, utils
+    for name in ("matplotlib", "tensorboardX", "imageio", "configargparse"):      # non-numeric imports of the reference
+        try:
+            importlib.import_module(name)
+        except Exception:
+            if _COMPAT not in sys.path:
+                sys.path.append(_COMPAT)                                              # the same stand-ins the launcher uses
+            importlib.import_module(name)
+    saved_mods = {n: sys.modules.pop(n) for n in _NAMES if n in sys.modules}
+    saved_path = list(sys.path)
+    sys.path.insert(0, REF_ROOT)
+    try:
+        import ddp_train_nerf, ddp_model, depth_loss, utils  # noqa: E401
+        for m in (ddp_train_nerf, ddp_model, depth_loss, utils):
+            assert m.__file__.startswith(REF_ROOT), m.__file__
+        _loaded = (ddp_train_nerf, ddp_model, depth_loss, utils)
+    finally:
+        if isolated:
+            for n in _NAMES:
+                sys.modules.pop(n, None)
+            sys.modules.update(saved_mods)
+            sys.path[:] = saved_path
+    return _loaded

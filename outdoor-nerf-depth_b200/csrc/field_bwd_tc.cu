@@ -14,6 +14,7 @@
 //
 // All gradients inside this kernel are multiplied by a power-of-two loss scale (read from device memory) so that they
 // survive the fp16 operand format; wgrad_tc.cu divides it out again.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace npp {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const uint8_t* __restrict__ act,
                    const uint8_t* __restrict__ mask, const float* __restrict__ rgb, const float* __restrict__ raw_sigma, const float* __restrict__ d_sigma,
                    const float* __restrict__ d_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
-                   uint8_t* __restrict__ dz, float* __restrict__ d_raw_sigma, float* __restrict__ d_raw_rgb) {
+                   uint8_t* __restrict__ dz, float* __restrict__ d_raw_sigma, float* __restrict__ d_raw_rgb, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
@@ -94,6 +95,7 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
         for (int i = 0; i < tab.n; ++i, ++it) {
           const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1;
           mbar_wait(bar(B_WEMPTY + st), ph ^ 1);
+          if ((flags & 8) && it >= NSTAGE) { mbar_arrive(bar(B_WFULL + st)); continue; }   // timing experiment: no refill (wrong results)
           mbar_expect_tx(bar(B_WFULL + st), STAGE_BYTES);
           bulk_g2s(s_base + OFF_W + st * STAGE_BYTES, blobs + tab.s[i].blob_off, STAGE_BYTES, bar(B_WFULL + st));
         }
@@ -263,7 +265,7 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
           }
           // the copy for the weight-gradient kernel leaves behind the arrive, off the chain the tensor pipe waits for,
           // through shared memory and one bulk copy per warp pair
-          stage_store_chunk(stg, stg_flip, dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), q, lane, hh, pk);
+          if (!(flags & 1024)) stage_store_chunk(stg, stg_flip, dz + act_chunk_off(l, (size_t)num_tiles, (size_t)tile, j), q, lane, hh, pk, (flags & 2048) != 0);
         }
       }
     }
@@ -328,8 +330,10 @@ int npp_field_dgrad(const void* packed, const void* act, const void* mask, const
   const uint8_t* blobs = (const uint8_t*)packed;
   const float* tail = (const float*)(blobs + tcb::h_tab.total);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  static int dflags = -1;          // experiment switches (diagnostics only), same meaning as field_tc.cu's
+  if (dflags < 0) { const char* f = getenv("NERFPP_TC_FLAGS"); dflags = f ? atoi(f) : 0; }
   tcb::field_dgrad_kernel<<<grid, tcb::THREADS, tcb::SMEM_BYTES, st>>>(blobs, tail, (const uint8_t*)act, (const uint8_t*)mask, rgb, raw_sigma, d_sigma, d_rgb,
-                                                                        scale, total, num_tiles, (uint8_t*)dz, d_raw_sigma, d_raw_rgb);
+                                                                        scale, total, num_tiles, (uint8_t*)dz, d_raw_sigma, d_raw_rgb, dflags);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -138,7 +138,7 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 template <int KIND, bool SAVE>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
-                                               uint32_t& stg_flip, float& sig_part, long long* probe_slot) {
+                                               uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
   uint32_t v[2][32];
   uint32_t mbits[4];
   tmem_ld32(acc_addr, v[0]);
@@ -158,7 +158,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
     if (probe_slot) probe_slot[j] = clock64();
     if (SAVE) {   // training, behind the arrive: the fp16 activations leave through shared memory and one bulk copy per warp
                   // pair (tc_common.cuh), and their ReLU mask is kept as bits for the dgrad chain
-      stage_store_chunk(stg, stg_flip, act_chunk0 + (size_t)j * CHUNK_BYTES, row >> 5, lane, hh, pk);
+      if (!(xflags & 1024)) stage_store_chunk(stg, stg_flip, act_chunk0 + (size_t)j * CHUNK_BYTES, row >> 5, lane, hh, pk, (xflags & 2048) != 0);
       if (KIND != 2) mbits[j] = relu_mask_bits(pk);
     }
     if (KIND == 1) {
@@ -180,10 +180,10 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
 template <bool SAVE>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                   const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
-                                                  uint32_t& stg_flip, float& sig_part, long long* probe_slot) {
-  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
-  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
-  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot);
+                                                  uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
+  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
 }
 
 // Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
@@ -524,7 +524,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
         if (TRAIN) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
                                               reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)),
-                                              smem + OFF_STG_TRAIN, stg_flip, sig_part, probe);
+                                              smem + OFF_STG_TRAIN, stg_flip, sig_part, probe, flags);
         else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe);
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
         if (m == 0) flush_pending();
@@ -709,8 +709,9 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     save.mask = w + tc::train_ws_mask_off((size_t)num_tiles);
   }
 #define NPP_TC_LAUNCH(BG, C, T) launch_tc<BG, C, T>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
-  if (train_ws) {     // the training forward always runs unclustered (the cluster variant is an inference experiment)
-    return bg ? NPP_TC_LAUNCH(true, 1, true) : NPP_TC_LAUNCH(false, 1, true);
+  if (train_ws) {     // (the cluster variant is an experiment: NERFPP_TC_CLUSTER=2)
+    if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, true) : NPP_TC_LAUNCH(true, 2, true);
+    return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, true) : NPP_TC_LAUNCH(false, 2, true);
   }
   if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, false) : NPP_TC_LAUNCH(true, 2, false);
   return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, false) : NPP_TC_LAUNCH(false, 2, false);

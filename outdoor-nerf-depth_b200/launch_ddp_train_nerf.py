@@ -13,6 +13,10 @@ How the drop-in works:
     (ddp_train_nerf.py:51-130) and children are started with the ``spawn`` method (fresh import per child,
     :742-745), so they are patched inside each child before ``ddp_train_nerf.ddp_train_nerf(rank, args)`` runs.
     ``ddp_test_nerf.py:16`` imports ``render_single_image`` from the trainer module, so the same patch covers it.
+  * the trainer imports four non-numeric packages at module scope (configargparse, tensorboardX, imageio, matplotlib);
+    where they are not installed the minimal stand-ins in ``compat/`` (appended to the END of sys.path) let it start.
+
+tests/test_trainer_gpu.py runs the unmodified trainer this way (world size 1 and 2) on a synthetic on-disk scene.
 """
 import os
 import sys
@@ -20,11 +24,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+COMPAT = os.path.join(HERE, "compat")
+
+
 def _paths(reference_dir):
     for p in (reference_dir, HERE):          # HERE ends up first
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
+    # stand-ins for configargparse / tensorboardX / imageio / matplotlib go LAST: an installed package always wins
+    if COMPAT not in sys.path:
+        sys.path.append(COMPAT)
 
 
 def patch_trainer_module(mod):
