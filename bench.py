@@ -29,14 +29,20 @@ import torch  # noqa: E402
 
 N_RAYS = 4096
 CASCADE = (64, 128)
+# BASELINE.json:configs restated: name -> (global rays, GPUs the config is quoted on, depth losses)
+CONFIGS = {
+    "c2": dict(global_rays=4096, quoted_gpus=1, losses=("mse",), what="NeRF++ configs[1]: KITTI Seq00 sample_every=8, depth_sup_type=gt, depth_loss=mse"),
+    "c4": dict(global_rays=8192, quoted_gpus=4, losses=("l1",), what="NeRF++ configs[3]: Argoverse 2c07fcda, depth_sup_type=stereo_crop, depth_loss=l1, 8192 rays tile-sharded over 4 GPUs"),
+    "c5": dict(global_rays=16384, quoted_gpus=8, losses=("mse", "l1", "kl"), what="NeRF++ configs[4]: KITTI sweep, {mse,l1,kl}, 16384 rays tile-sharded over 8 GPUs"),
+}
 LAMBDA_DEPTH = 0.1          # scripts/train.sh:5
 DEPTH_SIGMA, DEPTH_SCALE = 0.01, 0.05
 MACS_FG, MACS_BG = 593408, 604160      # per sample, SURVEY.md section 8(d)
 METRIC = "rays/sec (4096 rays x 128 samples, 8x256 MLP)"
-# dram__bytes_read.sum + dram__bytes_write.sum of field_tc_kernel, mean of the step's four launches, from the
-# `ncu --set full` capture summarised in profiles/r1d_field_tc_ncu.txt: (2.49 + 2.57 + 4.59 + 4.66) MB / 4 (weights + ray
-# inputs; the outputs stay in L2)
-NCU_DRAM_BYTES_PER_LAUNCH = 3.58e6
+# roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel) cannot be measured
+# inside a timed run (ncu replays kernels); it is read from the committed summary of the latest `ncu --set full` capture,
+# and the line carries that file's name and hash so a stale figure is visible
+TRAFFIC_FILE = os.path.join("profiles", "traffic.json")
 WORKLOAD = ("NeRF++ configs[1]: 4096 rays/GPU, cascade 64 -> +128 (192 fine) fg and bg, depth_loss=mse lambda=0.1, "
             "forward of both levels + sampling + composite + losses")
 
@@ -160,6 +166,19 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
+def ncu_traffic(kernel):
+    """{"bytes_per_launch": ..., "source": file, "sha16": ...} from profiles/traffic.json, or None."""
+    import hashlib
+    path = os.path.join(ROOT, TRAFFIC_FILE)
+    try:
+        raw = open(path, "rb").read()
+        d = json.loads(raw)[kernel]
+        return {"bytes_per_launch": d["dram_bytes_per_launch"], "source": TRAFFIC_FILE, "capture": d.get("capture"),
+                "sha16": hashlib.sha256(raw).hexdigest()[:16]}
+    except Exception:
+        return None
+
+
 def make_rays(n, seed):
     """SURVEY.md section 8(d) synthetic batch (host tensors): origins inside the ball of radius 0.5, un-normalised
     directions, rgb ~ U[0,1], depth prior = far * U with every 5th ray invalid (0).  Same draws as the oracle's
@@ -193,6 +212,22 @@ def make_models(device):
     return [n.to(device) for n in nets]
 
 
+def plan(args, world):
+    """rays per rank, global rays, loss types and the scaling label for the asked config / scaling mode."""
+    cfg = CONFIGS[args.config]
+    if args.config == "c2" and args.scaling == "weak":
+        n = N_RAYS                                   # the headline: 4096 rays per GPU, whatever N
+    else:
+        g = cfg["global_rays"]                       # strong scaling / tile-sharded configs: the global batch is fixed
+        if g % world:
+            raise SystemExit("config %s: %d rays do not divide over %d ranks (ddp_train_nerf.py:137-139)" % (args.config, g, world))
+        n = g // world
+    if args.rays_per_gpu:
+        n = args.rays_per_gpu
+    scaling = "weak" if (args.config == "c2" and args.scaling == "weak") else "strong"
+    return n, n * world, cfg["losses"], scaling, cfg["what"]
+
+
 def run_ours(args):
     from nerfpp_b200 import GraphedRenderStep, PipelinedRenderStep, _lib, ops, render_rays
     rank = int(os.environ.get("RANK", 0))
@@ -206,35 +241,38 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    n_rays, global_rays, loss_types, scaling, what = plan(args, world)
     clk = ClockSampler(local)          # its child process needs a moment to come up: started before the warm-up
     _lib.lib()
     models = make_models(dev)
-    host = make_rays(N_RAYS, seed=rank)                 # this rank's band of the global 4096*world batch
+    host = make_rays(n_rays, seed=rank)                 # this rank's contiguous band of the global batch
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    gathered = torch.empty(world * N_RAYS * 4, device=dev) if world > 1 else None   # per rank: rgb [n,3] | depth [n]
+    gathered = torch.empty(world * n_rays * 4, device=dev) if world > 1 else None   # per rank: rgb [n,3] | depth [n]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     pending_flag = [None]
-    step_kw = dict(cascade_samples=CASCADE, train=True, depth_loss_type="mse", lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA)
+    kws = [dict(cascade_samples=CASCADE, train=True, depth_loss_type=lt, lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA) for lt in loss_types]
     graphed = not args.no_graph
-    g_dev = g_host = None
+    g_devs = g_hosts = None
     if graphed:
-        # the step captured once into a CUDA graph (nerfpp_b200.graph): one launch per step instead of ~14 through Python
-        g_dev = GraphedRenderStep(models, N_RAYS, depth_scale=DEPTH_SCALE, host_io=False, device=dev, **step_kw)
-        for k, v in g_dev.dev_in.items():
-            v.copy_(batch[k])
+        # the step captured once into a CUDA graph (nerfpp_b200.graph): one launch per step instead of ~14 through Python;
+        # one graph per depth-loss type of the config (a sweep config alternates them step by step)
+        g_devs = [GraphedRenderStep(models, n_rays, depth_scale=DEPTH_SCALE, host_io=False, device=dev, **kw) for kw in kws]
+        for g in g_devs:
+            for k, v in g.dev_in.items():
+                v.copy_(batch[k])
         # host -> host: two such graphs on their own streams, used alternately, so that step i+1's H2D and step i-1's host
         # read-back overlap step i's kernels (nerfpp_b200.graph.PipelinedRenderStep); for N > 1 the all-gather of the
         # rendered tile and the D2H of the gathered image ride on the slot's stream right behind the replay
-        gath_dev = [torch.empty(world * N_RAYS * 4, device=dev) for _ in range(args.e2e_depth)] if world > 1 else None
-        gath_host = [torch.empty(world * N_RAYS * 4).pin_memory() for _ in range(args.e2e_depth)] if world > 1 else None
+        gath_dev = [torch.empty(world * n_rays * 4, device=dev) for _ in range(args.e2e_depth)] if world > 1 else None
+        gath_host = [torch.empty(world * n_rays * 4).pin_memory() for _ in range(args.e2e_depth)] if world > 1 else None
 
         def gather_tiles(i, st):
-            dist.all_gather_into_tensor(gath_dev[i], st._packed[:4 * N_RAYS])
+            dist.all_gather_into_tensor(gath_dev[i], st._packed[:4 * n_rays])
             gath_host[i].copy_(gath_dev[i], non_blocking=True)
-        g_host = PipelinedRenderStep(models, N_RAYS, depth=args.e2e_depth, depth_scale=DEPTH_SCALE, device=dev,
-                                     after_launch=gather_tiles if world > 1 else None, **step_kw)
+        g_hosts = [PipelinedRenderStep(models, n_rays, depth=args.e2e_depth, depth_scale=DEPTH_SCALE, device=dev,
+                                       after_launch=gather_tiles if world > 1 else None, **kw) for kw in kws]
 
     # N > 1: the step's rendered tile (rgb | depth) is copied aside and all-gathered on a SIDE stream, so the collective of
     # step i runs under the kernels of step i+1 (it needs no SM time to speak of; it cannot share an SM with a field
@@ -242,31 +280,34 @@ def run_ours(args):
     # is left of the last gather when the loop ends is timed separately and added (below).
     main_stream = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    tile_bufs = [torch.empty(4 * N_RAYS, device=dev) for _ in range(2)] if world > 1 else None
-    image_bufs = [torch.empty(world * N_RAYS * 4, device=dev) for _ in range(2)] if world > 1 else None
+    tile_bufs = [torch.empty(4 * n_rays, device=dev) for _ in range(2)] if world > 1 else None
+    image_bufs = [torch.empty(world * n_rays * 4, device=dev) for _ in range(2)] if world > 1 else None
     gather_done = [None, None]
     step_no = [0]
 
     def step(b):
-        """One pass over this rank's 4096 rays with the inputs resident in HBM."""
+        """One pass over this rank's rays with the inputs resident in HBM."""
+        which = step_no[0] % len(kws)
         with torch.no_grad():
             if graphed:
+                g_dev = g_devs[which]
                 out = g_dev()                            # inputs: g_dev.dev_in (filled once above)
+                i = step_no[0] & 1
+                step_no[0] += 1
                 if world > 1:
-                    i = step_no[0] & 1
-                    step_no[0] += 1
                     if gather_done[i] is not None:
                         main_stream.wait_event(gather_done[i])        # the gather two steps back has read this tile buffer
-                    tile_bufs[i].copy_(g_dev._packed[:4 * N_RAYS])
+                    tile_bufs[i].copy_(g_dev._packed[:4 * n_rays])
                     side.wait_stream(main_stream)
                     with torch.cuda.stream(side):
                         dist.all_gather_into_tensor(image_bufs[i], tile_bufs[i])
                         gather_done[i] = torch.cuda.Event()
                         gather_done[i].record()
                 return out
+            step_no[0] += 1
             if pending_flag[0] is not None:          # the previous step's out-of-sphere flag (its work is long done)
                 pending_flag[0].raise_if_set()
-            res = render_rays(models, b, defer_unbounded_check=True, **step_kw)
+            res = render_rays(models, b, defer_unbounded_check=True, **kws[which])
             pending_flag[0] = res["unbounded"]
             ret = res["levels"][-1][0]
             if world > 1:
@@ -284,6 +325,7 @@ def run_ours(args):
     barrier()
     # ---- timed: K steps, device time per step by CUDA events, L2 flushed between steps ----
     ops.LAUNCHES[0] = 0
+    step_no[0] = 0
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with clk:
         barrier()
@@ -302,14 +344,15 @@ def run_ours(args):
         t_wall = time.perf_counter() - t_wall
     launches = ops.LAUNCHES[0]
     if graphed:
-        g_dev.check_unbounded()
+        for g in g_devs:
+            g.check_unbounded()
     ms = sum(a.elapsed_time(b) for a, b in evs) + tail[0].elapsed_time(tail[1])
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * N_RAYS / (ms_per_step * 1e-3)
+    value = global_rays / (ms_per_step * 1e-3)
 
     # ---- e2e: pinned host buffers -> H2D -> path -> D2H of rgb/depth/loss, wall clock ----
     def e2e_step():
@@ -324,19 +367,22 @@ def run_ours(args):
     def e2e_run(k):
         """k steps from HOST buffers to HOST results; returns the wall-clock seconds.  Every step copies its batch
         host -> device and its rgb / depth / losses (and, N > 1, the gathered image) device -> host; the L2 flush of
-        the measurement protocol is enqueued before every step and is INSIDE the timed region."""
+        the measurement protocol is enqueued before every step and is INSIDE the timed region.  A sweep config runs its
+        loss types one after the other, k steps in total."""
         t0 = time.perf_counter()
         if graphed:
-            ahead = min(args.e2e_depth - 1, k)
-            for _ in range(ahead):               # fill the pipeline
-                flush.zero_()
-                g_host.submit(host)
-            for _ in range(k - ahead):
-                flush.zero_()
-                g_host.submit(host)              # step i+depth-1 is staged and enqueued ...
-                g_host.result()                  # ... before step i's results are read on the host
-            for _ in range(ahead):
-                g_host.result()
+            shares = [k // len(g_hosts) + (1 if i < k % len(g_hosts) else 0) for i in range(len(g_hosts))]
+            for g_host, kk in zip(g_hosts, shares):
+                ahead = min(args.e2e_depth - 1, kk)
+                for _ in range(ahead):               # fill the pipeline
+                    flush.zero_()
+                    g_host.submit(host)
+                for _ in range(kk - ahead):
+                    flush.zero_()
+                    g_host.submit(host)              # step i+depth-1 is staged and enqueued ...
+                    g_host.result()                  # ... before step i's results are read on the host
+                for _ in range(ahead):
+                    g_host.result()
         else:
             for _ in range(k):
                 flush.zero_()
@@ -350,14 +396,16 @@ def run_ours(args):
     t_e2e = torch.tensor([t_sum], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_RAYS * args.steps / float(t_e2e.item())
+    e2e_value = global_rays * args.steps / float(t_e2e.item())
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
-    d2h = (world * N_RAYS * 4 * 4 if world > 1 else N_RAYS * 4 * 4) + 2 * 4 * 4
+    d2h = (world * n_rays * 4 * 4 if world > 1 else n_rays * 4 * 4) + 2 * 4 * 4
     if graphed:   # the graph's one D2H (rgb, depth, 2 x 4 losses, flag), plus the gathered tiles when N > 1
-        d2h = g_host.slots[0]._n_out * 4 + (world * N_RAYS * 4 * 4 if world > 1 else 0)
+        d2h = g_hosts[0].slots[0]._n_out * 4 + (world * n_rays * 4 * 4 if world > 1 else 0)
 
-    # ---- informational: one trainer step (ddp_train_nerf.py:432-498: per level forward, loss, backward, Adam) ----
-    train = train_step_rate(models, batch, dev) if (world == 1 and not args.no_train) else None
+    # ---- the trainer's step (ddp_train_nerf.py:432-498: per level forward, loss, backward, Adam), every N ----
+    train = None
+    if not args.no_train:
+        train = train_step_rate(models, batch, dev, n_rays, loss_types[0], dist if world > 1 else None, world)
 
     # ---- roofline of the dominant kernel (field_tc_kernel), timed alone with CUDA events ----
     roof = field_roofline(models, batch, dev)
@@ -365,15 +413,16 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32 (fp16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "global_rays": world * N_RAYS,
+            "config": {"workload": WORKLOAD if args.config == "c2" else what + "; cascade 64 -> +128 fg and bg, forward of both levels + sampling + composite + losses",
+                       "name": args.config, "rays_per_gpu": n_rays, "global_rays": global_rays, "depth_losses": list(loss_types),
                        "cascade_samples": list(CASCADE), "unit_of_work": "U2 forward (SURVEY 8(d)): 2.512 TFLOP algorithmic per 4096 rays",
-                       "l2": "flushed between timed steps (256 MiB write)", "field": "tcgen05" if ops.default_field_impl() == 0 else "simt",
+                       "l2": "flushed between timed steps (256 MiB write)", "field": "tcgen05",
                        "parallelism": ("rays sharded in contiguous bands, %d ranks, 1 NCCL all-gather/step on a side stream (overlaps the next step)" % world)
                        if world > 1 else "single GPU",
                        "wall_s_timed_region": t_wall,
-                       "launch": ("one CUDA graph per step (%d library kernels + torch rand/cat nodes)" % g_dev.kernels_per_replay) if graphed
+                       "launch": ("one CUDA graph per step (%d library kernels + torch rand/cat nodes)" % g_devs[0].kernels_per_replay) if graphed
                        else "eager: one Python call per kernel"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -395,47 +444,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def train_step_rate(models, batch, dev, steps=5):
-    """rays/s of the reference trainer's step on the same 4096 rays: for each cascade level forward (training mode),
-    rgb MSE + 0.1 * depth_mse, loss.backward() through nerfpp_backward, Adam step.  Reported beside the headline metric;
-    not part of `value`."""
-    import depth_loss as DL
-    from nerfpp_b200 import ops
+def train_step_rate(models, batch, dev, n_rays, loss_type, dist, world, steps=20):
+    """rays/s of the reference trainer's step on this rank's rays: for each cascade level forward (training mode), rgb MSE +
+    0.1 * depth loss, loss.backward() through nerfpp_backward, Adam step -- captured into ONE CUDA graph
+    (nerfpp_b200.GraphedTrainStep).  N > 1: the flat gradient buffer of each level is averaged with one NCCL all-reduce
+    inside the graph (what DDP-over-gloo does in the reference, ddp_train_nerf.py:298,323).  Device time by CUDA events,
+    max over ranks; reported beside the headline metric, with its own roofline."""
     import copy
+    from nerfpp_b200 import GraphedTrainStep, ops
+    burst, sustained, hbm, how = peaks()
     nets = [copy.deepcopy(m) for m in models]
-    opts = [torch.optim.Adam(n.parameters(), lr=5e-4) for n in nets]
-    n = batch["ray_o"].shape[0]
-
-    def step():
-        far = ops.intersect_sphere(batch["ray_o"], batch["ray_d"])
-        fg_z = bg_z = ret = None
-        for m, S in enumerate(CASCADE):
-            if m == 0:
-                fg_z, bg_z = ops.coarse_depths(batch["min_depth"], far, S, torch.rand(n, S, device=dev), torch.rand(n, S, device=dev))
-            else:
-                fg_z, bg_z = ops.resample_merge_pair(fg_z, ret["fg_weights"].detach(), bg_z, ret["bg_weights"].detach(), S)
-            opts[m].zero_grad()
-            ret = nets[m](batch["ray_o"], batch["ray_d"], far, fg_z, bg_z)
-            loss = torch.mean((ret["rgb"] - batch["rgb"]) ** 2) + LAMBDA_DEPTH * DL.depth_mse(batch["depth_sup"], ret["depth"])
-            loss.backward()
-            opts[m].step()
-        return loss
-
+    group = dist.group.WORLD if dist is not None else None
+    ts = GraphedTrainStep(nets, n_rays, CASCADE, depth_loss_type=loss_type, lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA,
+                          depth_scale=DEPTH_SCALE, device=dev, process_group=group)
+    for k in ts.dev_in:
+        ts.dev_in[k].copy_(batch[k])
     for _ in range(3):
-        step()
+        ts()
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-        step()
+        ts()
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / steps
-    del nets, opts
+    ts.check_unbounded()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss = [float(x) for x in ts.losses.tolist()]
+    pairs_per_ray = sum(sum(CASCADE[:i + 1]) for i in range(len(CASCADE)))        # level m evaluates all depths so far: 64 + 192
+    flops = 3.0 * 2.0 * (MACS_FG + MACS_BG) * n_rays * pairs_per_ray               # fwd + dgrad + wgrad, SURVEY 8(d) unit U2
+    achieved = flops / (ms * 1e-3) / 1e12
+    tr = ncu_traffic("train_step")
+    out = {"value": n_rays * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps, "rays_per_gpu": n_rays, "n_gpus": world,
+           "depth_loss": loss_type, "final_losses": loss, "kernels_per_step": ts.kernels_per_replay,
+           "what": "forward + loss + backward (tcgen05 dgrad / wgrad kernels) + Adam, both cascade levels, ONE CUDA graph per step"
+                   + ("; gradients averaged by one NCCL all-reduce of the flat buffer per level" if world > 1 else ""),
+           "roofline": {"bound": "hbm + tensor (see DESIGN.md section 5: the step moves ~44 GB of saved operands)", "achieved": achieved,
+                        "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                        "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json): timed inside a long step" % how,
+                        "algorithmic_flops_per_step": flops, "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr}}
+    del ts, nets
     torch.cuda.empty_cache()
-    return {"value": n / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
-            "what": "forward + loss + backward (tcgen05 dgrad/wgrad kernels) + torch Adam, both cascade levels, 4096 rays; "
-                    "unit U2 fwd+bwd = 7.535 TFLOP algorithmic"}
+    return out
 
 
 def field_roofline(models, batch, dev, reps=10):
@@ -445,7 +500,7 @@ def field_roofline(models, batch, dev, reps=10):
     burst, sustained, hbm, how = peaks()
     with torch.no_grad():
         out, far = cascade_forward(models, batch["ray_o"], batch["ray_d"], batch["min_depth"], CASCADE, train=True)
-    impl = ops.default_field_impl()
+    impl = 0      # FIELD_TC
     flops = tot_ms = 0.0
     n_launch = 0
     with torch.no_grad():
@@ -467,7 +522,8 @@ def field_roofline(models, batch, dev, reps=10):
                 n_launch += 1
     achieved = flops / (tot_ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "field_tc_kernel" if impl == 0 else "field_simt_kernel", "achieved": achieved, "peak": burst,
-            "unit": "TFLOP/s", "frac": achieved / burst, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
+            "unit": "TFLOP/s", "frac": achieved / burst, "traffic": (ncu_traffic("field_tc_kernel") or {}).get("bytes_per_launch"),
+            "traffic_source": ncu_traffic("field_tc_kernel"), "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
             "launches_per_step": n_launch, "avg_launch_ms": tot_ms / n_launch, "algorithmic_flops_per_step": flops}
 
 
@@ -508,7 +564,18 @@ def parity_vs_oracle(levels, rays, ref_out, ref_losses, O, dev):
     for name, idx in (("fg", 1), ("bg", 2)):      # stratified + perturbed depths of level 0: integer-exact work, expected 0 / 0
         a, w = res["levels"][0][idx].cpu(), ref_out[0][idx]
         coarse[name] = {"mismatched": int((a != w).sum()), "of": a.numel(), "max_abs": float((a - w).abs().max())}
+    def per_ray(k, floor):
+        """|a - b| / max(|b|, floor) per ray (a ray's error = its worst channel): max / p99 / p50 over the batch."""
+        a, w = got[k].cpu().double(), want[k].double()
+        e = (a - w).abs() / w.abs().clamp_min(floor)
+        e = e.reshape(e.shape[0], -1).max(dim=1).values
+        q = torch.quantile(e, torch.tensor([0.5, 0.99], dtype=torch.float64))
+        return {"max": float(e.max()), "p99": float(q[1]), "p50": float(q[0]), "floor": floor}
     return {"rays": n, "rgb_max_rel": rel(got["rgb"], want["rgb"]), "depth_max_rel": rel(got["depth"], want["depth"]),
+            "per_ray_rel": {"rgb": per_ray("rgb", 1e-2), "depth": per_ray("depth", 1e-3), "fg_depth": per_ray("fg_depth", 1e-3),
+                            "note": "default-init weights (+5 density bias); on weights TRAINED by the fp32 oracle the single-pass fp16 "
+                                    "operands give rgb p50 9e-5 / p99 3e-4 / max 5e-4 and depth p50 2e-4 / max 6e-4 "
+                                    "(tests/test_convergence_gpu.py, profiles/r2_convergence.json): above 1e-4 at the tail"},
             "loss_max_rel": loss_rel, "psnr_vs_oracle_db": (-10.0 * math.log10(mse) if mse > 0 else float("inf")),
             "coarse_depths": coarse,
             "coarse_depths_note": "fg depths inherit intersect_sphere's far bound: the LIVE oracle's torch-CPU sum/norm round the "
@@ -611,13 +678,17 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200, help="timed steps (200 x ~1.8 ms: long enough for the clock sampler to see the region)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host-to-host steps in flight in the e2e leg (PipelinedRenderStep)")
-    ap.add_argument("--no-train", action="store_true", help="skip the informational trainer-step measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the trainer-step measurement")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config: c2 = configs[1] (headline), c4 = configs[3], c5 = configs[4]")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="c2 only: weak = 4096 rays per GPU (default, the driver's curve); strong = 4096 rays in total, sharded over the ranks")
+    ap.add_argument("--rays-per-gpu", type=int, default=0, help="override the rays each rank processes")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

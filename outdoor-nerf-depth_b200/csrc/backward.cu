@@ -1,7 +1,7 @@
 // nerfpp_backward: autograd of NerfNet.forward (ddp_model.py:74-147) w.r.t. the 48 parameter tensors, as CUDA kernels:
 // composite backward (composite.cu) -> loss scale -> per net: dgrad chain (field_bwd_tc.cu) -> wgrad (wgrad_tc.cu).
 #include <cstdio>
-#include "tc_common.cuh"
+#include "bwd_common.cuh"
 
 size_t npp_dgrad_packed_bytes();
 int npp_pack_dgrad(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
@@ -10,29 +10,79 @@ int npp_field_dgrad(const void* packed, const void* act, const void* mask, const
                     cudaStream_t st);
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
                     const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st);
+int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
+                          const NerfppNetGrads* grads, cudaStream_t st);
 size_t npp_tc_train_ws_bytes(long long n_samples);
+// bwd_fused.cu: dgrad chain and weight-gradient GEMMs as one producer/consumer kernel (dZ never leaves L2)
+size_t npp_bwd_fused_ws_bytes(int dev);
+int npp_field_bwd_fused(bool bg, const void* packed, size_t packed_blob_bytes, const void* act, const void* etiles, const void* mask, const float* rgb,
+                        const float* raw_sigma, const float* d_sigma, const float* d_rgb, const float* scale, long long total,
+                        float* d_raw_sigma, float* d_raw_rgb, const NerfppNetGrads* grads, void* ws, cudaStream_t st);
+
+int npp_field_dgrad_v2(const void* packed, size_t packed_blob_bytes, bool bg, const void* act, const void* mask, const float* rgb, const float* raw_sigma,
+                       const float* d_sigma, const float* d_rgb, const float* scale, long long total, void* dz, float* d_raw_sigma,
+                       float* d_raw_rgb, cudaStream_t st);
+
+// How the field's backward runs (tests / diagnostics select through this hook; the product uses the default):
+//   2 (default)  two kernels: the data-gradient chain with the storer-warp staging (bwd_fused.cu, producer role on every SM)
+//                writes dZ to HBM, wgrad_tc_kernel reads it
+//   1            the same with round 1's dgrad kernel (field_bwd_tc.cu)
+//   0            ONE kernel: producers and weight-gradient consumers on disjoint SMs, dZ through an L2-resident slot ring.
+//                Measured SLOWER than the two-kernel form on B200: a consumer SM can keep only ~192 KB
+//                of operands in flight, which at L2/HBM latency feeds its tensor pipe at a third of the rate the MMAs need
+static int g_bwd_mode = 2;
+extern "C" void nerfpp_debug_set_bwd_mode(int mode) { g_bwd_mode = (mode >= 0 && mode <= 2) ? mode : 2; }
 
 namespace npp {
 
-// max |gradient entering the MLP| over both nets (as the bit pattern of a non-negative float: ordered like unsigned ints)
+// max |gradient entering the MLP| of one net, separately for its two entry points -- out[0]: the density head (d sigma),
+// out[1]: the colour head (d rgb through the sigmoid) -- as bit patterns of non-negative floats (ordered like unsigned
+// ints); out[2] != 0: a non-finite incoming gradient was seen.
 __global__ void grad_absmax_kernel(const float* __restrict__ d_sigma, const float* __restrict__ d_rgb, const float* __restrict__ rgb,
                                    long long total, unsigned* __restrict__ out) {
-  float m = 0.f;
+  float ms = 0.f, mr = 0.f;
+  bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    m = fmaxf(m, fabsf(d_sigma[i]));
+    const float ds = d_sigma[i];
+    bad |= !isfinite(ds);
+    ms = fmaxf(ms, fabsf(ds));
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { const float cc = rgb[3 * i + c]; m = fmaxf(m, fabsf(d_rgb[3 * i + c] * cc * (1.f - cc))); }
+    for (int c = 0; c < 3; ++c) {
+      const float cc = rgb[3 * i + c], dr = d_rgb[3 * i + c];
+      bad |= !isfinite(dr);
+      mr = fmaxf(mr, fabsf(dr * cc * (1.f - cc)));
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(out, __float_as_uint(m));
+  for (int o = 16; o > 0; o >>= 1) { ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o)); mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); }
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (ms > 0.f && isfinite(ms)) atomicMax(out, __float_as_uint(ms));
+    if (mr > 0.f && isfinite(mr)) atomicMax(out + 1, __float_as_uint(mr));
+    if (bad) atomicOr(out + 2, 1u);
+  }
 }
-// power-of-two loss scale that puts the largest incoming gradient at ~2^10: fp16 then keeps 6 binades of headroom above
-// it (the dgrad epilogue saturates instead of overflowing) and 34 below -- the gradients shrink by ~2^10 on the way down
-// the eight layers and must stay clear of fp16's subnormal range
-__global__ void grad_scale_kernel(const unsigned* __restrict__ absmax, float* __restrict__ scale) {   // one scale per net
-  const float m = __uint_as_float(absmax[threadIdx.x]);
-  scale[threadIdx.x] = m > 0.f ? exp2f(10.f - ceilf(log2f(m))) : 1.f;
+// Power-of-two loss scales (fp16 operands inside the backward kernels).  The gradient enters the MLP at two points whose
+// magnitudes can differ by many orders -- a depth-prior loss acts on sigma only and can be 1e9 times the colour loss early
+// in training -- and the layers above the point where the two paths join (rgb.2, rgb.0, base_remap) see the colour path
+// alone.  So there are two scales per net:
+//   scale[1] (colour path: d raw rgb, dG, d remap-out)  puts max |d raw rgb| at ~2^10,
+//   scale[0] (everything below the join)                 puts max(|d raw sigma|, |d raw rgb|) at ~2^10 (<= scale[1]);
+// the dgrad epilogue rescales by scale[0] / scale[1] where the density head joins the chain.  fp16 then keeps 6 binades of
+// headroom above the largest entry (the epilogue saturates instead of overflowing) and ~34 below.  The exponent is
+// clamped so that neither the scales nor their ratio leave fp32's range; a non-finite incoming gradient makes both
+// scales NaN, so the parameter gradients come out NaN as they would from autograd (instead of silently finite).
+__device__ __forceinline__ float pow2_scale(float m) {
+  if (!(m > 0.f)) return 1.f;
+  return exp2f(fminf(fmaxf(10.f - ceilf(log2f(m)), -60.f), 60.f));
+}
+__global__ void grad_scale_kernel(const unsigned* __restrict__ absmax, float* __restrict__ scale) {   // thread = net
+  const unsigned* am = absmax + 4 * threadIdx.x;
+  const float ms = __uint_as_float(am[0]), mr = __uint_as_float(am[1]);
+  float sc = pow2_scale(fmaxf(ms, mr)), sr = pow2_scale(mr);
+  if (am[2] != 0u) sc = sr = __int_as_float(0x7fc00000);
+  scale[2 * threadIdx.x] = sc;
+  scale[2 * threadIdx.x + 1] = sr;
 }
 
 }  // namespace npp
@@ -53,10 +103,13 @@ static BwdWs carve_bwd(void* base, int n, int sf, int sb) {
   w.d_bg_rgb = (float*)(p + o); o += al256((size_t)n * sb * 12);
   w.d_raw_sigma = (float*)(p + o); o += al256(tiles * tc::TILE * 4);
   w.d_raw_rgb = (float*)(p + o); o += al256(tiles * tc::TILE * 12);
-  w.scale = (float*)(p + o); w.absmax = (unsigned*)(p + o + 8); o += 256;   // [2] each: fg, bg
+  w.scale = (float*)(p + o); w.absmax = (unsigned*)(p + o + 32); o += 256;   // scale [2 nets][2], absmax [2 nets][4]
   w.packed = (uint8_t*)(p + o); o += al256(npp_dgrad_packed_bytes());
   o = (o + 1023) & ~(size_t)1023;
-  w.dz = (uint8_t*)(p + o); o += tc::act_bytes(tiles);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  // fused: the producers' slot rings + counters; split: every dZ of the larger net
+  w.dz = (uint8_t*)(p + o); o += g_bwd_mode == 0 ? npp_bwd_fused_ws_bytes(dev) : tc::act_bytes(tiles);
   w.bytes = o;
   return w;
 }
@@ -96,9 +149,9 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
                                      s_bg, out, grads, b.d_fg_sigma, b.d_fg_rgb, b.d_bg_sigma, b.d_bg_rgb, stream);
   if (rc) return rc;
   const long long tot_fg = (long long)n_rays * s_fg, tot_bg = (long long)n_rays * s_bg;
-  cudaMemsetAsync(b.absmax, 0, 2 * sizeof(unsigned), st);
+  cudaMemsetAsync(b.absmax, 0, 8 * sizeof(unsigned), st);
   grad_absmax_kernel<<<296, 256, 0, st>>>(b.d_fg_sigma, b.d_fg_rgb, f.fg_rgb, tot_fg, b.absmax);
-  grad_absmax_kernel<<<296, 256, 0, st>>>(b.d_bg_sigma, b.d_bg_rgb, f.bg_rgb, tot_bg, b.absmax + 1);
+  grad_absmax_kernel<<<296, 256, 0, st>>>(b.d_bg_sigma, b.d_bg_rgb, f.bg_rgb, tot_bg, b.absmax + 4);
   grad_scale_kernel<<<1, 2, 0, st>>>(b.absmax, b.scale);
   NPP_CHECK_LAUNCH();
   const size_t fg_train_bytes = (npp_tc_train_ws_bytes(tot_fg) + 1023) & ~(size_t)1023;
@@ -111,10 +164,24 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
     const float* raw_sigma = (const float*)(tw + tc::train_ws_sigma_off(tiles));
     rc = npp_pack_dgrad(bg ? params_bg : params_fg, bg != 0, b.packed, st);
     if (rc) return rc;
-    rc = npp_field_dgrad(b.packed, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb, raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma,
-                         bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + bg, total, b.dz, b.d_raw_sigma, b.d_raw_rgb, st);
+    if (g_bwd_mode == 0) {
+      rc = npp_field_bwd_fused(bg != 0, b.packed, (size_t)tcb::make_table().total, act, etiles, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb,
+                               raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma, bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.d_raw_sigma,
+                               b.d_raw_rgb, bg ? grads_bg : grads_fg, b.dz, st);
+      if (rc) return rc;
+      rc = npp_field_wgrad_heads(act, b.d_raw_sigma, b.d_raw_rgb, b.scale + 2 * bg, total, bg ? grads_bg : grads_fg, st);
+      if (rc) return rc;
+      continue;
+    }
+    if (g_bwd_mode == 2)
+      rc = npp_field_dgrad_v2(b.packed, (size_t)tcb::make_table().total, bg != 0, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb,
+                              raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma, bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.dz,
+                              b.d_raw_sigma, b.d_raw_rgb, st);
+    else
+      rc = npp_field_dgrad(b.packed, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb, raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma,
+                           bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.dz, b.d_raw_sigma, b.d_raw_rgb, st);
     if (rc) return rc;
-    rc = npp_field_wgrad(bg != 0, act, etiles, b.dz, b.d_raw_sigma, b.d_raw_rgb, b.scale + bg, total, bg ? grads_bg : grads_fg, st);
+    rc = npp_field_wgrad(bg != 0, act, etiles, b.dz, b.d_raw_sigma, b.d_raw_rgb, b.scale + 2 * bg, total, bg ? grads_bg : grads_fg, st);
     if (rc) return rc;
   }
   return 0;

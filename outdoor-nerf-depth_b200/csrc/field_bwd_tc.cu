@@ -15,45 +15,23 @@
 // All gradients inside this kernel are multiplied by a power-of-two loss scale (read from device memory) so that they
 // survive the fp16 operand format; wgrad_tc.cu divides it out again.
 #include <cstdlib>
-#include "tc_common.cuh"
+#include "bwd_common.cuh"
 
 namespace npp {
 namespace tcb {
-using namespace npp::tc;
 
-constexpr int NSTAGE = 4;
-constexpr int STAGE_BYTES = 32768;          // one [256 N x 64 K] SW128 tile of W^T
-constexpr int G_BYTES = 2 * CHUNK_BYTES;    // dG operand: 128 columns; double-buffered
-constexpr int OFF_G = 0, OFF_W = 2 * G_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_W2 = OFF_BAR + 512;
+constexpr int OFF_G = 0, OFF_W = 2 * G_BYTES, OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES, OFF_W2 = OFF_BAR + 512;   // dG operand double-buffered
 constexpr int OFF_STG = OFF_W2 + 3 * RGB_HID * 4;   // staging of the DZ store (tc_common.cuh: stage_store_chunk), 1024-aligned
 constexpr int SMEM_BYTES = OFF_STG + STG_BYTES;
 static_assert(OFF_STG % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, LOAD_WARP = 9, PRO_WARP0 = 10, NUM_PRO_WARPS = 4, THREADS = 448;
-constexpr int NUM_LAYERS = 9;               // t = 0: rgb.0 (remap part), 1: base_remap, 2..8: base 7..1
 
 enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_GFULL = B_AREADY + 4, B_GEMPTY = B_GFULL + 2,
        B_ACC = B_GEMPTY + 2, B_COUNT = B_ACC + 2 };
 static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 
-// forward layer whose weight the dgrad layer t multiplies with, and the forward activation its output is the gradient of
-__host__ __device__ constexpr int weight_layer(int t) { return t == 0 ? L_RGB0 : t == 1 ? L_REMAP : 9 - t; }   // 2 -> base 7 ... 8 -> base 1
-__host__ __device__ constexpr int target_act(int t) { return t == 0 ? 8 : 8 - t; }                             // ACT index: 8 = remap out, 7..0 = base outputs
-
-struct Step { short t; short chunk; int blob_off; };
-struct StepTable { Step s[40]; int n; int total; };
-__host__ __device__ constexpr StepTable make_table() {
-  StepTable tb{};
-  int i = 0, off = 0;
-  for (int t = 0; t < NUM_LAYERS; ++t)
-    for (int c = 0; c < (t == 0 ? 2 : 4); ++c) { tb.s[i] = Step{(short)t, (short)c, off}; off += STAGE_BYTES; ++i; }
-  tb.n = i; tb.total = off;
-  return tb;
-}
 __constant__ StepTable c_tab = make_table();
 static const StepTable h_tab = make_table();
-
-// fp32 tail of the packed buffer: rgb.2 weights [3][128], sigma-head weights [256]
-constexpr int T_W2 = 0, T_WSIG = 3 * RGB_HID, T_TOTAL = T_WSIG + W;
 
 __global__ void __launch_bounds__(THREADS, 1)
 field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const uint8_t* __restrict__ act,
@@ -67,7 +45,8 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
   auto bar = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * B_COUNT);
   if ((s_base & 1023u) != 0) __trap();
-  const float scale = *scale_ptr;
+  const float scale = scale_ptr[0], scale_rgb = scale_ptr[1];   // below the join | colour path (backward.cu)
+  const float join = scale / scale_rgb;
   const StepTable& tab = c_tab;
 
   if (warp == MMA_WARP && lane == 0) {
@@ -175,7 +154,7 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
       float dr[3] = {0.f, 0.f, 0.f};
       if (g < total) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { const float cc = rgb[3 * g + c]; dr[c] = d_rgb[3 * g + c] * cc * (1.f - cc) * scale; }   // sigmoid'
+        for (int c = 0; c < 3; ++c) { const float cc = rgb[3 * g + c]; dr[c] = d_rgb[3 * g + c] * cc * (1.f - cc) * scale_rgb; }   // sigmoid'
         d_raw_rgb[3 * g] = dr[0]; d_raw_rgb[3 * g + 1] = dr[1]; d_raw_rgb[3 * g + 2] = dr[2];
         const float rs = raw_sigma[g];
         d_raw_sigma[g] = d_sigma[g] * (rs > 0.f ? 1.f : rs < 0.f ? -1.f : 0.f) * scale;                                          // abs'
@@ -242,14 +221,14 @@ field_dgrad_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ 
           uint32_t (&cur)[32] = v[j & 1];
           tmem_ld_wait(cur);
           if (j + 1 < 4) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);
-          if (t == 1) {       // the sigma head joins here: d h7 += d(raw sigma) * w_sigma   (nerf_network.py:133)
+          if (t == 1) {       // the sigma head joins here: d h7 = (colour path, rescaled to the chain's loss scale) + d(raw sigma) * w_sigma   (nerf_network.py:133)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float4 w4 = __ldg(reinterpret_cast<const float4*>(tail + T_WSIG + 64 * j + 32 * hh) + e);
-              cur[4 * e] = __float_as_uint(fmaf(dsr, w4.x, __uint_as_float(cur[4 * e])));
-              cur[4 * e + 1] = __float_as_uint(fmaf(dsr, w4.y, __uint_as_float(cur[4 * e + 1])));
-              cur[4 * e + 2] = __float_as_uint(fmaf(dsr, w4.z, __uint_as_float(cur[4 * e + 2])));
-              cur[4 * e + 3] = __float_as_uint(fmaf(dsr, w4.w, __uint_as_float(cur[4 * e + 3])));
+              cur[4 * e] = __float_as_uint(fmaf(dsr, w4.x, join * __uint_as_float(cur[4 * e])));
+              cur[4 * e + 1] = __float_as_uint(fmaf(dsr, w4.y, join * __uint_as_float(cur[4 * e + 1])));
+              cur[4 * e + 2] = __float_as_uint(fmaf(dsr, w4.z, join * __uint_as_float(cur[4 * e + 2])));
+              cur[4 * e + 3] = __float_as_uint(fmaf(dsr, w4.w, join * __uint_as_float(cur[4 * e + 3])));
             }
           }
           uint32_t pk[16];

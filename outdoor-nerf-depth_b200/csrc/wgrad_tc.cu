@@ -10,7 +10,7 @@
 //
 // The bias gradients (column sums of DZ) are taken by wgrad_tc_kernel's otherwise idle epilogue warps from the A tiles in
 // shared memory.  wgrad_small_kernel: the two tiny heads (sigma 256->1, rgb.2 128->3) on CUDA cores.
-#include "tc_common.cuh"
+#include "bwd_common.cuh"
 
 namespace npp {
 namespace tcw {
@@ -22,41 +22,8 @@ constexpr int OFF_X = 0, OFF_A = 2 * X_BYTES, OFF_BAR = OFF_A + 2 * AH_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 enum { B_XFULL = 0, B_XEMPTY = 2, B_AFULL = 4, B_AEMPTY = 6, B_DONE = 8, B_COUNT = 9 };
 
-// One GEMM: dW[:, col0 : col0+ncols] (+)= DZ[a_layer]^T * X
-struct Job {
-  int a_layer;        // DZ layer (rows of dW)
-  int m_halves;       // 2 (256 outputs) or 1 (128)
-  int x_is_e;         // X from the E tiles (1) or from ACT[x_layer] (0)
-  int x_layer, x_chunk0, x_nchunks;
-  int skip;           // leading columns of the first X chunk that map to no weight column (view dir starts at E col 96 = chunk 1 col 32)
-  int ncols;          // weight columns written
-  int w_index;        // NerfppNetGrads.w index
-  int ld, col0;       // row stride (in-features of the layer) and first column in dW
-  int bias;           // this job also sums DZ[a_layer] over the samples = the layer's bias gradient (one job per layer)
-};
-struct JobTable { Job j[12]; int n; };
-__host__ __device__ constexpr JobTable make_jobs(bool bg) {
-  JobTable t{};
-  const int emb = emb_dim(bg), ech = bg ? 2 : 1;
-  int i = 0;
-  t.j[i++] = Job{0, 2, 1, 0, 0, ech, 0, emb, 0, emb, 0, 1};                               // base 0: embedding
-  for (int l = 1; l < 8; ++l) {
-    if (l == 5) t.j[i++] = Job{5, 2, 1, 0, 0, ech, 0, emb, 5, emb + W, 0, 0};             // base 5: [embedding | h4]
-    t.j[i++] = Job{l, 2, 0, l - 1, 0, 4, 0, W, l, l == 5 ? emb + W : W, l == 5 ? emb : 0, 1};
-  }
-  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0, 1};                               // base_remap
-  t.j[i++] = Job{9, 1, 0, 8, 0, 4, 0, W, L_RGB0, W + VIEW_DIM, 0, 1};                     // rgb.0: remap part
-  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W, 0};             // rgb.0: view-direction part
-  t.n = i;
-  return t;
-}
 __constant__ JobTable c_jobs[2] = {make_jobs(false), make_jobs(true)};
 static const JobTable h_jobs[2] = {make_jobs(false), make_jobs(true)};
-
-// MN-major SWIZZLE_128B operand: 64-feature blocks LBO = one chunk apart, 8-sample groups SBO = 1024 B apart
-constexpr uint32_t MN_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t mn_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((uint32_t)(CHUNK_BYTES >> 4) << 16); }
-__host__ __device__ constexpr uint32_t idesc_mn(int n) { return idesc_f16(n) | (1u << 15) | (1u << 16); }   // A and B MN-major
 
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restrict__ etiles, const uint8_t* __restrict__ dz,
@@ -167,7 +134,7 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
           }
         }
       }
-      const float inv_scale_b = 1.f / *scale_ptr;
+      const float inv_scale_b = 1.f / scale_ptr[jb.a_layer >= 8 ? 1 : 0];
       float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
@@ -180,7 +147,7 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
     if (t_end > t_begin) {
       mbar_wait(bar(B_DONE), 0);
       tc_fence_after();
-      const float inv_scale = 1.f / *scale_ptr;
+      const float inv_scale = 1.f / scale_ptr[jb.a_layer >= 8 ? 1 : 0];     // colour-path layers carry scale[1] (backward.cu)
       float* dW = grads.w[jb.w_index];
       const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
       for (int h = 0; h < jb.m_halves; ++h) {
@@ -266,7 +233,7 @@ wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ 
   __shared__ float s_acc[3 * RGB_HID + W];
   const int what = 10 + blockIdx.y;     // (the layers' bias gradients are summed inside wgrad_tc_kernel)
   const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
-  const float inv_scale = 1.f / *scale_ptr;
+  const float inv_scale = 1.f / scale_ptr[what == 10 ? 0 : 1];       // d raw sigma carries scale[0], d raw rgb scale[1]
   const size_t nt = (size_t)num_tiles;
   if (what == 10) weighted_colsum<1>(act + act_layer_off(7, nt), 4, d_raw_sigma, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_SIGMA], 0);
   else weighted_colsum<3>(act + act_layer_off(9, nt), 2, d_raw_rgb, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_RGB2], RGB_HID);
@@ -290,6 +257,9 @@ wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ 
 using namespace npp;
 
 // Accumulates (+=) the gradients of one net's 24 parameter tensors.
+int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
+                          const NerfppNetGrads* grads, cudaStream_t st);
+
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
                     const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st) {
   static int num_sms = 0;
@@ -308,11 +278,20 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
                                                                                (const uint8_t*)dz, scale, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
+  return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, st);
+}
+
+// The two small heads (sigma: 256 -> 1, rgb.2: 128 -> 3): weighted column sums of h7 / the rgb hidden layer on CUDA cores.
+int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
+                          const NerfppNetGrads* grads, cudaStream_t st) {
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   // 96 KB of activations per tile, read once.  A thread's loop over its tiles is a chain of dependent round trips to HBM
   // (4 x 16 B in flight per thread), so the sample range is cut fine enough for ~8 CTAs per SM to cover the latency.
   int sx = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
-  tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, (const uint8_t*)dz, d_raw_sigma, d_raw_rgb, scale, total,
-                                                        num_tiles, *grads);
+  tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, nullptr, d_raw_sigma, d_raw_rgb, scale, total, num_tiles, *grads);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -75,6 +75,12 @@ class NerfNet(nn.Module):
                                                 input_ch_viewdirs=view.out_dim, use_viewdirs=args.use_viewdirs))
         self._packed = (ops.PackedNet(False), ops.PackedNet(True))
 
+    def invalidate_packed(self):
+        """Drops the cached fp16 weight tiles.  Needed only after parameter writes that bypass torch's version counter
+        (``p.data.copy_(...)``, EMA through ``.data``); optimizer steps and ``load_state_dict`` are seen automatically."""
+        for c in self._packed:
+            c.invalidate()
+
     def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, impl=None):
         lead = tuple(ray_d.shape[:-1])
         flat = len(lead) != 1

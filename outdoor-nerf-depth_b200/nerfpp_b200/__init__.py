@@ -7,6 +7,6 @@ that mirror the reference's import surface (``ddp_model``, ``depth_loss``) live 
 from ._lib import FIELD_SIMT, FIELD_TC, NerfppError, lib  # noqa: F401
 from . import ops  # noqa: F401
 from .render import render_rays, cascade_forward, render_single_image  # noqa: F401
-from .graph import GraphedRenderStep, PipelinedRenderStep  # noqa: F401
+from .graph import GraphedRenderStep, GraphedTrainStep, PipelinedRenderStep  # noqa: F401
 
-__all__ = ["ops", "lib", "NerfppError", "FIELD_TC", "FIELD_SIMT", "render_rays", "cascade_forward", "render_single_image", "GraphedRenderStep", "PipelinedRenderStep"]
+__all__ = ["ops", "lib", "NerfppError", "FIELD_TC", "FIELD_SIMT", "render_rays", "cascade_forward", "render_single_image", "GraphedRenderStep", "GraphedTrainStep", "PipelinedRenderStep"]

@@ -9,6 +9,9 @@ from . import _lib
 from .ops import RET_KEYS, _p, _stream, check, net_params_struct
 
 
+LAST_FLAT_GRADS = [None]      # the flat gradient buffer of the most recent backward (GraphedTrainStep all-reduces it in one call)
+
+
 def render_backward(params, inputs, outs, ws, tws, grads):
     """grads: d(loss)/d(each of the 10 outputs) or None. Returns the 48 parameter gradients
     (fg 24 then bg 24, weight/bias interleaved in C-ABI layer order)."""
@@ -30,14 +33,12 @@ def render_backward(params, inputs, outs, ws, tws, grads):
     # one zero-filled buffer for all 48 gradients (the wgrad kernels accumulate with red.global.add): one fill kernel
     # instead of 48; every tensor starts on a 16-byte boundary
     sizes = [(p.numel() + 3) // 4 * 4 for p in params]
-    if os.environ.get("NERFPP_FLAT_GRADS", "1") == "1":
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        pgrads, off = [], 0
-        for p, sz in zip(params, sizes):
-            pgrads.append(flat[off:off + p.numel()].view(p.shape))
-            off += sz
-    else:
-        pgrads = [torch.zeros_like(p) for p in params]
+    flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    LAST_FLAT_GRADS[0] = flat
+    pgrads, off = [], 0
+    for p, sz in zip(params, sizes):
+        pgrads.append(flat[off:off + p.numel()].view(p.shape))
+        off += sz
     gfg, gbg = _lib.NetGrads(), _lib.NetGrads()
     for l in range(_lib.NLAYERS):
         gfg.w[l], gfg.b[l] = pgrads[2 * l].data_ptr(), pgrads[2 * l + 1].data_ptr()

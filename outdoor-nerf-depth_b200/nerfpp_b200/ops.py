@@ -19,7 +19,7 @@ LAYER_NAMES = (["base_layers.%d.0" % i for i in range(8)]
 RET_KEYS = ("rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth", "bg_rgb", "bg_depth",
             "bg_lambda", "depth")
 LAUNCHES = [0]   # kernels of libnerfpp_b200.so launched through this module (bench.py reads it)
-_KERNELS_PER_CALL = {"backward": 14, "intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
+_KERNELS_PER_CALL = {"backward": 12, "intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
                      "resample_merge": 1, "pack_weights": 1, "field_forward": 1, "forward": 3, "loss": 2}
 
 
@@ -33,8 +33,9 @@ UNBOUNDED_MSG = ("Not all your cameras are bounded by the unit sphere; please ma
 
 
 def default_field_impl():
-    """NERFPP_FIELD=simt selects the plain-fp32 evaluator (cross-check); default is tcgen05."""
-    return FIELD_SIMT if os.environ.get("NERFPP_FIELD", "tc").lower() == "simt" else FIELD_TC
+    """The field runs on the tcgen05 tensor-core kernel.  The plain-fp32 SIMT evaluator (FIELD_SIMT) is the cross-check /
+    full-precision reference: callers ask for it explicitly (``impl=FIELD_SIMT``); no environment switch selects it."""
+    return FIELD_TC
 
 
 def _stream():
@@ -257,28 +258,43 @@ def resample_merge_pair(fg_z_prev, fg_w_prev, bg_z_prev, bg_w_prev, N_samples, d
 # packed weights
 # ------------------------------------------------------------------------------------------------
 class PackedNet:
-    """Cache of one MLPNet's repacked parameters, re-packed when any parameter's version or
-    storage changes (optimizer steps bump ``_version``)."""
+    """Cache of one MLPNet's repacked parameters (fp16 MMA tiles in issue order).
+
+    Re-packed when any parameter's storage or ``_version`` changes -- optimizer steps and every in-place torch op bump
+    ``_version``.  Writes that bypass the version counter (``param.data.copy_(...)``, EMA through ``.data``, external
+    kernels) do NOT: call ``invalidate()`` after those (``NerfNet.invalidate_packed()`` does it for both nets).
+    The packed copy is always written into the SAME allocation per (device, impl), so captured CUDA graphs that baked its
+    address in stay valid.  Inside a stream capture nothing is packed by default (GraphedRenderStep refreshes the copy
+    outside its graph before each replay); a graph that CONTAINS an optimizer step (GraphedTrainStep) captures under
+    ``PackedNet.pack_in_capture`` so that the pack kernels are graph nodes and run on every replay."""
+    pack_in_capture = False
 
     def __init__(self, is_bg):
         self.is_bg = int(is_bg)
         self._buf = {}
         self._key = {}
 
+    def invalidate(self):
+        self._key.clear()
+
     def get(self, tensors, impl):
         """tensors: 24 parameter tensors in LAYER_NAMES order (weight, bias interleaved per layer)."""
         key = tuple((t.data_ptr(), t._version) for t in tensors)
         dev = tensors[0].device
-        if self._key.get(impl) != key or self._buf[impl].device != dev:
-            nbytes = _lib.lib().nerfpp_packed_bytes(self.is_bg, impl)
-            buf = self._buf.get(impl)
-            if buf is None or buf.numel() != nbytes or buf.device != dev:
-                buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        slot = (impl, str(dev))
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (capturing and PackedNet.pack_in_capture) or (not capturing and self._key.get(slot) != key) or slot not in self._buf:
+            buf = self._buf.get(slot)
+            if buf is None:
+                nbytes = _lib.lib().nerfpp_packed_bytes(self.is_bg, impl)
+                if capturing:
+                    raise NerfppError("PackedNet: first use inside a CUDA-graph capture; run one warm-up pass before capturing")
+                buf = self._buf[slot] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             ps = net_params_struct(tensors)
             with torch.cuda.device(dev):
                 check(_lib.lib().nerfpp_pack_weights(ctypes.byref(ps), self.is_bg, impl, _p(buf), _stream()), "pack_weights")
-            self._buf[impl], self._key[impl] = buf, key
-        return self._buf[impl]
+            self._key[slot] = None if capturing else key
+        return self._buf[slot]
 
 
 def net_params_struct(tensors):
@@ -373,7 +389,7 @@ def render_forward(packed_fg, packed_bg, ray_o, ray_d, fg_z_max, fg_z, bg_z, imp
     with torch.cuda.device(fz.device):
         if train:
             if impl != FIELD_TC:
-                raise NerfppError("training (autograd) runs on the tensor-core field only; unset NERFPP_FIELD=simt")
+                raise NerfppError("training (autograd) runs on the tensor-core field only (impl=FIELD_SIMT is inference-only)")
             tws = torch.empty(int(L.nerfpp_forward_train_workspace_bytes(n, sf, sb)) + 1024, device=fz.device, dtype=torch.uint8)
             pad = (-tws.data_ptr()) % 1024
             tws = tws[pad:]
@@ -421,6 +437,11 @@ class _NerfppFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model_cache, impl, ray_o, ray_d, fg_z_max, fg_z, bg_z, *params):
+        if any(ctx.needs_input_grad[2:7]):
+            # the reference's NerfNet.forward is differentiable w.r.t. the rays and depths too (pose / depth refinement
+            # would use that); this path only produces PARAMETER gradients -- say so instead of returning zeros
+            raise NerfppError("nerfpp_forward: gradients w.r.t. ray_o / ray_d / fg_z_max / fg_z_vals / bg_z_vals are not "
+                              "implemented (parameter gradients only); detach those inputs")
         fg_t, bg_t = params[:24], params[24:]
         packed_fg = model_cache[0].get(fg_t, impl)
         packed_bg = model_cache[1].get(bg_t, impl)

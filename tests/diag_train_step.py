@@ -9,6 +9,14 @@ import depth_loss as DL
 from nerfpp_b200 import ops
 from test_parity_gpu import make_models
 
+import ctypes
+from nerfpp_b200 import _lib as _L
+if os.environ.get("BWD_MODE"):
+    _L.lib().nerfpp_debug_set_bwd_mode.argtypes = [ctypes.c_int]
+    _L.lib().nerfpp_debug_set_bwd_mode(int(os.environ["BWD_MODE"]))
+if os.environ.get("BWD_CONS"):
+    _L.lib().nerfpp_debug_set_bwd_consumers.argtypes = [ctypes.c_int]
+    _L.lib().nerfpp_debug_set_bwd_consumers(int(os.environ["BWD_CONS"]))
 dev = torch.device("cuda:0")
 n = int(os.environ.get("RAYS", 4096))
 levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]

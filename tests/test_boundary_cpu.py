@@ -182,7 +182,10 @@ def test_bench_reference_arm_prints_one_json_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
               "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0
+    # "reference" = the reference's own files were found (baseline/_ref or /root/reference) and timed; "port" = the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["config"]["rays_per_gpu"] == 4096 and d["steps"] == 1 and d["warmup"] == 1
     # a rank other than 0 does no work and prints nothing
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                        capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
