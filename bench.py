@@ -456,9 +456,7 @@ def train_step_rate(models, batch, dev, n_rays, loss_type, dist, world, steps=20
     nets = [copy.deepcopy(m) for m in models]
     group = dist.group.WORLD if dist is not None else None
     ts = GraphedTrainStep(nets, n_rays, CASCADE, depth_loss_type=loss_type, lambda_depth=LAMBDA_DEPTH, depth_sigma=DEPTH_SIGMA,
-                          depth_scale=DEPTH_SCALE, device=dev, process_group=group)
-    for k in ts.dev_in:
-        ts.dev_in[k].copy_(batch[k])
+                          depth_scale=DEPTH_SCALE, device=dev, process_group=group, batch=batch)
     for _ in range(3):
         ts()
     if dist is not None:

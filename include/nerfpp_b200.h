@@ -53,7 +53,12 @@ typedef struct NerfppNetGrads {
 
 /* Field evaluators. TC = tcgen05 tensor-core path (fp16 operands, fp32 accumulate in TMEM);
  * SIMT = plain fp32 FFMA path (bit-for-bit fp32 arithmetic, ~20x slower; the cross-check). */
-enum { NERFPP_FIELD_TC = 0, NERFPP_FIELD_SIMT = 1 };
+enum {
+  NERFPP_FIELD_TC = 0,        /* tcgen05 tensor cores, fp16 operands (one pass), fp32 accumulate: the fast path */
+  NERFPP_FIELD_SIMT = 1,      /* plain fp32 on CUDA cores: cross-check */
+  NERFPP_FIELD_TC_SPLIT = 2   /* tcgen05, every operand carried as a hi + lo fp16 pair (3 MMA passes, ~22-bit operands):
+                                 the full-precision inference mode -- meets 1e-4 on trained weights at ~1/3 of the rate */
+};
 
 int nerfpp_abi_version(void);
 const char* nerfpp_last_error(void);

@@ -8,9 +8,9 @@ size_t npp_simt_packed_bytes(bool bg);
 int npp_pack_simt(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
 int npp_field_simt(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
                    float* out_sigma, float* out_rgb, float* out_depth_real, cudaStream_t st);
-size_t npp_tc_packed_bytes(bool bg);
-int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st);
-int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
+size_t npp_tc_packed_bytes(bool bg, bool prec);
+int npp_pack_tc(const NerfppNetParams* p, bool bg, bool prec, void* out, cudaStream_t st);
+int npp_field_tc(const void* packed, bool bg, bool prec, const float* ray_o, const float* ray_d, const float* z, int n, int S,
                  float* out_sigma, float* out_rgb, float* out_depth_real, void* train_ws, cudaStream_t st);
 size_t npp_tc_train_ws_bytes(long long n_samples);
 
@@ -28,7 +28,7 @@ extern "C" const char* nerfpp_last_error(void) { return g_err; }
 
 extern "C" int64_t nerfpp_packed_bytes(int is_bg, int field_impl) {
   if (field_impl == NERFPP_FIELD_SIMT) return (int64_t)npp_simt_packed_bytes(is_bg != 0);
-  if (field_impl == NERFPP_FIELD_TC) return (int64_t)npp_tc_packed_bytes(is_bg != 0);
+  if (field_impl == NERFPP_FIELD_TC || field_impl == NERFPP_FIELD_TC_SPLIT) return (int64_t)npp_tc_packed_bytes(is_bg != 0, field_impl == NERFPP_FIELD_TC_SPLIT);
   return -1;
 }
 
@@ -36,7 +36,8 @@ extern "C" int nerfpp_pack_weights(const NerfppNetParams* params, int is_bg, int
   NPP_CHECK_ARG(params && out_packed, "null argument");
   for (int l = 0; l < NERFPP_NLAYERS; ++l) NPP_CHECK_ARG(params->w[l] && params->b[l], "null parameter tensor");
   if (field_impl == NERFPP_FIELD_SIMT) return npp_pack_simt(params, is_bg != 0, out_packed, (cudaStream_t)stream);
-  if (field_impl == NERFPP_FIELD_TC) return npp_pack_tc(params, is_bg != 0, out_packed, (cudaStream_t)stream);
+  if (field_impl == NERFPP_FIELD_TC || field_impl == NERFPP_FIELD_TC_SPLIT)
+    return npp_pack_tc(params, is_bg != 0, field_impl == NERFPP_FIELD_TC_SPLIT, out_packed, (cudaStream_t)stream);
   NPP_CHECK_ARG(false, "unknown field_impl");
 }
 
@@ -49,8 +50,9 @@ extern "C" int nerfpp_field_forward(const void* packed, int is_bg, int field_imp
   if (n_rays == 0) return 0;
   if (field_impl == NERFPP_FIELD_SIMT)
     return npp_field_simt(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, (cudaStream_t)stream);
-  if (field_impl == NERFPP_FIELD_TC)
-    return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, nullptr, (cudaStream_t)stream);
+  if (field_impl == NERFPP_FIELD_TC || field_impl == NERFPP_FIELD_TC_SPLIT)
+    return npp_field_tc(packed, is_bg != 0, field_impl == NERFPP_FIELD_TC_SPLIT, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real,
+                        nullptr, (cudaStream_t)stream);
   NPP_CHECK_ARG(false, "unknown field_impl");
 }
 
@@ -66,7 +68,7 @@ extern "C" int nerfpp_field_forward_train(const void* packed, int is_bg, const f
   NPP_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "bad shape");
   NPP_CHECK_ARG(!is_bg || out_depth_real, "background needs out_depth_real");
   if (n_rays == 0) return 0;
-  return npp_field_tc(packed, is_bg != 0, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, train_workspace,
+  return npp_field_tc(packed, is_bg != 0, false, ray_o, ray_d, z, n_rays, n_samples, out_sigma, out_rgb, out_depth_real, train_workspace,
                       (cudaStream_t)stream);
 }
 

@@ -71,12 +71,15 @@ struct Step {
   short chunk;     // 64-column chunk within the E / A region
   short n;         // rows of the tile = outputs of the layer (256 or 128)
   short bias;      // 1: [n x 16] bias tile at the head of the slot (blob: bias tile then weight tile)
+  short lo;        // split-precision mode: 1 = the tile holds the LOW halves  W - fp16(W)  of the weights
   int col0;        // first input feature (state-dict column) of the tile; -2 = view dir + bias columns
   int blob_off, blob_bytes;
 };
-struct StepTable { Step s[48]; int n; int total; };
+struct StepTable { Step s[96]; int n; int total; };
 
-__host__ __device__ constexpr StepTable make_table(bool bg) {
+// prec: the split-precision ("3-pass") variant -- every weight tile is followed by the tile of its low halves, and the
+// kernel accumulates  A_hi W_hi + A_lo W_hi + A_hi W_lo  (operands carried as hi + lo fp16 pairs, ~22 bits)
+__host__ __device__ constexpr StepTable make_table(bool bg, bool prec = false) {
   StepTable t{};
   int i = 0, off = 0;
   for (int m = 0; m < NUM_MMA_LAYERS; ++m) {
@@ -85,8 +88,12 @@ __host__ __device__ constexpr StepTable make_table(bool bg) {
     short bias = (m != 9);
     auto push = [&](short src, short chunk, int col0) {
       const int bytes = n * 128 + (bias ? n * BIAS_ROW_BYTES : 0);
-      t.s[i] = Step{(short)m, src, chunk, n, bias, col0, off, bytes};
+      t.s[i] = Step{(short)m, src, chunk, n, bias, 0, col0, off, bytes};
       off += bytes; ++i; bias = 0;
+      if (prec) {
+        t.s[i] = Step{(short)m, src, chunk, n, 0, 1, col0, off, n * 128};
+        off += n * 128; ++i;
+      }
     };
     if (m == 0 || m == 5) for (int c = 0; c < (bg ? 2 : 1); ++c) push(SRC_E, (short)c, 64 * c);
     if (m == 9) push(SRC_E, 1, -2);   // view-direction columns [96,123) + the bias columns of E -> rgb.0 inputs 256..282 + bias
@@ -97,8 +104,8 @@ __host__ __device__ constexpr StepTable make_table(bool bg) {
   return t;
 }
 
-__constant__ StepTable c_tab[2] = {make_table(false), make_table(true)};
-static const StepTable h_tab[2] = {make_table(false), make_table(true)};
+__constant__ StepTable c_tab[4] = {make_table(false), make_table(true), make_table(false, true), make_table(true, true)};   // [2 prec + bg]
+static const StepTable h_tab[4] = {make_table(false), make_table(true), make_table(false, true), make_table(true, true)};
 
 // sin/cos of x * 2^k for the fp16 operand: two-constant Cody-Waite reduction to [-pi, pi] (exact to
 // ~3e-7 for |arg| < 2^10), then the SFU approximations (abs error ~5e-7, far below the fp16 rounding
@@ -113,17 +120,28 @@ __device__ __forceinline__ void fast_sincos(float arg, float* sn, float* cs) {
 
 // Encodes one row (sample) of the E operand: columns [col_base, +dim(1+2 nfreq)) = Embedder(x)
 // (nerf_network.py:42-60); fp16, 128B-swizzled.
+// LO_OFF != 0 (split-precision mode): the low half  v - fp16(v)  of every value goes to the same place LO_OFF bytes on,
+// and sin / cos come from the accurate library routine (the SFU approximations are good to ~5e-7 absolute, which the
+// fp16 operand hides but a 22-bit operand does not).
+template <int LO_OFF>
+__device__ __forceinline__ void put_split(uint8_t* region, uint32_t off, float v) {
+  const __half h = __float2half_rn(v);
+  *reinterpret_cast<__half*>(region + off) = h;
+  if (LO_OFF) *reinterpret_cast<__half*>(region + off + LO_OFF) = __float2half_rn(v - __half2float(h));
+}
+template <int LO_OFF>
 __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, uint8_t* region, int row, int col_base) {
-  for (int c = 0; c < dim; ++c) *reinterpret_cast<__half*>(region + sw128_off(row, col_base + c)) = __float2half_rn(x[c]);
+  for (int c = 0; c < dim; ++c) put_split<LO_OFF>(region, sw128_off(row, col_base + c), x[c]);
 #pragma unroll 1
   for (int k = 0; k < nfreq; ++k) {
     const float f = (float)(1 << k);
     for (int c = 0; c < dim; ++c) {
       float sn, cs;
-      fast_sincos(x[c] * f, &sn, &cs);
+      if (LO_OFF) sincosf(x[c] * f, &sn, &cs);
+      else fast_sincos(x[c] * f, &sn, &cs);
       const int col = col_base + dim + 2 * k * dim + c;
-      *reinterpret_cast<__half*>(region + sw128_off(row, col)) = __float2half_rn(sn);
-      *reinterpret_cast<__half*>(region + sw128_off(row, col + dim)) = __float2half_rn(cs);
+      put_split<LO_OFF>(region, sw128_off(row, col), sn);
+      put_split<LO_OFF>(region, sw128_off(row, col + dim), cs);
     }
   }
 }
@@ -135,7 +153,7 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 //   KIND 0  hidden layer: ReLU + fp16 pack, written back over the fp32 columns just read = next layer's A operand
 //   KIND 1  base layer 7: the same, then the sigma head (nerf_network.py:133) on the fp32 values AFTER the arrive
 //   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
-template <int KIND, bool SAVE>
+template <int KIND, bool SAVE, bool PREC>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
                                                uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
@@ -151,6 +169,17 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
 #pragma unroll
     for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
     tmem_st16(acc_addr + 64u * j, pk);
+    if (PREC) {   // the low halves  v - fp16(v)  go to the 16 columns behind the high halves (free: 32 fp32 columns were read)
+      uint32_t pl[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        float v0 = __uint_as_float(cur[2 * t]), v1 = __uint_as_float(cur[2 * t + 1]);
+        if (KIND != 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&pk[t]));
+        pl[t] = pack_f16x2<false>(__float_as_uint(v0 - hf.x), __float_as_uint(v1 - hf.y));
+      }
+      tmem_st16(acc_addr + 64u * j + 16u, pl);
+    }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
@@ -177,13 +206,13 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
   if (SAVE && KIND != 2) *mask_dst = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
 }
 
-template <bool SAVE>
+template <bool SAVE, bool PREC>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                   const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
                                                   uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
-  if (m < 7) epilogue_layer<0, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
-  else if (m == 7) epilogue_layer<1, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
-  else epilogue_layer<2, SAVE>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+  if (m < 7) epilogue_layer<0, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+  else if (m == 7) epilogue_layer<1, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+  else epilogue_layer<2, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
 }
 
 // Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
@@ -238,14 +267,18 @@ __device__ __forceinline__ void rgb_head(uint32_t acc_addr, uint32_t free_bar, i
 // CTA fetches 1/CLUSTER of it from L2 and multicasts that slice into all CLUSTER rings.
 // TRAIN: the training-mode forward (saves activations / masks / E tiles for the backward) is a separate instantiation so
 // that the inference kernel's register allocation never sees the save code.
-template <bool BG, int CLUSTER, bool TRAIN>
+// PREC: split-precision ("3-pass") inference variant, see make_table().  The E operand is then single-buffered: its two
+// 32 KB buffers hold the high and the low halves of one tile's encoding.
+template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
                 float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, TrainSave save, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  static_assert(!PREC || (!TRAIN && CLUSTER == 1), "the split-precision variant is inference-only");
   constexpr int D = BG ? 4 : 3;
-  const StepTable& tab = c_tab[BG ? 1 : 0];
+  constexpr uint32_t NEB = PREC ? 1 : 2;       // E buffers in rotation
+  const StepTable& tab = c_tab[(PREC ? 2 : 0) + (BG ? 1 : 0)];
   // read the thread coordinates once through volatile asm: otherwise ptxas re-reads %tid / %ctaid with S2R (tens of cycles
   // each) inside the epilogue's per-chunk loop, on the critical path of every mbarrier arrive
   uint32_t tid_pinned, cta_pinned;
@@ -283,8 +316,10 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     for (int i = (int)tid_pinned; i < 2 * E_BYTES / 16; i += NUM_EPI_WARPS * 32) reinterpret_cast<uint4*>(smem + OFF_E)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int eb = (int)tid_pinned >> 7, row = (int)tid_pinned & 127;
-    *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL)) = __float2half_rn(1.f);
-    *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL + 1)) = __float2half_rn(1.f);
+    if (!PREC || eb == 0) {        // (split precision: buffer 1 holds the low halves, whose constant columns stay 0)
+      *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL)) = __float2half_rn(1.f);
+      *reinterpret_cast<__half*>(smem + OFF_E + eb * E_BYTES + sw128_off(row, ONE_COL + 1)) = __float2half_rn(1.f);
+    }
     fence_proxy_async();
   }
   float* const tail_s = reinterpret_cast<float*>(smem + OFF_TAIL);
@@ -346,10 +381,11 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         mma_ts<1>(d, a0 + 40u, blo + 6u, idesc);
       };
       for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
-        const uint32_t eb = tile_i & 1;
+        const uint32_t eb = tile_i % NEB;
         const uint32_t e_addr = s_base + OFF_E + eb * E_BYTES;
+        const uint32_t e_lo_addr = e_addr + E_BYTES;                           // PREC: the low halves of the encoding
         const uint32_t one_lo = sw128_lo(e_addr + CHUNK_BYTES + 3 * 32);   // E columns [112,128): the constant-one columns
-        mbar_wait(bar(B_EFULL + eb), (tile_i >> 1) & 1);
+        mbar_wait(bar(B_EFULL + eb), (tile_i / NEB) & 1);
         if (TRAIN && lane == 0) bulk_s2g(save.e + (size_t)(grp * CLUSTER + (int)cta_rank) * E_BYTES, e_addr, E_BYTES);   // training: keep the E operand
         // layer 9 of the previous tile reads its A operand from accumulator buffer 0, which layer 0 is about to
         // overwrite: wait until those MMAs have completed (that ACC barrier completes 5 times per tile; layer 9 is the 5th)
@@ -369,11 +405,28 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                   const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
 #pragma unroll
                   for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
+                  if (PREC) {            // + E_lo W_hi
+                    const uint32_t allo = sw128_lo(e_lo_addr + c * CHUNK_BYTES);
+#pragma unroll
+                    for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, allo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
+                  }
                   release(wempty);
-                  if (m == 0 && c == E_CHUNKS - 1) tc_commit(bar(B_ACC));
+                  if (!PREC && m == 0 && c == E_CHUNKS - 1) tc_commit(bar(B_ACC));
                 }
                 __syncwarp();
                 advance();
+                if (PREC) {              // + E_hi W_lo (the next ring stage)
+                  wait_stage();
+                  if (elect_one()) {
+                    const uint32_t alo = sw128_lo(e_addr + c * CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+#pragma unroll
+                    for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, alo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
+                    release(wempty);
+                    if (m == 0 && c == E_CHUNKS - 1) tc_commit(bar(B_ACC));
+                  }
+                  __syncwarp();
+                  advance();
+                }
               }
             }
             if (m == 9) {                // view-direction columns + bias columns of E against rgb.0's view/bias tile
@@ -384,11 +437,28 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                 const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
                 mma_ss<0>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
                 mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
+                if (PREC) {
+                  const uint32_t allo = sw128_lo(e_lo_addr + CHUNK_BYTES);
+                  mma_ss<1>(d_tmem, allo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
+                  mma_ss<1>(d_tmem, allo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
+                }
                 release(wempty);
-                tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer (the bulk store below was waited for)
+                if (!PREC) tc_commit(bar(B_EEMPTY + eb));      // last reader of this tile's E buffer (the bulk store below was waited for)
               }
               __syncwarp();
               advance();
+              if (PREC) {
+                wait_stage();
+                if (elect_one()) {
+                  const uint32_t alo = sw128_lo(e_addr + CHUNK_BYTES), blo = sw128_lo(slot + AUX_BYTES);
+                  mma_ss<1>(d_tmem, alo + 4u, SW128_HI, blo + 4u, SW128_HI, idesc);
+                  mma_ss<1>(d_tmem, alo + 6u, SW128_HI, blo + 6u, SW128_HI, idesc);
+                  release(wempty);
+                  tc_commit(bar(B_EEMPTY + eb));
+                }
+                __syncwarp();
+                advance();
+              }
             }
             if (m != 0) {
               const bool early_bias = (m != 1 && m != 5 && m != 9);
@@ -411,14 +481,28 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                 if (elect_one()) {
                   if (c == 0 && m == 1) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, idesc);
                   ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), idesc);
+                  if (PREC) ts4(d_tmem, a_tmem + 64u * c + 16u, sw128_lo(slot + AUX_BYTES), idesc);     // + A_lo W_hi
                   release(wempty);
-                  if (c == 3) {
+                  if (!PREC && c == 3) {
                     tc_commit(bar(B_ACC + (m & 1)));
                     if (m == 9) tc_commit(bar(B_RGBREADY));   // the colour head (embedding warps) has its own barrier: one phase per tile
                   }
                 }
                 __syncwarp();
                 advance();
+                if (PREC) {              // + A_hi W_lo (the next ring stage)
+                  wait_stage();
+                  if (elect_one()) {
+                    ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), idesc);
+                    release(wempty);
+                    if (c == 3) {
+                      tc_commit(bar(B_ACC + (m & 1)));
+                      if (m == 9) tc_commit(bar(B_RGBREADY));
+                    }
+                  }
+                  __syncwarp();
+                  advance();
+                }
               }
               a_par ^= 1;
             }
@@ -446,13 +530,14 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       else rgb_head<false>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, nullptr, dst);
     };
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {
-      const uint32_t eb = tile_i & 1;
+      const uint32_t eb = tile_i % NEB;
       const int tile = grp * CLUSTER + (int)cta_rank;
       // tile_i - 2 finishes its layer 9 about when it releases the E buffer this iteration refills: the colour head is
       // the urgent one (layer 1 of tile_i - 1 waits for it), the embedding is not needed for another tile
-      if (tile_i >= 2) colour_head(tile_of(tile_i - 2), tile_i - 2);
+      // (split precision: ONE E buffer, released by layer 9 of tile_i - 1, whose colour head therefore comes first)
+      if (!PREC && tile_i >= 2) colour_head(tile_of(tile_i - 2), tile_i - 2);
       if (timing) mtt = clock64();
-      mbar_wait(bar(B_EEMPTY + eb), ((tile_i >> 1) & 1) ^ 1);
+      mbar_wait(bar(B_EEMPTY + eb), ((tile_i / NEB) & 1) ^ 1);
       if (timing) m_wait += clock64() - mtt;
       uint8_t* sE = smem + OFF_E + eb * E_BYTES;
       long long g = (long long)tile * TILE + row;
@@ -473,14 +558,17 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       float dn = norm3(d[0], d[1], d[2]);
       float vd[3] = {d[0] / dn, d[1] / dn, d[2] / dn};                              // ddp_model.py:82-83
       if (!(flags & 512)) {   // experiment: 512 = no embedding work (results wrong, timing only)
-        embed_vec(x, D, NF_POS, sE, row, 0);
-        embed_vec(vd, 3, NF_VIEW, sE, row, VIEW_COL);
+        embed_vec<PREC ? E_BYTES : 0>(x, D, NF_POS, sE, row, 0);
+        embed_vec<PREC ? E_BYTES : 0>(vd, 3, NF_VIEW, sE, row, VIEW_COL);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EFULL + eb));
+      // split precision: the single E buffer is released early in the previous tile's layer 9 (its view-direction MMAs come
+      // first), so the encoding above overlaps the rest of that layer; its colour head follows here
+      if (PREC && tile_i >= 1) colour_head(tile_of(tile_i - 1), tile_i - 1);
     }
-    for (uint32_t ti = tile_i >= 2 ? tile_i - 2 : 0; ti < tile_i; ++ti) colour_head(tile_of(ti), ti);
+    for (uint32_t ti = tile_i >= NEB ? tile_i - NEB : 0; ti < tile_i; ++ti) colour_head(tile_of(ti), ti);
     if (timing && (int)tid_pinned == EMB_WARP0 * 32) { dbg[8 * (int)cta_pinned + 4] = clock64() - m_t0; dbg[8 * (int)cta_pinned + 7] = m_wait; }
   } else {
     // ================= epilogue warps =================
@@ -522,10 +610,10 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (probe) probe_base[1] = clock64();
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 10 + m] = clock64();
         const uint32_t acc_addr = lane_addr + (uint32_t)(ab * 256 + 32 * hh);
-        if (TRAIN) epilogue_dispatch<true>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
+        if (TRAIN) epilogue_dispatch<true, false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
                                               reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)),
                                               smem + OFF_STG_TRAIN, stg_flip, sig_part, probe, flags);
-        else epilogue_dispatch<false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe);
+        else epilogue_dispatch<false, PREC>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe);
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
         if (m == 0) flush_pending();
       }
@@ -566,8 +654,10 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
 }
 
 // ---- packer: state-dict tensors -> fp16 tiles in MMA issue order + fp32 tail ------------------------
-__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__ out, int blob_total) {
-  const StepTable& tab = c_tab[bg ? 1 : 0];
+__device__ __forceinline__ float low_half(float v) { return v - __half2float(__float2half_rn(v)); }
+
+__global__ void pack_tc_kernel(NerfppNetParams p, bool bg, bool prec, uint8_t* __restrict__ out, int blob_total) {
+  const StepTable& tab = c_tab[(prec ? 2 : 0) + (bg ? 1 : 0)];
   const int i = blockIdx.y;
   if (i < tab.n) {
     const Step s = tab.s[i];
@@ -595,7 +685,7 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
         if (s.col0 == -2) {           // rgb.0: view part + bias columns
           const int c = 64 * s.chunk + kk;
           if (c >= VIEW_COL && c < VIEW_COL + VIEW_DIM) v = Wl[(size_t)nn * nin + W + (c - VIEW_COL)];
-          else if (c == ONE_COL || c == ONE_COL + 1) {
+          else if ((c == ONE_COL || c == ONE_COL + 1) && !s.lo) {       // (a low-half tile carries no bias: its columns stay 0)
             const float b = Bl[nn];
             const float hi = __half2float(__float2half_rn(b));
             v = (c == ONE_COL) ? hi : b - hi;
@@ -607,6 +697,7 @@ __global__ void pack_tc_kernel(NerfppNetParams p, bool bg, uint8_t* __restrict__
       } else {
         v = Wl[(size_t)nn * nin + s.col0 + kk];
       }
+      if (s.lo && !(s.src == SRC_E && s.col0 == -2 && (64 * s.chunk + kk == ONE_COL || 64 * s.chunk + kk == ONE_COL + 1))) v = low_half(v);
       blob[((nn >> 3) * 1024 + (nn & 7) * 128 + (((kk >> 3) ^ (nn & 7)) << 4)) / 2 + (kk & 7)] = __float2half_rn(v);
     }
   } else {
@@ -643,22 +734,25 @@ static void tc_config() {
   if (g_cluster != 1 && g_cluster != 2) g_cluster = 1;
 }
 
-size_t npp_tc_packed_bytes(bool bg) { tc_config(); return (size_t)tc::h_tab[bg].total + tc::T_TOTAL * sizeof(float); }
+size_t npp_tc_packed_bytes(bool bg, bool prec) { tc_config(); return (size_t)tc::h_tab[(prec ? 2 : 0) + bg].total + tc::T_TOTAL * sizeof(float); }
 
-int npp_pack_tc(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st) {
+int npp_pack_tc(const NerfppNetParams* p, bool bg, bool prec, void* out, cudaStream_t st) {
   tc_config();
-  const tc::StepTable& t = tc::h_tab[bg];
-  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, (uint8_t*)out, t.total);
+  const tc::StepTable& t = tc::h_tab[(prec ? 2 : 0) + bg];
+  tc::pack_tc_kernel<<<dim3(8, t.n + 1), 256, 0, st>>>(*p, bg, prec, (uint8_t*)out, t.total);
   NPP_CHECK_LAUNCH();
   return 0;
 }
 
-template <bool BG, int CLUSTER, bool TRAIN>
+template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, tc::TrainSave save, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER, TRAIN>;
-  static bool configured = false;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER, TRAIN, PREC>;
+  static bool configured_dev[64] = {false};       // the shared-memory opt-in is per device
   static int max_clusters = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     cudaLaunchConfig_t q{};
@@ -689,19 +783,18 @@ extern "C" void nerfpp_debug_set_tc_flags(int f) { g_flags = f; }
 
 size_t npp_tc_train_ws_bytes(long long n_samples) { return tc::train_ws_bytes((size_t)((n_samples + tc::TILE - 1) / tc::TILE)); }
 
-int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* ray_d, const float* z, int n, int S,
+int npp_field_tc(const void* packed, bool bg, bool prec, const float* ray_o, const float* ray_d, const float* z, int n, int S,
                  float* out_sigma, float* out_rgb, float* out_depth_real, void* train_ws, cudaStream_t st) {
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int sms_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& num_sms = sms_dev[dev & 63];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   tc_config();
   const long long total = (long long)n * S;
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;
-  const float* tail = (const float*)(blobs + tc::h_tab[bg].total);
+  const float* tail = (const float*)(blobs + tc::h_tab[(prec ? 2 : 0) + bg].total);
   tc::TrainSave save{nullptr, nullptr, nullptr, nullptr};
   if (train_ws) {
     uint8_t* w = (uint8_t*)train_ws;
@@ -709,6 +802,11 @@ int npp_field_tc(const void* packed, bool bg, const float* ray_o, const float* r
     save.mask = w + tc::train_ws_mask_off((size_t)num_tiles);
   }
 #define NPP_TC_LAUNCH(BG, C, T) launch_tc<BG, C, T>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
+  if (prec) {         // split precision: inference only
+    if (train_ws) { npp_set_error("field_tc: the split-precision variant has no training mode"); return -1; }
+    return bg ? launch_tc<true, 1, false, true>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
+              : launch_tc<false, 1, false, true>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st);
+  }
   if (train_ws) {     // (the cluster variant is an experiment: NERFPP_TC_CLUSTER=2)
     if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, true) : NPP_TC_LAUNCH(true, 2, true);
     return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, true) : NPP_TC_LAUNCH(false, 2, true);

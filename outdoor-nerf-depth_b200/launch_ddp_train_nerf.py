@@ -1,6 +1,6 @@
 """Launcher that runs the reference's UNMODIFIED ``ddp_train_nerf.py`` / ``ddp_test_nerf.py`` on the B200 kernels.
 
-    python launch_ddp_train_nerf.py --reference /path/to/outdoor-nerf-depth/nerf-methods/nerfplusplus \
+    python launch_ddp_train_nerf.py --reference /path/to/outdoor-nerf-depth/nerf-methods/nerfplusplus [--test] [--nccl] \
            --config configs/kitti.txt ...            (every other flag is the trainer's own, ddp_train_nerf.py:657-727)
 
 How the drop-in works:
@@ -57,7 +57,22 @@ def _use_reference_loader(reference_dir):
     return mod
 
 
-def _child(rank, args, reference_dir, entry):
+def patch_process_group(mod):
+    """--nccl: the trainer's ``setup`` (ddp_train_nerf.py:292-298) creates a gloo group, so DDP's gradient all-reduce
+    stages every bucket through host memory and TCP.  This replacement keeps its rendezvous (localhost, --port) but asks
+    for ``cpu:gloo,cuda:nccl``: CUDA tensors (the gradients) go over NCCL / NVLink, CPU tensors (render_single_image's
+    gather of host images, :229-243) still find gloo."""
+    import torch.distributed as dist
+
+    def setup(rank, world_size, port):
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world_size)
+    mod.setup = setup
+    return mod
+
+
+def _child(rank, args, reference_dir, entry, nccl=False):
     _paths(reference_dir)
     import importlib
     import torch
@@ -68,6 +83,8 @@ def _child(rank, args, reference_dir, entry):
     if os.environ.get("NERFPP_REFERENCE_LOADER") == "1":
         _use_reference_loader(reference_dir)
     trainer = patch_trainer_module(importlib.import_module("ddp_train_nerf"))
+    if nccl:
+        patch_process_group(trainer)
     if entry == "train":
         trainer.ddp_train_nerf(rank, args)
     else:
@@ -87,6 +104,9 @@ def main(argv=None):
     if "--test" in argv:
         argv.remove("--test")
         entry = "test"
+    nccl = "--nccl" in argv
+    if nccl:
+        argv.remove("--nccl")
     _paths(reference_dir)
     import torch
     if os.environ.get("NERFPP_REFERENCE_LOADER") == "1":
@@ -96,7 +116,7 @@ def main(argv=None):
     args = parser.parse_args(argv)
     if args.world_size == -1:                 # ddp_train_nerf.py:737-739
         args.world_size = torch.cuda.device_count()
-    torch.multiprocessing.spawn(_child, args=(args, reference_dir, entry), nprocs=args.world_size, join=True)
+    torch.multiprocessing.spawn(_child, args=(args, reference_dir, entry, nccl), nprocs=args.world_size, join=True)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("NERFPP_B200_LIB") or os.path.join(HERE, "libnerfpp_b2
 NLAYERS = 12
 ABI_VERSION = 1
 
-FIELD_TC, FIELD_SIMT = 0, 1
+FIELD_TC, FIELD_SIMT, FIELD_TC_SPLIT = 0, 1, 2
 DEPTH_NONE, DEPTH_MSE, DEPTH_L1, DEPTH_KL = 0, 1, 2, 3
 
 

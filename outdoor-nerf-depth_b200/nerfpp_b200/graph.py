@@ -211,7 +211,7 @@ class GraphedTrainStep(object):
     averaged across ranks with a single NCCL all-reduce per level inside the graph, replacing DDP-over-gloo (:298,323)."""
 
     def __init__(self, models, n_rays, cascade_samples=(64, 128), depth_loss_type="mse", lambda_depth=0.1, depth_sigma=0.01,
-                 depth_scale=1.0, lr=5e-4, device=None, process_group=None, warmup=3):
+                 depth_scale=1.0, lr=5e-4, device=None, process_group=None, warmup=3, batch=None):
         from . import backward as B
         from . import losses as LS
         self.models, self.n = list(models), int(n_rays)
@@ -226,8 +226,13 @@ class GraphedTrainStep(object):
         for k, w in keys:
             self.dev_in[k] = self._in_dev[off:off + n * w].view((n, w) if w > 1 else (n,))
             off += n * w
-        self.dev_in["ray_d"][:, 2] = 1.0
-        self.dev_in["min_depth"].fill_(1e-4)
+        self.dev_in["ray_d"][:, 2] = 1.0              # a valid batch for the warm-up passes: origin 0, direction +z,
+        self.dev_in["min_depth"].fill_(1e-4)          # grey pixels, a depth prior inside the sphere (no empty-mask NaN)
+        self.dev_in["rgb"].fill_(0.5)
+        self.dev_in["depth_sup"].fill_(0.5)
+        if batch is not None:
+            for k in self.dev_in:
+                self.dev_in[k].copy_(batch[k])
         self.optimizers = [torch.optim.Adam(m.parameters(), lr=lr, capturable=True) for m in self.models]
         self.process_group = process_group
         world = 1
@@ -271,6 +276,9 @@ class GraphedTrainStep(object):
                 losses.append(loss.detach())
             return torch.stack(losses), flag.flag
 
+        # the warm-up passes below are real optimisation steps: remember the weights and undo them afterwards (in place --
+        # the graph has the parameter and optimizer-state addresses baked in)
+        saved = [[p.detach().clone() for p in m.parameters()] for m in self.models]
         ops.PackedNet.pack_in_capture = True
         try:
             side = torch.cuda.Stream(device=dev)
@@ -287,6 +295,15 @@ class GraphedTrainStep(object):
             self.kernels_per_replay = ops.LAUNCHES[0] - before
         finally:
             ops.PackedNet.pack_in_capture = False
+        with torch.no_grad():
+            for m, keep, opt in zip(self.models, saved, self.optimizers):
+                for p, k in zip(m.parameters(), keep):
+                    p.copy_(k)
+                    p.grad = None if p.grad is None else p.grad.zero_()
+                for st in opt.state.values():          # exp_avg, exp_avg_sq, step: back to a fresh optimizer, same tensors
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
         self.replays = 0
 
     def __call__(self, batch=None):

@@ -96,6 +96,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--loss", default="mse")
+    ap.add_argument("--dense", action="store_true", help="raise the density bias of the initial weights by 5 (well-conditioned start)")
+    ap.add_argument("--quick", action="store_true", help="training + PSNR only (skip the parity tables)")
     ap.add_argument("--twin", action="store_true", help="also train a second fp32 arm from weights perturbed by 1e-6 (noise floor)")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r2_convergence.json"))
     args = ap.parse_args()
@@ -105,9 +107,12 @@ def main():
     train = TH.load_views(base, "synth_learnable", "train")
     test = TH.load_views(base, "synth_learnable", "test")
     init = O.make_params_levels(2)
-    rep = {"steps": args.steps, "rays": args.rays, "loss": args.loss, "lambda_depth": 0.1}
+    if args.dense:
+        init = [O.densify(p, 5.0) for p in init]
+    rep = {"steps": args.steps, "rays": args.rays, "loss": args.loss, "lambda_depth": 0.1, "dense_init": bool(args.dense)}
 
-    rep["init_forward_parity"] = forward_parity(init, train, dev)
+    if not args.quick:
+        rep["init_forward_parity"] = forward_parity(init, train, dev)
 
     t0 = time.time()
     w_ref, h_ref = TH.train_oracle(init, train, args.steps, dev, n_rand=args.rays, loss_type=args.loss, log=100)
@@ -146,6 +151,12 @@ def main():
         rep["test_oracle_twin"] = score(lambda v: TH.render_oracle(w_twin, v, dev))
         rep["noise_floor_db"] = rep["test_oracle_twin"]["psnr_mean"] - rep["test_oracle"]["psnr_mean"]
 
+    rep["loss_curve_every_50"] = {"oracle": [h_ref[i] for i in range(0, len(h_ref), 50)], "ours": [h_ours[i] for i in range(0, len(h_ours), 50)]}
+    if args.quick:
+        s = json.dumps(rep, indent=1)
+        print(s)
+        open(args.out, "w").write(s)
+        return
     rep["trained_forward_parity"] = forward_parity(w_ref, train, dev)
     rep["trained_backward_parity"] = backward_parity(w_ref, train, dev)
     rep["init_backward_parity"] = backward_parity(init, train, dev)

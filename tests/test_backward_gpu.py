@@ -117,8 +117,11 @@ def test_training_forward_saves_activations(is_bg):
 @pytest.mark.parametrize("loss_type", ["mse", "kl"])
 def test_full_backward_matches_oracle_autograd(loss_type):
     """loss.backward() through the drop-in module (nerfpp_forward_train + nerfpp_backward) vs torch autograd of the oracle,
-    for the trainer's loss (ddp_train_nerf.py:481-493).  Operands inside the kernels are fp16 under a loss scale: each
-    gradient tensor must agree to 2e-2 of its own max (typically a few 1e-3)."""
+    for the trainer's loss (ddp_train_nerf.py:481-493).  Operands inside the kernels are fp16 under two power-of-two loss
+    scales per net (backward.cu): every gradient tensor must have cosine >= 0.999 and a norm within 2 % of autograd's,
+    and its worst single entry must lie within 6 % (mse; measured 4.0 %) / 20 % (kl; measured 14 %) of the tensor's
+    LARGEST entry -- the KL prior's gradient -1/(w + 1e-5) spans eight decades across the samples of a batch, and what is
+    small next to the largest sample's contribution is carried with few fp16 bits."""
     from test_parity_gpu import make_models
     import depth_loss as DL
     n, cascade = 96, (64, 128)
@@ -161,7 +164,7 @@ def test_full_backward_matches_oracle_autograd(loss_type):
     print("worst relative gradient error", worst)
     # fp16 operands (11-bit significand) through nine layers of sums with heavy cancellation: individual entries of a
     # gradient tensor carry noise of a few percent of the tensor's largest entry, like any mixed-precision backward
-    assert worst <= 0.2, max(errs, key=errs.get)
+    assert worst <= (0.2 if loss_type == "kl" else 0.06), max(errs, key=errs.get)
 
 
 def test_backward_matches_reference_golden_gradients(golden_dir):
