@@ -243,7 +243,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n_rays, global_rays, loss_types, scaling, what = plan(args, world)
     clk = ClockSampler(local)          # its child process needs a moment to come up: started before the warm-up
-    _lib.lib()
+    L = _lib.lib()
+    if args.overlap is not None:       # A/B diagnostic: fg / bg nets on two streams -- 0 never, 1 default, 2 always
+        import ctypes
+        L.nerfpp_debug_set_overlap.argtypes = [ctypes.c_int]
+        L.nerfpp_debug_set_overlap(args.overlap)
     models = make_models(dev)
     host = make_rays(n_rays, seed=rank)                 # this rank's contiguous band of the global batch
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
@@ -687,6 +691,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="c2 only: weak = 4096 rays per GPU (default, the driver's curve); strong = 4096 rays in total, sharded over the ranks")
     ap.add_argument("--rays-per-gpu", type=int, default=0, help="override the rays each rank processes")
+    ap.add_argument("--overlap", type=int, default=None, help="diagnostic: fg / bg nets on two streams (0 never, 1 library default, 2 always)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

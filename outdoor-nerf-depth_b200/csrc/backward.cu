@@ -90,26 +90,29 @@ __global__ void grad_scale_kernel(const unsigned* __restrict__ absmax, float* __
 using namespace npp;
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-struct BwdWs { float *d_fg_sigma, *d_fg_rgb, *d_bg_sigma, *d_bg_rgb, *d_raw_sigma, *d_raw_rgb, *scale; unsigned* absmax; uint8_t *packed, *dz; size_t bytes; };
+// d_raw_* / packed / dz exist once PER NET: the two nets' chains run concurrently on two streams
+struct BwdWs { float *d_fg_sigma, *d_fg_rgb, *d_bg_sigma, *d_bg_rgb, *d_raw_sigma[2], *d_raw_rgb[2], *scale; unsigned* absmax; uint8_t *packed[2], *dz[2]; size_t bytes; };
 static BwdWs carve_bwd(void* base, int n, int sf, int sb) {
   BwdWs w;
   char* p = (char*)base;
   size_t o = 0;
-  const size_t smax = (size_t)n * (sf > sb ? sf : sb);
-  const size_t tiles = (smax + tc::TILE - 1) / tc::TILE;
+  const size_t tiles_net[2] = {((size_t)n * sf + tc::TILE - 1) / tc::TILE, ((size_t)n * sb + tc::TILE - 1) / tc::TILE};
   w.d_fg_sigma = (float*)(p + o); o += al256((size_t)n * sf * 4);
   w.d_fg_rgb = (float*)(p + o); o += al256((size_t)n * sf * 12);
   w.d_bg_sigma = (float*)(p + o); o += al256((size_t)n * sb * 4);
   w.d_bg_rgb = (float*)(p + o); o += al256((size_t)n * sb * 12);
-  w.d_raw_sigma = (float*)(p + o); o += al256(tiles * tc::TILE * 4);
-  w.d_raw_rgb = (float*)(p + o); o += al256(tiles * tc::TILE * 12);
   w.scale = (float*)(p + o); w.absmax = (unsigned*)(p + o + 32); o += 256;   // scale [2 nets][2], absmax [2 nets][4]
-  w.packed = (uint8_t*)(p + o); o += al256(npp_dgrad_packed_bytes());
-  o = (o + 1023) & ~(size_t)1023;
   int dev = 0;
   cudaGetDevice(&dev);
-  // fused: the producers' slot rings + counters; split: every dZ of the larger net
-  w.dz = (uint8_t*)(p + o); o += g_bwd_mode == 0 ? npp_bwd_fused_ws_bytes(dev) : tc::act_bytes(tiles);
+  for (int net = 0; net < 2; ++net) {
+    w.d_raw_sigma[net] = (float*)(p + o); o += al256(tiles_net[net] * tc::TILE * 4);
+    w.d_raw_rgb[net] = (float*)(p + o); o += al256(tiles_net[net] * tc::TILE * 12);
+    w.packed[net] = (uint8_t*)(p + o); o += al256(npp_dgrad_packed_bytes());
+    o = (o + 1023) & ~(size_t)1023;
+    // fused: the producers' slot rings + counters; two-kernel form: every dZ of the net
+    w.dz[net] = (uint8_t*)(p + o); o += g_bwd_mode == 0 ? npp_bwd_fused_ws_bytes(dev) : tc::act_bytes(tiles_net[net]);
+    o = (o + 1023) & ~(size_t)1023;
+  }
   w.bytes = o;
   return w;
 }
@@ -155,34 +158,41 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
   grad_scale_kernel<<<1, 2, 0, st>>>(b.absmax, b.scale);
   NPP_CHECK_LAUNCH();
   const size_t fg_train_bytes = (npp_tc_train_ws_bytes(tot_fg) + 1023) & ~(size_t)1023;
+  // the foreground and the background chain are independent: the background's kernels go to the side stream
+  cudaStream_t side = npp_fork(st);
+  int rc_net[2] = {0, 0};
   for (int bg = 0; bg < 2; ++bg) {
+    cudaStream_t s = bg ? side : st;
     const long long total = bg ? tot_bg : tot_fg;
     const size_t tiles = (size_t)((total + tc::TILE - 1) / tc::TILE);
     const uint8_t* tw = (const uint8_t*)train_workspace + (bg ? fg_train_bytes : 0);
     const uint8_t* act = tw;
     const uint8_t* etiles = tw + tc::train_ws_e_off(tiles);
     const float* raw_sigma = (const float*)(tw + tc::train_ws_sigma_off(tiles));
-    rc = npp_pack_dgrad(bg ? params_bg : params_fg, bg != 0, b.packed, st);
-    if (rc) return rc;
+    const uint8_t* mask = tw + tc::train_ws_mask_off(tiles);
+    const float* rgb = bg ? f.bg_rgb : f.fg_rgb;
+    const float* d_sigma = bg ? b.d_bg_sigma : b.d_fg_sigma;
+    const float* d_rgb = bg ? b.d_bg_rgb : b.d_fg_rgb;
+    const NerfppNetGrads* grads_net = bg ? grads_bg : grads_fg;
+    const float* scale = b.scale + 2 * bg;
+    int& r = rc_net[bg];
+    r = npp_pack_dgrad(bg ? params_bg : params_fg, bg != 0, b.packed[bg], s);
+    if (r) continue;
     if (g_bwd_mode == 0) {
-      rc = npp_field_bwd_fused(bg != 0, b.packed, (size_t)tcb::make_table().total, act, etiles, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb,
-                               raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma, bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.d_raw_sigma,
-                               b.d_raw_rgb, bg ? grads_bg : grads_fg, b.dz, st);
-      if (rc) return rc;
-      rc = npp_field_wgrad_heads(act, b.d_raw_sigma, b.d_raw_rgb, b.scale + 2 * bg, total, bg ? grads_bg : grads_fg, st);
-      if (rc) return rc;
+      r = npp_field_bwd_fused(bg != 0, b.packed[bg], (size_t)tcb::make_table().total, act, etiles, mask, rgb, raw_sigma, d_sigma, d_rgb, scale, total,
+                              b.d_raw_sigma[bg], b.d_raw_rgb[bg], grads_net, b.dz[bg], s);
+      if (!r) r = npp_field_wgrad_heads(act, b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, s);
       continue;
     }
     if (g_bwd_mode == 2)
-      rc = npp_field_dgrad_v2(b.packed, (size_t)tcb::make_table().total, bg != 0, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb,
-                              raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma, bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.dz,
-                              b.d_raw_sigma, b.d_raw_rgb, st);
+      r = npp_field_dgrad_v2(b.packed[bg], (size_t)tcb::make_table().total, bg != 0, act, mask, rgb, raw_sigma, d_sigma, d_rgb, scale, total, b.dz[bg],
+                             b.d_raw_sigma[bg], b.d_raw_rgb[bg], s);
     else
-      rc = npp_field_dgrad(b.packed, act, tw + tc::train_ws_mask_off(tiles), bg ? f.bg_rgb : f.fg_rgb, raw_sigma, bg ? b.d_bg_sigma : b.d_fg_sigma,
-                           bg ? b.d_bg_rgb : b.d_fg_rgb, b.scale + 2 * bg, total, b.dz, b.d_raw_sigma, b.d_raw_rgb, st);
-    if (rc) return rc;
-    rc = npp_field_wgrad(bg != 0, act, etiles, b.dz, b.d_raw_sigma, b.d_raw_rgb, b.scale + 2 * bg, total, bg ? grads_bg : grads_fg, st);
-    if (rc) return rc;
+      r = npp_field_dgrad(b.packed[bg], act, mask, rgb, raw_sigma, d_sigma, d_rgb, scale, total, b.dz[bg], b.d_raw_sigma[bg], b.d_raw_rgb[bg], s);
+    if (!r) r = npp_field_wgrad(bg != 0, act, etiles, b.dz[bg], b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, s);
   }
+  npp_join(st, side);
+  if (rc_net[0]) return rc_net[0];
+  if (rc_net[1]) return rc_net[1];
   return 0;
 }

@@ -23,6 +23,28 @@ void npp_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// fg / bg nets on two streams: 0 never, 1 (default) in the training entry points and for SMALL inference batches,
+// 2 always (tests and diagnostics select 0 / 2)
+static int g_overlap = 1;
+extern "C" void nerfpp_debug_set_overlap(int mode) { g_overlap = (mode >= 0 && mode <= 2) ? mode : 1; }
+static int g_overlap_tiles = 12 * 148;       // inference: fork when a net's launch has fewer 128-sample tiles than this
+extern "C" void nerfpp_debug_set_overlap_tiles(int tiles) { g_overlap_tiles = tiles; }
+NppFork* npp_fork_state() {
+  static NppFork st[64];
+  static bool made[64] = {false};
+  if (!g_overlap) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!made[dev]) {
+    if (cudaStreamCreateWithFlags(&st[dev].side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&st[dev].fork_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&st[dev].join_ev, cudaEventDisableTiming);
+    made[dev] = true;
+  }
+  return &st[dev];
+}
+
 extern "C" int nerfpp_abi_version(void) { return NERFPP_ABI_VERSION; }
 extern "C" const char* nerfpp_last_error(void) { return g_err; }
 
@@ -100,10 +122,17 @@ extern "C" int nerfpp_forward(const void* packed_fg, const void* packed_bg, int 
   NPP_CHECK_ARG(n_rays >= 0 && s_fg >= 1 && s_bg >= 1, "bad shape");
   if (n_rays == 0) return 0;
   FwdWs w = carve(workspace, n_rays, s_fg, s_bg);
+  // Inference: at 4096 rays per launch (14-42 waves of tiles) issuing the two nets on two streams measured neutral
+  // (1.93 vs 1.93 ms per step) -- the tails are short; with few waves per launch (strong scaling: 512 rays per GPU =
+  // 1.7 waves at the coarse level) the ragged last wave and the prologue are a large share, and the other net fills them.
+  const long long tiles_fg = ((long long)n_rays * s_fg + 127) / 128;
+  const bool fork = g_overlap == 2 || (g_overlap == 1 && tiles_fg < g_overlap_tiles);
+  cudaStream_t side = fork ? npp_fork((cudaStream_t)stream) : (cudaStream_t)stream;
   int rc = nerfpp_field_forward(packed_fg, 0, field_impl, ray_o, ray_d, fg_z, n_rays, s_fg, w.fg_sigma, w.fg_rgb, nullptr, stream);
+  int rc2 = nerfpp_field_forward(packed_bg, 1, field_impl, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr, (void*)side);
+  if (fork) npp_join((cudaStream_t)stream, side);
   if (rc) return rc;
-  rc = nerfpp_field_forward(packed_bg, 1, field_impl, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr, stream);
-  if (rc) return rc;
+  if (rc2) return rc2;
   return nerfpp_composite(ray_d, fg_z_max, fg_z, bg_z, w.fg_sigma, w.fg_rgb, w.bg_sigma, w.bg_rgb, w.bg_dr, n_rays, s_fg,
                           s_bg, out, stream);
 }
@@ -124,11 +153,13 @@ extern "C" int nerfpp_forward_train(const void* packed_fg, const void* packed_bg
   if (n_rays == 0) return 0;
   FwdWs w = carve(workspace, n_rays, s_fg, s_bg);
   const size_t fg_bytes = (npp_tc_train_ws_bytes((long long)n_rays * s_fg) + 1023) & ~(size_t)1023;
+  cudaStream_t side = npp_fork((cudaStream_t)stream);         // the two nets meet again in the composite (measured: -2 % per training step)
   int rc = nerfpp_field_forward_train(packed_fg, 0, ray_o, ray_d, fg_z, n_rays, s_fg, w.fg_sigma, w.fg_rgb, nullptr, train_workspace, stream);
+  int rc2 = nerfpp_field_forward_train(packed_bg, 1, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr,
+                                       (char*)train_workspace + fg_bytes, (void*)side);
+  npp_join((cudaStream_t)stream, side);
   if (rc) return rc;
-  rc = nerfpp_field_forward_train(packed_bg, 1, ray_o, ray_d, bg_z, n_rays, s_bg, w.bg_sigma, w.bg_rgb, w.bg_dr,
-                                  (char*)train_workspace + fg_bytes, stream);
-  if (rc) return rc;
+  if (rc2) return rc2;
   return nerfpp_composite(ray_d, fg_z_max, fg_z, bg_z, w.fg_sigma, w.fg_rgb, w.bg_sigma, w.bg_rgb, w.bg_dr, n_rays, s_fg,
                           s_bg, out, stream);
 }

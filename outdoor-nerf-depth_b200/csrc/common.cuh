@@ -121,6 +121,27 @@ __device__ __forceinline__ float bg_point(const BgRay& r, float depth, float pts
 
 }  // namespace npp
 
+// Fork / join of the caller's stream onto a library-owned side stream (one per device): the foreground and background
+// nets of a NerfNet are independent until the composite, so their kernels are issued on two streams.  Each field kernel
+// is a persistent one-CTA-per-SM grid, so they do not share SMs; what overlaps is the ragged last wave of one net with
+// the first tiles of the other (and prologues with tails).  Works under stream capture: the side stream joins the
+// capture through the fork event and must be joined back before the capture ends (npp_join does).
+struct NppFork { cudaStream_t side; cudaEvent_t fork_ev, join_ev; };
+NppFork* npp_fork_state();                       // capi.cu: lazily created per device; nullptr = overlap disabled
+inline cudaStream_t npp_fork(cudaStream_t main) {
+  NppFork* f = npp_fork_state();
+  if (!f) return main;
+  cudaEventRecord(f->fork_ev, main);
+  cudaStreamWaitEvent(f->side, f->fork_ev, 0);
+  return f->side;
+}
+inline void npp_join(cudaStream_t main, cudaStream_t side) {
+  if (side == main) return;
+  NppFork* f = npp_fork_state();
+  cudaEventRecord(f->join_ev, side);
+  cudaStreamWaitEvent(main, f->join_ev, 0);
+}
+
 // error plumbing shared by the .cu files
 void npp_set_error(const char* fmt, ...);
 #define NPP_CHECK_ARG(cond, msg) do { if (!(cond)) { npp_set_error("%s: %s", __func__, msg); return -1; } } while (0)

@@ -297,13 +297,13 @@ int npp_pack_dgrad(const NerfppNetParams* p, bool bg, void* out, cudaStream_t st
 int npp_field_dgrad(const void* packed, const void* act, const void* mask, const float* rgb, const float* raw_sigma, const float* d_sigma,
                     const float* d_rgb, const float* scale, long long total, void* dz, float* d_raw_sigma, float* d_raw_rgb,
                     cudaStream_t st) {
-  static int num_sms = 0;
-  static bool configured = false;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int sms_dev[64] = {0};               // both caches are per device (the shared-memory opt-in is a per-device attribute)
+  static bool configured_dev[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& num_sms = sms_dev[dev & 63];
+  bool& configured = configured_dev[dev & 63];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (!configured) { cudaFuncSetAttribute(tcb::field_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::SMEM_BYTES); configured = true; }
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const uint8_t* blobs = (const uint8_t*)packed;

@@ -262,13 +262,13 @@ int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float
 
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
                     const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st) {
-  static int num_sms = 0;
-  static bool configured = false;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int sms_dev[64] = {0};               // both caches are per device (the shared-memory opt-in is a per-device attribute)
+  static bool configured_dev[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& num_sms = sms_dev[dev & 63];
+  bool& configured = configured_dev[dev & 63];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (!configured) { cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcw::SMEM_BYTES); configured = true; }
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const int njobs = tcw::h_jobs[bg].n;

@@ -53,5 +53,49 @@ def full(path):
                 print("  %-82s %14s %s" % (m, r[i], units[i]))
 
 
+def _rows(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    return hdr, units, rows[2:]
+
+
+def _gb(val, unit):
+    """ncu prints dram bytes in a unit of its choosing per column (byte, Kbyte, Mbyte, Gbyte)."""
+    f = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(val.replace(",", "")) * f
+
+
+def traffic(field_rep, train_rep):
+    """profiles/traffic.json: what bench.py reports as roofline.traffic (it cannot run ncu inside a timed run).
+
+        python profiles/summarize_ncu.py traffic gpurun_out/prof_r2c_field.ncu-rep gpurun_out/prof_r2c_train.ncu-rep > profiles/traffic.json
+
+    field_tc_kernel: dram__bytes_read.sum + dram__bytes_write.sum averaged over the captured launches of the INFERENCE
+    kernel (one step = coarse/fine x fg/bg).  train_step: the same summed over every captured launch of one training
+    step's kernels (training forward, dgrad chain, wgrad, heads)."""
+    import json
+    import os
+    out = {}
+    hdr, units, rows = _rows(field_rep)
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    # template arguments <BG, CLUSTER, TRAIN, PREC>: the fast inference kernel is <., 1, 0, 0> (ncu prints bools as 0 / 1 or as
+    # (bool)0 / (bool)1 depending on the page)
+    norm = lambda k: k.replace("(bool)", "").replace("(int)", "").replace("false", "0").replace("true", "1")
+    vals = [_gb(r[ri], units[ri]) + _gb(r[wi], units[wi]) for r in rows if "field_tc_kernel" in r[ki] and ", 0, 0>" in norm(r[ki])]
+    out["field_tc_kernel"] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+                              "capture": "ncu --set full --clock-control none, " + os.path.basename(field_rep)}
+    hdr, units, rows = _rows(train_rep)
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    per = collections.OrderedDict()
+    for r in rows:
+        k = r[ki].split("(")[0].replace("void ", "")
+        per[k] = per.get(k, 0.0) + _gb(r[ri], units[ri]) + _gb(r[wi], units[wi])
+    out["train_step"] = {"dram_bytes_per_launch": sum(per.values()), "per_kernel": per, "launches": len(rows),
+                         "capture": "ncu --set full --clock-control none, one training step (both levels), " + os.path.basename(train_rep),
+                         "note": "bytes per STEP (sum over the step's field kernels)"}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
