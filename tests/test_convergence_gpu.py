@@ -53,7 +53,8 @@ def test_psnr_parity_after_training(trained):
     a second fp32 run from weights perturbed by 1e-6: 22.67 dB; depth RMSE 2.48 m (oracle), 2.09 m (CUDA), 1.87 m (twin).
     The oracle's weights rendered by the CUDA renderer give the oracle's PSNR to 0.002 dB -- the difference is the
     training trajectory, not the renderer.  From the reference's plain initialisation (chaotic start, see the fixture)
-    the same comparison gave -0.03 dB at 14.4 dB.  Bars: |dPSNR| <= 0.6 dB (a lag of ~40 steps), depth RMSE within 30 %."""
+    the same comparison gave -0.03 dB at 14.4 dB.  Bars: |dPSNR| <= 0.8 dB (a lag of ~50 steps; twice the worst seen),
+    depth RMSE within 50 % (the two fp32 runs differ by 25 %)."""
     TH, dev = trained["TH"], trained["dev"]
     ps, rm = {"ref": [], "ours": []}, {"ref": [], "ours": []}
     for v in trained["test"]:
@@ -67,8 +68,8 @@ def test_psnr_parity_after_training(trained):
     print("PSNR oracle %.3f dB, CUDA path %.3f dB, delta %+.3f dB; depth RMSE %.2f vs %.2f" % (
         mean(ps["ref"]), mean(ps["ours"]), d_psnr, mean(rm["ref"]), mean(rm["ours"])))
     assert mean(ps["ref"]) > 20.0 and mean(ps["ours"]) > 20.0
-    assert abs(d_psnr) <= 0.6, (ps, d_psnr)
-    assert abs(mean(rm["ours"]) / mean(rm["ref"]) - 1.0) <= 0.30, rm
+    assert abs(d_psnr) <= 0.8, (ps, d_psnr)
+    assert abs(mean(rm["ours"]) / mean(rm["ref"]) - 1.0) <= 0.50, rm
     # the renderer alone: the oracle's weights through the CUDA path render the oracle's image
     nets_ref = TH.make_ours(trained["w_ref"], dev)
     v = trained["test"][0]
