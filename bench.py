@@ -407,13 +407,24 @@ def run_ours(args):
         d2h = g_hosts[0].slots[0]._n_out * 4 + (world * n_rays * 4 * 4 if world > 1 else 0)
 
     # ---- the trainer's step (ddp_train_nerf.py:432-498: per level forward, loss, backward, Adam), every N ----
+    # (auxiliary legs never take the headline line down with them: a failure is reported in place of the numbers)
     train = None
     if not args.no_train:
-        train = train_step_rate(models, batch, dev, n_rays, loss_types[0], dist if world > 1 else None, world)
+        try:
+            train = train_step_rate(models, batch, dev, n_rays, loss_types[0], dist if world > 1 else None, world)
+        except Exception as e:   # noqa: BLE001
+            if world > 1:
+                raise            # a rank that drops out of a collective would hang the others: fail loudly instead
+            train = {"error": repr(e)[:500]}
 
     # ---- roofline of the dominant kernel (field_tc_kernel), timed alone with CUDA events ----
     roof = field_roofline(models, batch, dev)
-    cpu, parity = cpu_baseline(dev=dev) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else (None, None)
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, parity = cpu_baseline(dev=dev)
+        except Exception as e:   # noqa: BLE001
+            cpu = {"error": repr(e)[:500]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

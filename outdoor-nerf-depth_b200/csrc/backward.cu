@@ -9,9 +9,10 @@ int npp_field_dgrad(const void* packed, const void* act, const void* mask, const
                     const float* d_rgb, const float* scale, long long total, void* dz, float* d_raw_sigma, float* d_raw_rgb,
                     cudaStream_t st);
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
-                    const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st);
+                    const float* scale, long long total, const NerfppNetGrads* grads, void* ws, cudaStream_t st);
 int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
-                          const NerfppNetGrads* grads, cudaStream_t st);
+                          const NerfppNetGrads* grads, void* part_h, cudaStream_t st);
+size_t npp_wgrad_ws_bytes(int dev);
 size_t npp_tc_train_ws_bytes(long long n_samples);
 // bwd_fused.cu: dgrad chain and weight-gradient GEMMs as one producer/consumer kernel (dZ never leaves L2)
 size_t npp_bwd_fused_ws_bytes(int dev);
@@ -91,7 +92,7 @@ using namespace npp;
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // d_raw_* / packed / dz exist once PER NET: the two nets' chains run concurrently on two streams
-struct BwdWs { float *d_fg_sigma, *d_fg_rgb, *d_bg_sigma, *d_bg_rgb, *d_raw_sigma[2], *d_raw_rgb[2], *scale; unsigned* absmax; uint8_t *packed[2], *dz[2]; size_t bytes; };
+struct BwdWs { float *d_fg_sigma, *d_fg_rgb, *d_bg_sigma, *d_bg_rgb, *d_raw_sigma[2], *d_raw_rgb[2], *scale; unsigned* absmax; uint8_t *packed[2], *dz[2], *wg[2]; size_t bytes; };
 static BwdWs carve_bwd(void* base, int n, int sf, int sb) {
   BwdWs w;
   char* p = (char*)base;
@@ -111,6 +112,9 @@ static BwdWs carve_bwd(void* base, int n, int sf, int sb) {
     o = (o + 1023) & ~(size_t)1023;
     // fused: the producers' slot rings + counters; two-kernel form: every dZ of the net
     w.dz[net] = (uint8_t*)(p + o); o += g_bwd_mode == 0 ? npp_bwd_fused_ws_bytes(dev) : tc::act_bytes(tiles_net[net]);
+    o = (o + 1023) & ~(size_t)1023;
+    // per-CTA partials of the weight-gradient kernels (summed in a fixed order: the step is bit-reproducible)
+    w.wg[net] = (uint8_t*)(p + o); o += npp_wgrad_ws_bytes(dev);
     o = (o + 1023) & ~(size_t)1023;
   }
   w.bytes = o;
@@ -181,7 +185,7 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
     if (g_bwd_mode == 0) {
       r = npp_field_bwd_fused(bg != 0, b.packed[bg], (size_t)tcb::make_table().total, act, etiles, mask, rgb, raw_sigma, d_sigma, d_rgb, scale, total,
                               b.d_raw_sigma[bg], b.d_raw_rgb[bg], grads_net, b.dz[bg], s);
-      if (!r) r = npp_field_wgrad_heads(act, b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, s);
+      if (!r) r = npp_field_wgrad_heads(act, b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, b.wg[bg], s);
       continue;
     }
     if (g_bwd_mode == 2)
@@ -189,7 +193,7 @@ extern "C" int nerfpp_backward(const NerfppNetParams* params_fg, const NerfppNet
                              b.d_raw_sigma[bg], b.d_raw_rgb[bg], s);
     else
       r = npp_field_dgrad(b.packed[bg], act, mask, rgb, raw_sigma, d_sigma, d_rgb, scale, total, b.dz[bg], b.d_raw_sigma[bg], b.d_raw_rgb[bg], s);
-    if (!r) r = npp_field_wgrad(bg != 0, act, etiles, b.dz[bg], b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, s);
+    if (!r) r = npp_field_wgrad(bg != 0, act, etiles, b.dz[bg], b.d_raw_sigma[bg], b.d_raw_rgb[bg], scale, total, grads_net, b.wg[bg], s);
   }
   npp_join(st, side);
   if (rc_net[0]) return rc_net[0];

@@ -27,7 +27,8 @@ static const JobTable h_jobs[2] = {make_jobs(false), make_jobs(true)};
 
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restrict__ etiles, const uint8_t* __restrict__ dz,
-                const float* __restrict__ scale_ptr, int num_tiles, int splits, NerfppNetGrads grads) {
+                const float* __restrict__ scale_ptr, int num_tiles, int splits, NerfppNetGrads grads, float* __restrict__ part_w,
+                float* __restrict__ part_b) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,13 +137,22 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
       }
       const float inv_scale_b = 1.f / scale_ptr[jb.a_layer >= 8 ? 1 : 0];
       float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
+      // two threads (rh = 0 / 1: the two halves of the sample rows) hold partial sums of the same feature pair: they meet
+      // in shared memory and are added in a fixed order
+      __shared__ float s_b[2][256];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         if (h < jb.m_halves) {
           const int f0 = 128 * h + 64 * (p >> 5) + col;
-          atomicAdd(db + f0, bsum[h][0] * inv_scale_b);
-          atomicAdd(db + f0 + 1, bsum[h][1] * inv_scale_b);
+          s_b[rh][f0] = bsum[h][0];
+          s_b[rh][f0 + 1] = bsum[h][1];
         }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int f = t; f < 128 * jb.m_halves; f += 128) {
+        const float v = (s_b[0][f] + s_b[1][f]) * inv_scale_b;
+        if (part_b) part_b[(size_t)blockIdx.x * 256 + f] = v;      // deterministic: summed over the splits by wgrad_reduce_kernel
+        else atomicAdd(db + f, v);
+      }
     }
     if (t_end > t_begin) {
       mbar_wait(bar(B_DONE), 0);
@@ -157,10 +167,18 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
           uint32_t v[32];
           tmem_ld32(lane_addr + 256u * (uint32_t)h + (uint32_t)c0, v);
           tmem_ld_wait(v);
+          if (part_w) {     // deterministic: this CTA's partial [256 rows][256 columns], 128 contiguous bytes per thread
+            float4* dst = reinterpret_cast<float4*>(part_w + ((size_t)blockIdx.x * 256 + orow) * 256 + c0);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int col = c0 + e - jb.skip;
-            if (col >= 0 && col < jb.ncols) atomicAdd(wrow + col, __uint_as_float(v[e]) * inv_scale);
+            for (int e = 0; e < 8; ++e)
+              dst[e] = make_float4(__uint_as_float(v[4 * e]) * inv_scale, __uint_as_float(v[4 * e + 1]) * inv_scale,
+                                   __uint_as_float(v[4 * e + 2]) * inv_scale, __uint_as_float(v[4 * e + 3]) * inv_scale);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int col = c0 + e - jb.skip;
+              if (col >= 0 && col < jb.ncols) atomicAdd(wrow + col, __uint_as_float(v[e]) * inv_scale);
+            }
           }
         }
       }
@@ -174,19 +192,51 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
   }
 }
 
+// Sums the per-CTA partials of wgrad_tc_kernel over the sample splits IN ORDER and adds them to the gradients: every
+// weight / bias gradient entry is produced by exactly one job, so the result does not depend on scheduling -- the
+// training step is bit-reproducible (with red.global.add the order of the 24 partials per entry was not).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __restrict__ part_b, int num_tiles, int splits, NerfppNetGrads grads) {
+  const JobTable& jt = c_jobs[bg];
+  const int j = blockIdx.y;
+  if (j >= jt.n) return;
+  const Job jb = jt.j[j];
+  const int rows = 128 * jb.m_halves;
+  const int n_w = rows * jb.ncols, n_all = n_w + (jb.bias ? rows : 0);
+  float* dW = grads.w[jb.w_index];
+  float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    if (i < n_w) {
+      const int orow = i / jb.ncols, col = i - orow * jb.ncols;
+      for (int sp = 0; sp < splits; ++sp) {
+        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
+        if (t_end > t_begin) acc += part_w[((size_t)(j * splits + sp) * 256 + orow) * 256 + col + jb.skip];
+      }
+      dW[(size_t)orow * jb.ld + jb.col0 + col] += acc;
+    } else {
+      const int f = i - n_w;
+      for (int sp = 0; sp < splits; ++sp) {
+        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
+        if (t_end > t_begin) acc += part_b[(size_t)(j * splits + sp) * 256 + f];
+      }
+      db[f] += acc;
+    }
+  }
+}
+
 // Weighted column sums over all samples of a chunked [tiles][nch][128 rows][64 cols] fp16 operand buffer:
-//   out[ch][col] += inv_scale * sum_rows wgt[row][ch] * X[row][col]        (wgt == nullptr: plain column sums)
+//   out[ch][col] = inv_scale * sum_rows wgt[row][ch] * X[row][col]
 // This is the sigma head (X = h7, wgt = d raw sigma) and rgb.2 (X = rgb hidden, wgt = d raw rgb, NCH = 3).  blockIdx.x = sample-range split; one thread owns one 16-byte unit (8 columns) of
-// four rows of every chunk, so all loads are 16-byte and a warp reads 512 contiguous bytes; the 8-column partials meet in
-// shared memory and leave with one atomicAdd per column per CTA.  HBM-bound: every operand byte is read exactly once.
+// four rows of every chunk, so all loads are 16-byte and a warp reads 512 contiguous bytes; the 32 row groups' partials of
+// a column meet in shared memory and are added in a FIXED order.  HBM-bound: every operand byte is read exactly once.
+// The CTA's result goes to `part` (deterministic two-stage reduction: heads_reduce_kernel adds the CTAs in order).
 template <int NCH>
 __device__ __forceinline__ void weighted_colsum(const uint8_t* __restrict__ layer_base, int nch, const float* __restrict__ wgt,
-                                                long long total, int t_begin, int t_end, float inv_scale, float* s_acc,
-                                                float* __restrict__ out, int out_ld) {
+                                                long long total, int t_begin, int t_end, float inv_scale, float* s_scr,
+                                                float* __restrict__ part) {
   const int tid = threadIdx.x, u = tid & 7, r8 = tid >> 3;          // physical unit, row group: rows r8 + 32 k
   const int lu = u ^ (r8 & 7);                                       // logical unit (columns 8 lu .. 8 lu + 7) of all four rows
-  for (int i = tid; i < NCH * 64 * nch; i += 256) s_acc[i] = 0.f;
-  __syncthreads();
   for (int c = 0; c < nch; ++c) {
     float acc[NCH][8];
 #pragma unroll
@@ -203,7 +253,7 @@ __device__ __forceinline__ void weighted_colsum(const uint8_t* __restrict__ laye
         float w[NCH];
         const long long g = (long long)tile * TILE + r;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) w[ch] = wgt ? (g < total ? wgt[(size_t)g * NCH + ch] : 0.f) : 1.f;
+        for (int ch = 0; ch < NCH; ++ch) w[ch] = g < total ? wgt[(size_t)g * NCH + ch] : 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __half22float2(hp[e]);
@@ -212,43 +262,70 @@ __device__ __forceinline__ void weighted_colsum(const uint8_t* __restrict__ laye
         }
       }
     }
+    // s_scr[r8][ch][64 columns of this chunk]; then column (ch, col) = sum over r8 = 0..31 in order
+    __syncthreads();
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[ch * 64 * nch + c * 64 + lu * 8 + e], acc[ch][e]);
-  }
-  __syncthreads();
-  for (int i = tid; i < NCH * 64 * nch; i += 256) {
-    const int ch = i / (64 * nch), col = i % (64 * nch);
-    atomicAdd(out + (size_t)ch * out_ld + col, s_acc[i] * inv_scale);
+      for (int e = 0; e < 8; ++e) s_scr[(r8 * NCH + ch) * 64 + lu * 8 + e] = acc[ch][e];
+    __syncthreads();
+    for (int i = tid; i < NCH * 64; i += 256) {
+      const int ch = i >> 6, col = i & 63;
+      float a = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) a += s_scr[(q * NCH + ch) * 64 + col];
+      part[ch * 64 * nch + c * 64 + col] = a * inv_scale;
+    }
   }
 }
+
+constexpr int HEADS_PART = 512;     // floats per (CTA, head): <= 3 x 128 weight partials, then the bias partial(s) at [384..387)
 
 // blockIdx.y: 0 = sigma head weights (X = h7, weights d raw sigma), 1 = rgb.2 weights (X = rgb hidden, weights d raw rgb);
 // the heads' bias gradients (plain sums of 1 / 3 numbers per sample) are done by the same CTAs.
 __global__ void __launch_bounds__(256)
-wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ dz, const float* __restrict__ d_raw_sigma,
-                   const float* __restrict__ d_raw_rgb, const float* __restrict__ scale_ptr, long long total, int num_tiles,
-                   NerfppNetGrads grads) {
-  __shared__ float s_acc[3 * RGB_HID + W];
+wgrad_small_kernel(const uint8_t* __restrict__ act, const float* __restrict__ d_raw_sigma, const float* __restrict__ d_raw_rgb,
+                   const float* __restrict__ scale_ptr, long long total, int num_tiles, float* __restrict__ part_h) {
+  __shared__ float s_scr[32 * 3 * 64];
+  __shared__ float s_warp[8];
   const int what = 10 + blockIdx.y;     // (the layers' bias gradients are summed inside wgrad_tc_kernel)
   const int t_begin = (int)((long long)num_tiles * blockIdx.x / gridDim.x), t_end = (int)((long long)num_tiles * (blockIdx.x + 1) / gridDim.x);
   const float inv_scale = 1.f / scale_ptr[what == 10 ? 0 : 1];       // d raw sigma carries scale[0], d raw rgb scale[1]
   const size_t nt = (size_t)num_tiles;
-  if (what == 10) weighted_colsum<1>(act + act_layer_off(7, nt), 4, d_raw_sigma, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_SIGMA], 0);
-  else weighted_colsum<3>(act + act_layer_off(9, nt), 2, d_raw_rgb, total, t_begin, t_end, inv_scale, s_acc, grads.w[L_RGB2], RGB_HID);
-  // bias of the head: sum over the CTA's samples of d raw sigma / d raw rgb
+  float* part = part_h + ((size_t)blockIdx.x * 2 + blockIdx.y) * HEADS_PART;
+  if (what == 10) weighted_colsum<1>(act + act_layer_off(7, nt), 4, d_raw_sigma, total, t_begin, t_end, inv_scale, s_scr, part);
+  else weighted_colsum<3>(act + act_layer_off(9, nt), 2, d_raw_rgb, total, t_begin, t_end, inv_scale, s_scr, part);
+  // bias of the head: sum over the CTA's samples of d raw sigma / d raw rgb (warp sums, then the 8 warps in order)
   const int nch = what == 10 ? 1 : 3;
   const float* d = what == 10 ? d_raw_sigma : d_raw_rgb;
-  float* bout = what == 10 ? grads.b[L_SIGMA] : grads.b[L_RGB2];
   long long lo = (long long)t_begin * TILE, hi = (long long)t_end * TILE;
   if (hi > total) hi = total;
   for (int ch = 0; ch < nch; ++ch) {
     float a = 0.f;
     for (long long g = lo + threadIdx.x; g < hi; g += 256) a += d[(size_t)g * nch + ch];
     a = warp_sum(a);
-    if ((threadIdx.x & 31) == 0 && a != 0.f) atomicAdd(bout + ch, a * inv_scale);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      part[384 + ch] = t * inv_scale;
+    }
   }
+}
+
+// adds the CTAs' partials of wgrad_small_kernel in order: block 0 = sigma head (256 weights + 1 bias), block 1 = rgb.2 (384 + 3)
+__global__ void __launch_bounds__(512)
+heads_reduce_kernel(const float* __restrict__ part_h, int n_ctas, NerfppNetGrads grads) {
+  const int what = blockIdx.x, i = threadIdx.x;
+  const int n_w = what == 0 ? W : 3 * RGB_HID, n_b = what == 0 ? 1 : 3;
+  if (i >= n_w && !(i >= 384 && i < 384 + n_b)) return;
+  float a = 0.f;
+  for (int x = 0; x < n_ctas; ++x) a += part_h[((size_t)x * 2 + what) * HEADS_PART + i];
+  if (i < n_w) grads.w[what == 0 ? L_SIGMA : L_RGB2][i] += a;
+  else grads.b[what == 0 ? L_SIGMA : L_RGB2][i - 384] += a;
 }
 
 }  // namespace tcw
@@ -256,12 +333,26 @@ wgrad_small_kernel(const uint8_t* __restrict__ act, const uint8_t* __restrict__ 
 
 using namespace npp;
 
-// Accumulates (+=) the gradients of one net's 24 parameter tensors.
-int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
-                          const NerfppNetGrads* grads, cudaStream_t st);
+// Workspace of the deterministic reductions: the per-CTA partials of wgrad_tc_kernel (weights, biases) and of the heads kernel.
+static int wgrad_splits(int num_sms, int njobs, int num_tiles) {
+  int splits = (2 * num_sms) / njobs;              // ~2 waves of CTAs; every job gets the same number of sample ranges
+  if (splits > num_tiles) splits = num_tiles;
+  return splits < 1 ? 1 : splits;
+}
+static int heads_ctas(int num_sms, int num_tiles) { return num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms; }
+size_t npp_wgrad_ws_bytes(int dev) {
+  int num_sms = 148;
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t ctas = (size_t)2 * num_sms + tcw::MAX_JOBS;
+  return ctas * 256 * 256 * 4 + ctas * 256 * 4 + (size_t)4 * num_sms * 2 * tcw::HEADS_PART * 4 + 1024;
+}
 
+int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
+                          const NerfppNetGrads* grads, void* ws, cudaStream_t st);
+
+// Accumulates (+=) the gradients of one net's 24 parameter tensors.  `ws`: npp_wgrad_ws_bytes() bytes (256-byte aligned).
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
-                    const float* scale, long long total, const NerfppNetGrads* grads, cudaStream_t st) {
+                    const float* scale, long long total, const NerfppNetGrads* grads, void* ws, cudaStream_t st) {
   static int sms_dev[64] = {0};               // both caches are per device (the shared-memory opt-in is a per-device attribute)
   static bool configured_dev[64] = {false};
   int dev = 0;
@@ -272,26 +363,33 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   if (!configured) { cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcw::SMEM_BYTES); configured = true; }
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   const int njobs = tcw::h_jobs[bg].n;
-  int splits = (2 * num_sms) / njobs;              // ~2 waves of CTAs; every job gets the same number of sample ranges
-  if (splits > num_tiles) splits = num_tiles;
-  if (splits < 1) splits = 1;
+  const int splits = wgrad_splits(num_sms, njobs, num_tiles);
+  const size_t ctas_max = (size_t)2 * num_sms + tcw::MAX_JOBS;
+  float* part_w = (float*)ws;
+  float* part_b = part_w + ctas_max * 256 * 256;
+  float* part_h = part_b + ctas_max * 256;
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
-                                                                               (const uint8_t*)dz, scale, num_tiles, splits, *grads);
+                                                                               (const uint8_t*)dz, scale, num_tiles, splits, *grads, part_w, part_b);
   NPP_CHECK_LAUNCH();
-  return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, st);
+  tcw::wgrad_reduce_kernel<<<dim3(64, njobs), 256, 0, st>>>(bg ? 1 : 0, part_w, part_b, num_tiles, splits, *grads);
+  NPP_CHECK_LAUNCH();
+  return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, part_h, st);
 }
 
 // The two small heads (sigma: 256 -> 1, rgb.2: 128 -> 3): weighted column sums of h7 / the rgb hidden layer on CUDA cores.
+// `part_h`: 4 * #SMs * 2 * 512 floats (inside npp_wgrad_ws_bytes' workspace).
 int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
-                          const NerfppNetGrads* grads, cudaStream_t st) {
+                          const NerfppNetGrads* grads, void* part_h, cudaStream_t st) {
   int dev = 0, num_sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const int num_tiles = (int)((total + tc::TILE - 1) / tc::TILE);
   // 96 KB of activations per tile, read once.  A thread's loop over its tiles is a chain of dependent round trips to HBM
   // (4 x 16 B in flight per thread), so the sample range is cut fine enough for ~8 CTAs per SM to cover the latency.
-  int sx = num_tiles < 4 * num_sms ? num_tiles : 4 * num_sms;
-  tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, nullptr, d_raw_sigma, d_raw_rgb, scale, total, num_tiles, *grads);
+  const int sx = heads_ctas(num_sms, num_tiles);
+  tcw::wgrad_small_kernel<<<dim3(sx, 2), 256, 0, st>>>((const uint8_t*)act, d_raw_sigma, d_raw_rgb, scale, total, num_tiles, (float*)part_h);
+  NPP_CHECK_LAUNCH();
+  tcw::heads_reduce_kernel<<<2, 512, 0, st>>>((const float*)part_h, sx, *grads);
   NPP_CHECK_LAUNCH();
   return 0;
 }

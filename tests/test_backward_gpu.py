@@ -301,3 +301,72 @@ def test_backward_kernel_variants_agree(n, sf, sb):
             assert torch.isfinite(a).all(), (mode, k)
             err = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
             assert err <= 5e-4, (mode, k, err)
+
+
+def test_graphed_train_step():
+    """nerfpp_b200.GraphedTrainStep: the trainer's whole step (both levels: forward, loss, backward, Adam) as one CUDA graph.
+    Construction (warm-up passes + capture) must leave weights and optimizer state untouched; replays must train --
+    the first replay's loss is that of an eager step on the same batch (different uniform draws move the depth term a lot:
+    within a factor of 3), the losses fall over 30 replays, parameters move, and the weights the graph re-packs on every replay are the ones it updates."""
+    import copy
+    from test_parity_gpu import make_models
+    import depth_loss as DL
+    from nerfpp_b200 import GraphedTrainStep, ops
+    levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]
+    nets = make_models(levels)
+    before = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in nets]
+    n = 512
+    rays = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in O.synthetic_rays(n, seed=9).items()}
+    step = GraphedTrainStep(nets, n, (64, 128), depth_loss_type="mse", lambda_depth=0.1, depth_scale=rays["depth_scale"], batch=rays)
+    for net, sd in zip(nets, before):
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, sd[k]), k                    # construction did not train
+    for opt in step.optimizers:
+        assert all(float(v.abs().sum()) == 0.0 for st in opt.state.values() for v in st.values() if torch.is_tensor(v))
+    # an eager step of level 0 on the same batch, for scale
+    ref = copy.deepcopy(nets[0])
+    far = ops.intersect_sphere(rays["ray_o"], rays["ray_d"])
+    fg_z, bg_z = ops.coarse_depths(rays["min_depth"], far, 64, torch.rand(n, 64, device="cuda"), torch.rand(n, 64, device="cuda"))
+    out = ref(rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)
+    eager0 = float(torch.mean((out["rgb"] - rays["rgb"]) ** 2) + 0.1 * DL.depth_mse(rays["depth_sup"], out["depth"]))
+    first = step().clone()
+    assert eager0 / 3.0 <= float(first[0]) <= 3.0 * eager0, (float(first[0]), eager0)
+    for _ in range(30):
+        last = step()
+    step.check_unbounded()
+    last = last.clone()
+    assert torch.isfinite(last).all() and float(last[1]) < 0.9 * float(first[1]), (first, last)
+    moved = nets[1].state_dict()["nerf_net.fg_net.base_layers.3.0.weight"]
+    assert not torch.equal(moved, before[1]["nerf_net.fg_net.base_layers.3.0.weight"])
+    # eager inference with the trained weights after invalidating the host-side cache keys == the graph's own view
+    step.invalidate_inference_caches()
+    with torch.no_grad():
+        a = nets[1](rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)["rgb"]
+        nets[1].nerf_net.invalidate_packed()
+        b = nets[1](rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)["rgb"]
+    assert torch.equal(a, b)
+
+
+def test_backward_is_bit_reproducible():
+    """The weight-gradient kernels write per-CTA partials that are summed in a fixed order (wgrad_reduce_kernel,
+    heads_reduce_kernel) instead of red.global.add-ing into the gradient: two backward passes over the same batch give
+    bit-identical gradients for all 48 tensors, so a training run is reproducible."""
+    from test_parity_gpu import make_models
+    net = make_models([O.densify(O.make_params(), 5.0)])[0]
+    n = 1500
+    rays = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in O.synthetic_rays(n, seed=77).items()}
+    far = O.intersect_sphere(rays["ray_o"].cpu(), rays["ray_d"].cpu()).cuda()
+    g = torch.Generator().manual_seed(1)
+    fg_z = (torch.sort(torch.rand(n, 192, generator=g), -1)[0]).cuda() * far[:, None]
+    bg_z = torch.sort(torch.rand(n, 192, generator=g), -1)[0].cuda()
+    runs = []
+    for _ in range(3):
+        net.zero_grad()
+        out = net(rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)
+        loss = torch.mean((out["rgb"] - rays["rgb"]) ** 2) + 0.1 * torch.mean((out["depth"] - rays["depth_sup"]) ** 2)
+        loss.backward()
+        torch.cuda.synchronize()
+        runs.append({k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    for k in runs[0]:
+        assert float(runs[0][k].abs().max()) > 0, k
+        assert torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[0][k], runs[2][k]), k
