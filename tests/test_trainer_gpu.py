@@ -71,6 +71,11 @@ def test_unmodified_trainer_runs_on_the_kernels(scene):
     assert s0 is not None and s49 is not None, log[-3000:]
     assert all(np.isfinite(v) for v in s49.values()), s49
     assert s49["level_1/rgb_loss"] < 1e-3 * s0["level_1/rgb_loss"], (s0, s49)        # from ~1e7 (untrained background depth) to O(0.1)
+    # the trainer's own wall clock per iteration (:418,504-505: 1024 rays, both levels, its .item() syncs included)
+    its = [(_scalars(log, k) or {}).get("iter_time") for k in range(20, 50)]
+    its = sorted(t for t in its if t is not None)
+    print("unmodified trainer: median iter_time %.4f s over steps 20-49 (1024 rays/step => %.0f rays/s)" % (its[len(its) // 2], 1024 / its[len(its) // 2]))
+    assert its[len(its) // 2] < 0.25
     # ---- step 0 against the oracle: replay the trainer's RNG (ddp_train_nerf.py:404-408, 423-424; nerf_sample_ray_split.py:178)
     views = TH.load_views(scene, "synth_learnable", "train")
     np.random.seed(777)
