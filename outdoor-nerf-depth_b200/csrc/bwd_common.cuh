@@ -48,6 +48,9 @@ struct Job {
   int w_index;        // NerfppNetGrads.w index
   int ld, col0;       // row stride (in-features of the layer) and first column in dW
   int bias;           // this job also sums DZ[a_layer] over the samples = the layer's bias gradient (one job per layer)
+  int head;           // wgrad_tc_kernel's idle epilogue warps also take a small head's gradient from operands this job stages anyway:
+                      // 1 = sigma head (weights = sum d_raw_sigma * h7: this job's X IS h7), 2 = rgb.2 (sum d_raw_rgb * rgb hidden: the
+                      // 32 KB tile of ACT[9] rides along in the unused part of this job's X buffer)
 };
 constexpr int MAX_JOBS = 12;
 struct JobTable { Job j[MAX_JOBS]; int n; };
@@ -60,9 +63,9 @@ __host__ __device__ constexpr JobTable make_jobs(bool bg) {
     if (l == 5) t.j[i++] = Job{5, 2, 1, 0, 0, ech, 0, emb, 5, emb + W, 0, 0};             // base 5: [embedding | h4]
     t.j[i++] = Job{l, 2, 0, l - 1, 0, 4, 0, W, l, l == 5 ? emb + W : W, l == 5 ? emb : 0, 1};
   }
-  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0, 1};                               // base_remap
+  t.j[i++] = Job{8, 2, 0, 7, 0, 4, 0, W, L_REMAP, W, 0, 1, 1};                            // base_remap (+ sigma head)
   t.j[i++] = Job{9, 1, 0, 8, 0, 4, 0, W, L_RGB0, W + VIEW_DIM, 0, 1};                     // rgb.0: remap part
-  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W, 0};             // rgb.0: view-direction part
+  t.j[i++] = Job{9, 1, 1, 0, 1, 1, 32, VIEW_DIM, L_RGB0, W + VIEW_DIM, W, 0, 2};          // rgb.0: view-direction part (+ rgb.2 head)
   t.n = i;
   return t;
 }

@@ -22,13 +22,15 @@ constexpr int OFF_X = 0, OFF_A = 2 * X_BYTES, OFF_BAR = OFF_A + 2 * AH_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 enum { B_XFULL = 0, B_XEMPTY = 2, B_AFULL = 4, B_AEMPTY = 6, B_DONE = 8, B_COUNT = 9 };
 
+constexpr int HEAD_PART = 512;        // floats per CTA of a head job: <= 3 x 128 weight partials, bias partial(s) at 256 / 384..386
 __constant__ JobTable c_jobs[2] = {make_jobs(false), make_jobs(true)};
 static const JobTable h_jobs[2] = {make_jobs(false), make_jobs(true)};
 
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restrict__ etiles, const uint8_t* __restrict__ dz,
                 const float* __restrict__ scale_ptr, int num_tiles, int splits, NerfppNetGrads grads, float* __restrict__ part_w,
-                float* __restrict__ part_b) {
+                float* __restrict__ part_b, float* __restrict__ part_s, const float* __restrict__ d_raw_sigma,
+                const float* __restrict__ d_raw_rgb, long long total) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,10 +42,12 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
   const int t_begin = (int)((long long)num_tiles * split / splits), t_end = (int)((long long)num_tiles * (split + 1) / splits);
   const int N = 64 * jb.x_nchunks;
   const size_t nt = (size_t)num_tiles;
+  const int head = part_s ? jb.head : 0;          // (the heads ride along only in the deterministic two-kernel backward)
 
   if (threadIdx.x == 0) {
-    // an A half is released by the MMAs' commit and, in a bias job, also by each of the four column-sum warps
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_XEMPTY + i), 1); mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), jb.bias ? 5 : 1); }
+    // an A half is released by the MMAs' commit and, in a bias job, also by each of the four column-sum warps; likewise
+    // the X tile in a job that carries a head
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_XFULL + i), 1); mbar_init(bar(B_XEMPTY + i), head ? 5 : 1); mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), jb.bias ? 5 : 1); }
     mbar_init(bar(B_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -65,8 +69,10 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
         mbar_wait(bar(B_XEMPTY + xb), ((ix >> 1) & 1) ^ 1);
         const uint8_t* xsrc = jb.x_is_e ? etiles + ((size_t)tile * 2 + jb.x_chunk0) * CHUNK_BYTES
                                         : act + act_chunk_off(jb.x_layer, nt, (size_t)tile, jb.x_chunk0);
-        mbar_expect_tx(bar(B_XFULL + xb), (uint32_t)(jb.x_nchunks * CHUNK_BYTES));
+        mbar_expect_tx(bar(B_XFULL + xb), (uint32_t)((jb.x_nchunks + (head == 2 ? 2 : 0)) * CHUNK_BYTES));
         bulk_g2s(s_base + OFF_X + xb * X_BYTES, xsrc, (uint32_t)(jb.x_nchunks * CHUNK_BYTES), bar(B_XFULL + xb));
+        if (head == 2)      // the rgb hidden layer's tile, behind this job's single X chunk
+          bulk_g2s(s_base + OFF_X + xb * X_BYTES + CHUNK_BYTES, act + act_chunk_off(9, nt, (size_t)tile, 0), 2 * CHUNK_BYTES, bar(B_XFULL + xb));
         ++ix;
         for (int h = 0; h < jb.m_halves; ++h, ++ia) {
           const uint32_t ab = ia & 1;
@@ -108,50 +114,121 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
     // A operand: in a bias job they add it up over the samples (the bias gradient) instead of a second kernel reading
     // all of DZ from HBM again.  Thread = one pair of adjacent features x one half of the 128 sample rows; a warp reads
     // one 128-byte row of the swizzled image per step (conflict-free).
-    if (jb.bias && t_end > t_begin) {
+    if ((jb.bias || head) && t_end > t_begin) {
       const int t = threadIdx.x, p = t & 63, rh = t >> 6;
       const int col = 2 * (p & 31);
       const uint32_t coff = (uint32_t)((p >> 5) * CHUNK_BYTES + (col & 7) * 2);
       float bsum[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-      uint32_t ia = 0;
+      float hs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, hb[3] = {0.f, 0.f, 0.f};     // head: weight-gradient partials, bias partial
+      __shared__ float s_hw[2][3 * TILE];           // the tile's per-sample head gradients (double-buffered by tile parity)
+      uint32_t ia = 0, ix = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
+        if (head) {
+          // every thread fetches one sample's gradient(s); zero beyond the last sample
+          const long long g = (long long)tile * TILE + t;
+          float* hw = s_hw[ix & 1];
+          if (head == 1) hw[t] = g < total ? d_raw_sigma[g] : 0.f;
+          else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h < jb.m_halves) {
-            const uint32_t ab = ia & 1;
-            mbar_wait(bar(B_AFULL + ab), (ia >> 1) & 1);
-            const uint8_t* ah = smem + OFF_A + ab * AH_BYTES + coff;
+            for (int ch = 0; ch < 3; ++ch) hw[3 * t + ch] = g < total ? d_raw_rgb[3 * g + ch] : 0.f;
+          }
+          const uint32_t xb = ix & 1;
+          mbar_wait(bar(B_XFULL + xb), (ix >> 1) & 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (head == 1) {
+            // sigma head: columns (2 (t & 31), +1) of chunk t >> 5 of h7, all 128 rows; a warp reads one 128-byte row per step
+            const uint8_t* xc = smem + OFF_X + xb * X_BYTES + (t >> 5) * CHUNK_BYTES + ((t & 31) & 3) * 4;
+            const int unit = (t & 31) >> 2;
 #pragma unroll 8
+            for (int r = 0; r < TILE; ++r) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xc + (r >> 3) * 1024 + (r & 7) * 128 + ((unit ^ (r & 7)) << 4)));
+              const float w = hw[r];
+              hs[0][0] = fmaf(w, f.x, hs[0][0]);
+              hs[0][1] = fmaf(w, f.y, hs[0][1]);
+              hb[0] += w;
+            }
+          } else {
+            // rgb.2: columns (col, col + 1) of the rgb hidden tile (behind the E chunk), this thread's half of the rows
+            const uint8_t* xc = smem + OFF_X + xb * X_BYTES + CHUNK_BYTES + coff;
+#pragma unroll 4
             for (int k = 0; k < 64; ++k) {
               const int r = rh * 64 + k;
-              const __half2 v = *reinterpret_cast<const __half2*>(ah + (r >> 3) * 1024 + (r & 7) * 128 + (((col >> 3) ^ (r & 7)) << 4));
-              const float2 f = __half22float2(v);
-              bsum[h][0] += f.x;
-              bsum[h][1] += f.y;
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xc + (r >> 3) * 1024 + (r & 7) * 128 + (((col >> 3) ^ (r & 7)) << 4)));
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                const float w = hw[3 * r + ch];
+                hs[ch][0] = fmaf(w, f.x, hs[ch][0]);
+                hs[ch][1] = fmaf(w, f.y, hs[ch][1]);
+                hb[ch] += w;
+              }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_AEMPTY + ab));
-            ++ia;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_XEMPTY + xb));
+          ++ix;
+        }
+        if (jb.bias) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < jb.m_halves) {
+              const uint32_t ab = ia & 1;
+              mbar_wait(bar(B_AFULL + ab), (ia >> 1) & 1);
+              const uint8_t* ah = smem + OFF_A + ab * AH_BYTES + coff;
+#pragma unroll 8
+              for (int k = 0; k < 64; ++k) {
+                const int r = rh * 64 + k;
+                const __half2 v = *reinterpret_cast<const __half2*>(ah + (r >> 3) * 1024 + (r & 7) * 128 + (((col >> 3) ^ (r & 7)) << 4));
+                const float2 f = __half22float2(v);
+                bsum[h][0] += f.x;
+                bsum[h][1] += f.y;
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(B_AEMPTY + ab));
+              ++ia;
+            }
           }
         }
       }
-      const float inv_scale_b = 1.f / scale_ptr[jb.a_layer >= 8 ? 1 : 0];
-      float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
-      // two threads (rh = 0 / 1: the two halves of the sample rows) hold partial sums of the same feature pair: they meet
-      // in shared memory and are added in a fixed order
       __shared__ float s_b[2][256];
+      if (jb.bias) {
+        const float inv_scale_b = 1.f / scale_ptr[jb.a_layer >= 8 ? 1 : 0];
+        float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
+        // two threads (rh = 0 / 1: the two halves of the sample rows) hold partial sums of the same feature pair: they meet
+        // in shared memory and are added in a fixed order
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if (h < jb.m_halves) {
-          const int f0 = 128 * h + 64 * (p >> 5) + col;
-          s_b[rh][f0] = bsum[h][0];
-          s_b[rh][f0 + 1] = bsum[h][1];
+        for (int h = 0; h < 2; ++h)
+          if (h < jb.m_halves) {
+            const int f0 = 128 * h + 64 * (p >> 5) + col;
+            s_b[rh][f0] = bsum[h][0];
+            s_b[rh][f0 + 1] = bsum[h][1];
+          }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int f = t; f < 128 * jb.m_halves; f += 128) {
+          const float v = (s_b[0][f] + s_b[1][f]) * inv_scale_b;
+          if (part_b) part_b[(size_t)blockIdx.x * 256 + f] = v;      // deterministic: summed over the splits by wgrad_reduce_kernel
+          else atomicAdd(db + f, v);
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int f = t; f < 128 * jb.m_halves; f += 128) {
-        const float v = (s_b[0][f] + s_b[1][f]) * inv_scale_b;
-        if (part_b) part_b[(size_t)blockIdx.x * 256 + f] = v;      // deterministic: summed over the splits by wgrad_reduce_kernel
-        else atomicAdd(db + f, v);
+      }
+      if (head == 1) {          // sigma head: 256 weight partials (one column pair per thread) + the bias partial
+        const float inv = 1.f / scale_ptr[0];
+        float* ps = part_s + (size_t)blockIdx.x * HEAD_PART;
+        ps[2 * t] = hs[0][0] * inv;
+        ps[2 * t + 1] = hs[0][1] * inv;
+        if (t == 0) ps[256] = hb[0] * inv;
+      } else if (head == 2) {   // rgb.2: the two row halves of a column pair meet in shared memory, fixed order
+        const float inv = 1.f / scale_ptr[1];
+        float* ps = part_s + (size_t)blockIdx.x * HEAD_PART;
+        const int c0 = 64 * (p >> 5) + col;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");         // the previous channel's sums have been read
+          s_b[rh][c0] = hs[ch][0];
+          s_b[rh][c0 + 1] = hs[ch][1];
+          if (p == 0) s_b[rh][128] = hb[ch];                     // (every thread of a row half holds the same bias partial)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          ps[ch * RGB_HID + t] = (s_b[0][t] + s_b[1][t]) * inv;
+          if (t == 0) ps[384 + ch] = (s_b[0][128] + s_b[1][128]) * inv;
+        }
       }
     }
     if (t_end > t_begin) {
@@ -196,13 +273,16 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
 // weight / bias gradient entry is produced by exactly one job, so the result does not depend on scheduling -- the
 // training step is bit-reproducible (with red.global.add the order of the 24 partials per entry was not).
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __restrict__ part_b, int num_tiles, int splits, NerfppNetGrads grads) {
+wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __restrict__ part_b, const float* __restrict__ part_s, int num_tiles,
+                    int splits, NerfppNetGrads grads) {
   const JobTable& jt = c_jobs[bg];
   const int j = blockIdx.y;
   if (j >= jt.n) return;
   const Job jb = jt.j[j];
   const int rows = 128 * jb.m_halves;
-  const int n_w = rows * jb.ncols, n_all = n_w + (jb.bias ? rows : 0);
+  const int n_b = jb.bias ? rows : 0;
+  const int n_h = !part_s ? 0 : jb.head == 1 ? W + 1 : jb.head == 2 ? 3 * RGB_HID + 3 : 0;      // head weights, then its bias(es)
+  const int n_w = rows * jb.ncols, n_all = n_w + n_b + n_h;
   float* dW = grads.w[jb.w_index];
   float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += gridDim.x * blockDim.x) {
@@ -214,13 +294,23 @@ wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __res
         if (t_end > t_begin) acc += part_w[((size_t)(j * splits + sp) * 256 + orow) * 256 + col + jb.skip];
       }
       dW[(size_t)orow * jb.ld + jb.col0 + col] += acc;
-    } else {
+    } else if (i < n_w + n_b) {
       const int f = i - n_w;
       for (int sp = 0; sp < splits; ++sp) {
         const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
         if (t_end > t_begin) acc += part_b[(size_t)(j * splits + sp) * 256 + f];
       }
       db[f] += acc;
+    } else {
+      const int f = i - n_w - n_b;
+      const int nw = jb.head == 1 ? W : 3 * RGB_HID;
+      const int src = f < nw ? f : (jb.head == 1 ? 256 : 384) + (f - nw);
+      for (int sp = 0; sp < splits; ++sp) {
+        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
+        if (t_end > t_begin) acc += part_s[(size_t)(j * splits + sp) * HEAD_PART + src];
+      }
+      const int l = jb.head == 1 ? L_SIGMA : L_RGB2;
+      if (f < nw) grads.w[l][f] += acc; else grads.b[l][f - nw] += acc;
     }
   }
 }
@@ -344,11 +434,18 @@ size_t npp_wgrad_ws_bytes(int dev) {
   int num_sms = 148;
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t ctas = (size_t)2 * num_sms + tcw::MAX_JOBS;
-  return ctas * 256 * 256 * 4 + ctas * 256 * 4 + (size_t)4 * num_sms * 2 * tcw::HEADS_PART * 4 + 1024;
+  return ctas * 256 * 256 * 4 + ctas * 256 * 4 + ctas * tcw::HEAD_PART * 4 + (size_t)4 * num_sms * 2 * tcw::HEADS_PART * 4 + 1024;
 }
 
 int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float* d_raw_rgb, const float* scale, long long total,
                           const NerfppNetGrads* grads, void* ws, cudaStream_t st);
+
+// The two small heads (sigma, rgb.2) can ride along in wgrad_tc_kernel's base_remap / view-direction jobs (Job::head: no
+// second pass over ACT[7] / ACT[9], 1.7 GB per step) -- built, correct, and measured 0.2 ms per step SLOWER than their own
+// HBM-bound kernel (10.41 vs 10.21 ms, same box, gpurun_out/exp18.log): the CUDA-core sums make those two jobs' CTAs the
+// long pole of the launch.  Off by default; tests may switch it on.
+static int g_heads_folded = 0;
+extern "C" void nerfpp_debug_set_heads_folded(int on) { g_heads_folded = on ? 1 : 0; }
 
 // Accumulates (+=) the gradients of one net's 24 parameter tensors.  `ws`: npp_wgrad_ws_bytes() bytes (256-byte aligned).
 int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz, const float* d_raw_sigma, const float* d_raw_rgb,
@@ -367,13 +464,16 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
   const size_t ctas_max = (size_t)2 * num_sms + tcw::MAX_JOBS;
   float* part_w = (float*)ws;
   float* part_b = part_w + ctas_max * 256 * 256;
-  float* part_h = part_b + ctas_max * 256;
+  float* part_s = part_b + ctas_max * 256;
+  // the two small heads (sigma, rgb.2) ride along in the base_remap and view-direction jobs: no second pass over ACT[7] / ACT[9]
   tcw::wgrad_tc_kernel<<<njobs * splits, tcw::THREADS, tcw::SMEM_BYTES, st>>>(bg ? 1 : 0, (const uint8_t*)act, (const uint8_t*)etiles,
-                                                                               (const uint8_t*)dz, scale, num_tiles, splits, *grads, part_w, part_b);
+                                                                               (const uint8_t*)dz, scale, num_tiles, splits, *grads, part_w, part_b,
+                                                                               g_heads_folded ? part_s : nullptr, d_raw_sigma, d_raw_rgb, total);
   NPP_CHECK_LAUNCH();
-  tcw::wgrad_reduce_kernel<<<dim3(64, njobs), 256, 0, st>>>(bg ? 1 : 0, part_w, part_b, num_tiles, splits, *grads);
+  tcw::wgrad_reduce_kernel<<<dim3(64, njobs), 256, 0, st>>>(bg ? 1 : 0, part_w, part_b, g_heads_folded ? part_s : nullptr, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
-  return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, part_h, st);
+  if (!g_heads_folded) return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, part_s + ctas_max * tcw::HEAD_PART, st);
+  return 0;
 }
 
 // The two small heads (sigma: 256 -> 1, rgb.2: 128 -> 3): weighted column sums of h7 / the rgb hidden layer on CUDA cores.

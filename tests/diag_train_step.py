@@ -17,6 +17,9 @@ if os.environ.get("BWD_MODE"):
 if os.environ.get("BWD_CONS"):
     _L.lib().nerfpp_debug_set_bwd_consumers.argtypes = [ctypes.c_int]
     _L.lib().nerfpp_debug_set_bwd_consumers(int(os.environ["BWD_CONS"]))
+if os.environ.get("HEADS_FOLDED"):
+    _L.lib().nerfpp_debug_set_heads_folded.argtypes = [ctypes.c_int]
+    _L.lib().nerfpp_debug_set_heads_folded(int(os.environ["HEADS_FOLDED"]))
 dev = torch.device("cuda:0")
 n = int(os.environ.get("RAYS", 4096))
 levels = [O.densify(p, 5.0) for p in O.make_params_levels(2)]

@@ -347,6 +347,38 @@ def test_graphed_train_step():
     assert torch.equal(a, b)
 
 
+def test_heads_folded_into_wgrad_agree():
+    """Job::head (wgrad_tc.cu): the sigma / rgb.2 head gradients taken by the base_remap / view-direction jobs' idle
+    epilogue warps instead of wgrad_small_kernel -- off by default (measured slower), must give the same gradients."""
+    import ctypes
+    from nerfpp_b200 import _lib
+    from test_parity_gpu import make_models
+    L = _lib.lib()
+    L.nerfpp_debug_set_heads_folded.argtypes = [ctypes.c_int]
+    net = make_models([O.densify(O.make_params(), 5.0)])[0]
+    n = 300
+    rays = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in O.synthetic_rays(n, seed=5).items()}
+    far = O.intersect_sphere(rays["ray_o"].cpu(), rays["ray_d"].cpu()).cuda()
+    g = torch.Generator().manual_seed(2)
+    fg_z = (torch.sort(torch.rand(n, 100, generator=g), -1)[0]).cuda() * far[:, None]
+    bg_z = torch.sort(torch.rand(n, 70, generator=g), -1)[0].cuda()
+    res = {}
+    try:
+        for folded in (0, 1):
+            L.nerfpp_debug_set_heads_folded(folded)
+            net.zero_grad()
+            out = net(rays["ray_o"], rays["ray_d"], far, fg_z, bg_z)
+            (torch.mean((out["rgb"] - rays["rgb"]) ** 2) + 0.1 * torch.mean((out["depth"] - rays["depth_sup"]) ** 2)).backward()
+            torch.cuda.synchronize()
+            res[folded] = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    finally:
+        L.nerfpp_debug_set_heads_folded(0)
+    for k in res[0]:
+        a, b = res[1][k].double(), res[0][k].double()
+        tol = 1e-5 if ("sigma_layers" in k or "rgb_layers.2" in k) else 0.0     # the heads: same products, another summation order
+        assert float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-30), k
+
+
 def test_backward_is_bit_reproducible():
     """The weight-gradient kernels write per-CTA partials that are summed in a fixed order (wgrad_reduce_kernel,
     heads_reduce_kernel) instead of red.global.add-ing into the gradient: two backward passes over the same batch give
