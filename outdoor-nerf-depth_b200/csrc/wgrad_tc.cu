@@ -272,6 +272,22 @@ wgrad_tc_kernel(int bg, const uint8_t* __restrict__ act, const uint8_t* __restri
 // Sums the per-CTA partials of wgrad_tc_kernel over the sample splits IN ORDER and adds them to the gradients: every
 // weight / bias gradient entry is produced by exactly one job, so the result does not depend on scheduling -- the
 // training step is bit-reproducible (with red.global.add the order of the 24 partials per entry was not).
+// ordered sum of `n` partials `stride` floats apart: the loads are issued eight at a time (independent), the additions stay in
+// index order, so the result is the same whatever the scheduling
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, size_t stride, int n) {
+  float acc = 0.f;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(i + k) * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k];
+  }
+  for (; i < n; ++i) acc += __ldg(p + (size_t)i * stride);
+  return acc;
+}
+
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __restrict__ part_b, const float* __restrict__ part_s, int num_tiles,
                     int splits, NerfppNetGrads grads) {
@@ -283,32 +299,23 @@ wgrad_reduce_kernel(int bg, const float* __restrict__ part_w, const float* __res
   const int n_b = jb.bias ? rows : 0;
   const int n_h = !part_s ? 0 : jb.head == 1 ? W + 1 : jb.head == 2 ? 3 * RGB_HID + 3 : 0;      // head weights, then its bias(es)
   const int n_w = rows * jb.ncols, n_all = n_w + n_b + n_h;
+  // splits with an empty sample range wrote nothing: they are the trailing ones only when splits > num_tiles, which the
+  // launcher excludes (splits <= num_tiles), so every split has at least one tile
   float* dW = grads.w[jb.w_index];
   float* db = grads.b[jb.a_layer < 8 ? jb.a_layer : jb.a_layer == 8 ? L_REMAP : L_RGB0];
+  const size_t cta0 = (size_t)j * splits;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += gridDim.x * blockDim.x) {
-    float acc = 0.f;
     if (i < n_w) {
       const int orow = i / jb.ncols, col = i - orow * jb.ncols;
-      for (int sp = 0; sp < splits; ++sp) {
-        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
-        if (t_end > t_begin) acc += part_w[((size_t)(j * splits + sp) * 256 + orow) * 256 + col + jb.skip];
-      }
-      dW[(size_t)orow * jb.ld + jb.col0 + col] += acc;
+      dW[(size_t)orow * jb.ld + jb.col0 + col] += ordered_sum(part_w + (cta0 * 256 + orow) * 256 + col + jb.skip, (size_t)256 * 256, splits);
     } else if (i < n_w + n_b) {
       const int f = i - n_w;
-      for (int sp = 0; sp < splits; ++sp) {
-        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
-        if (t_end > t_begin) acc += part_b[(size_t)(j * splits + sp) * 256 + f];
-      }
-      db[f] += acc;
+      db[f] += ordered_sum(part_b + cta0 * 256 + f, 256, splits);
     } else {
       const int f = i - n_w - n_b;
       const int nw = jb.head == 1 ? W : 3 * RGB_HID;
       const int src = f < nw ? f : (jb.head == 1 ? 256 : 384) + (f - nw);
-      for (int sp = 0; sp < splits; ++sp) {
-        const int t_begin = (int)((long long)num_tiles * sp / splits), t_end = (int)((long long)num_tiles * (sp + 1) / splits);
-        if (t_end > t_begin) acc += part_s[(size_t)(j * splits + sp) * HEAD_PART + src];
-      }
+      const float acc = ordered_sum(part_s + cta0 * HEAD_PART + src, HEAD_PART, splits);
       const int l = jb.head == 1 ? L_SIGMA : L_RGB2;
       if (f < nw) grads.w[l][f] += acc; else grads.b[l][f - nw] += acc;
     }
@@ -412,8 +419,7 @@ heads_reduce_kernel(const float* __restrict__ part_h, int n_ctas, NerfppNetGrads
   const int what = blockIdx.x, i = threadIdx.x;
   const int n_w = what == 0 ? W : 3 * RGB_HID, n_b = what == 0 ? 1 : 3;
   if (i >= n_w && !(i >= 384 && i < 384 + n_b)) return;
-  float a = 0.f;
-  for (int x = 0; x < n_ctas; ++x) a += part_h[((size_t)x * 2 + what) * HEADS_PART + i];
+  const float a = ordered_sum(part_h + (size_t)what * HEADS_PART + i, (size_t)2 * HEADS_PART, n_ctas);
   if (i < n_w) grads.w[what == 0 ? L_SIGMA : L_RGB2][i] += a;
   else grads.b[what == 0 ? L_SIGMA : L_RGB2][i - 384] += a;
 }
@@ -470,7 +476,7 @@ int npp_field_wgrad(bool bg, const void* act, const void* etiles, const void* dz
                                                                                (const uint8_t*)dz, scale, num_tiles, splits, *grads, part_w, part_b,
                                                                                g_heads_folded ? part_s : nullptr, d_raw_sigma, d_raw_rgb, total);
   NPP_CHECK_LAUNCH();
-  tcw::wgrad_reduce_kernel<<<dim3(64, njobs), 256, 0, st>>>(bg ? 1 : 0, part_w, part_b, g_heads_folded ? part_s : nullptr, num_tiles, splits, *grads);
+  tcw::wgrad_reduce_kernel<<<dim3(128, njobs), 256, 0, st>>>(bg ? 1 : 0, part_w, part_b, g_heads_folded ? part_s : nullptr, num_tiles, splits, *grads);
   NPP_CHECK_LAUNCH();
   if (!g_heads_folded) return npp_field_wgrad_heads(act, d_raw_sigma, d_raw_rgb, scale, total, grads, part_s + ctas_max * tcw::HEAD_PART, st);
   return 0;
