@@ -279,6 +279,8 @@ class PackedNet:
 
     def get(self, tensors, impl):
         """tensors: 24 parameter tensors in LAYER_NAMES order (weight, bias interleaved per layer)."""
+        for t in tensors:
+            _chk(t, "parameter")                 # CPU parameters: NerfppError (there is no CPU path), before any CUDA query
         key = tuple((t.data_ptr(), t._version) for t in tensors)
         dev = tensors[0].device
         slot = (impl, str(dev))
