@@ -526,7 +526,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       tc_fence_after();
       const long long hg = (long long)tile * TILE + hrow;
       float* const dst = hg < total ? out_rgb + 3 * hg : nullptr;
-      if (TRAIN) rgb_head<true>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0), dst);
+      if (TRAIN && !(flags & 4096)) rgb_head<true>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, save.act + act_chunk_off(9, (size_t)num_tiles, (size_t)tile, 0), dst);   // (4096: timing experiment, layer-9 activations not saved)
       else rgb_head<false>(rgb0_addr, bar(B_RGBFREE), lane, hrow, tail_s, nullptr, dst);
     };
     for (int grp = group0; grp < n_groups; grp += group_step, ++tile_i) {

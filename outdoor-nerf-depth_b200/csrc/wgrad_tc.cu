@@ -448,7 +448,7 @@ int npp_field_wgrad_heads(const void* act, const float* d_raw_sigma, const float
 
 // The two small heads (sigma, rgb.2) can ride along in wgrad_tc_kernel's base_remap / view-direction jobs (Job::head: no
 // second pass over ACT[7] / ACT[9], 1.7 GB per step) -- built, correct, and measured 0.2 ms per step SLOWER than their own
-// HBM-bound kernel (10.41 vs 10.21 ms, same box, gpurun_out/exp18.log): the CUDA-core sums make those two jobs' CTAs the
+// HBM-bound kernel (10.41 vs 10.21 ms, same box, profiles/r2_experiments/exp18.log): the CUDA-core sums make those two jobs' CTAs the
 // long pole of the launch.  Off by default; tests may switch it on.
 static int g_heads_folded = 0;
 extern "C" void nerfpp_debug_set_heads_folded(int on) { g_heads_folded = on ? 1 : 0; }
