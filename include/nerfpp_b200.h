@@ -303,6 +303,49 @@ int mip360_max_dilate(const float* t, const float* w, int n_rays, int n_bins, fl
                       float domain_max, int weights_mode, int renormalize, float eps, float* out_t, float* out_w,
                       void* stream);
 
+/* ---- config 3 (BASELINE.json configs[2]): the mipnerf360 field -- Model.__call__'s per-level body, models.py:200-231 ---- */
+/* One level's  s_to_t -> render.cast_rays -> MLP  (models.py:204-231): coord.construct_ray_warps with
+ * raydist_fn = reciprocal (coord.py:63-99), conical frusta as full-covariance Gaussians (render.py:21-85, ray_shape
+ * 'cone', diag=False), then MLP.__call__ (models.py:398-611) as configs/360.gin sets it up: warp_fn = coord.contract
+ * carried through coord.track_linearize (coord.py:22-60), lift_and_diagonalize on the 21-vector icosahedron basis
+ * (geopoly.generate_basis('icosahedron', 2)), integrated_pos_enc degrees 0..11 (504 features, coord.py:107-126),
+ * net_depth x net_width Dense + ReLU with the encoding concatenated back after layer 4, density = softplus(raw - 1);
+ * and, when has_rgb (NerfMLP), bottleneck 256 | pos_enc(viewdirs, 0, 4) -> Dense 128 + ReLU -> Dense 3 -> sigmoid with
+ * rgb_padding 0.001.  (net_depth, net_width) = (4, 256) PropMLP / (8, 1024) NerfMLP; disable_density_normals = True.
+ *
+ * Parameters arrive as flax holds them -- Dense_i kernels [in, out] row-major + biases, in construction order:
+ * Dense_0..Dense_{depth-1} trunk, Dense_depth density head, then (has_rgb) bottleneck, view layer, rgb head -- and are
+ * packed once into fp16 [out, in_padded] operand images (prec = 1: hi + lo halves, three MMA passes per layer). */
+typedef struct Mip360MlpParams {
+  const float* kernel[12];
+  const float* bias[12];
+} Mip360MlpParams;
+int64_t mip360_mlp_packed_bytes(int net_depth, int net_width, int has_rgb, int prec);
+int mip360_mlp_pack(const Mip360MlpParams* params, int net_depth, int net_width, int has_rgb, int prec, void* packed,
+                    void* stream);
+int64_t mip360_field_workspace_bytes(int64_t n_samples, int net_depth, int net_width, int has_rgb, int prec);
+/* sdist [n, S+1] normalised fenceposts, near / far / radii [n], origins / directions / viewdirs [n,3] ->
+ * out_tdist [n, S+1] (metric fenceposts), out_density [n, S], out_rgb [n, S, 3] (NULL unless has_rgb).  workspace:
+ * mip360_field_workspace_bytes(n*S, ...) bytes, 256-byte aligned. */
+int mip360_field_forward(const void* packed, int net_depth, int net_width, int has_rgb, int prec, const float* sdist,
+                         const float* near, const float* far, const float* origins, const float* directions,
+                         const float* viewdirs, const float* radii, int n_rays, int n_samples, float* out_tdist,
+                         float* out_density, float* out_rgb, void* workspace, void* stream);
+/* The first stage alone (tests): out_enc [n*S, 512] fp16 = the 504 integrated-positional-encoding features of every
+ * sample (+ 8 zero columns), out_means [n*S,3] / out_covs [n*S,9] = the contracted Gaussians (NULL = skip). */
+int mip360_cast_encode(const float* sdist, const float* near, const float* far, const float* origins,
+                       const float* directions, const float* viewdirs, const float* radii, int n_rays, int n_samples,
+                       float* out_tdist, void* out_enc, void* out_enc_lo, void* out_dir, void* out_dir_lo,
+                       float* out_means, float* out_covs, void* stream);
+/* One Dense layer on the tensor cores (tests, microbenchmarks): out[M,N] = act(a[M,K] w[N,K]^T + bias), fp16 operands
+ * and output, fp32 accumulation; K % 8 == 0, N % 128 == 0. */
+int mip360_dense_f16(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int relu,
+                     void* stream);
+/* Model.__call__'s logits for the next resampling (models.py:171-185): where(sdist[1:] > sdist[:-1],
+ * anneal * log(weights + padding), -inf).  sdist [n, M+1], weights [n, M] -> out_logits [n, M]. */
+int mip360_resample_logits(const float* sdist, const float* weights, int n_rays, int n_bins, float anneal,
+                           float resample_padding, float* out_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,10 @@ class RenderOut(Structure):
                                         "bg_rgb", "bg_depth", "bg_lambda", "depth")]
 
 
+class Mip360MlpParams(Structure):
+    _fields_ = [("kernel", c_void_p * 12), ("bias", c_void_p * 12)]
+
+
 class RenderGrads(Structure):
     _fields_ = [(k, c_void_p) for k in ("rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth",
                                         "bg_rgb", "bg_depth", "bg_lambda", "depth")]
@@ -77,6 +81,13 @@ SIGNATURES = {
     "mip360_volumetric_rendering": (c_int, [P, P, P, P, c_int, P, c_int, c_int, P, P, P]),
     "mip360_depth_loss_workspace_bytes": (c_int64, [c_int]),
     "mip360_depth_loss": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
+    "mip360_mlp_packed_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "mip360_mlp_pack": (c_int, [POINTER(Mip360MlpParams), c_int, c_int, c_int, c_int, P, P]),
+    "mip360_field_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
+    "mip360_field_forward": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P]),
+    "mip360_cast_encode": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "mip360_dense_f16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "mip360_resample_logits": (c_int, [P, P, c_int, c_int, c_float, c_float, P, P]),
 }
 OPTIONAL = {}
 _lib = None
