@@ -51,55 +51,61 @@ __device__ __forceinline__ float s_to_t(float s, float s_near, float s_far) {
 
 struct Gauss { float mean[3]; float cov[3][3]; };
 
+// Every operation below is rounded on its own (__f*_rn intrinsics are never contracted into FMAs) and sums run left to
+// right: this is the evaluation order of oracle/mip360_model_oracle.py: lifted_gaussians_ordered, operation for operation.
+// The path is badly conditioned -- feature sin(2^11 x) turns one ulp of a lifted mean into 5e-4, J cov J^T cancels ten
+// digits for distant samples -- so "the same arithmetic" has to mean the same order, not just the same formula.
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
 // render.conical_frustum_to_gaussian (stable form, render.py:42-66) + lift_gaussian (:21-39, diag=False) + origin
 __device__ __forceinline__ Gauss cast_cone(float t0, float t1, const float o[3], const float d[3], float radius) {
   const float eps = FLT_EPSILON;
-  const float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
-  const float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2;
-  const float denom = fmaxf(eps, 3.f * mu2 + hw2);
-  const float t_mean = mu + (2.f * mu * hw2) / denom;
-  const float t_var = hw2 / 3.f - (4.f / 15.f) * hw4 * (12.f * mu2 - hw2) / (denom * denom);
-  float r_var = mu2 / 4.f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 / denom;
-  r_var *= radius * radius;
-  const float dms = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  const float mu = DIV(ADD(t0, t1), 2.f), hw = DIV(SUB(t1, t0), 2.f);
+  const float mu2 = MUL(mu, mu), hw2 = MUL(hw, hw), hw4 = MUL(hw2, hw2);
+  const float denom = fmaxf(eps, ADD(MUL(3.f, mu2), hw2));
+  const float t_mean = ADD(mu, DIV(MUL(MUL(2.f, mu), hw2), denom));
+  const float t_var = SUB(DIV(hw2, 3.f), DIV(MUL(MUL((float)(4.0 / 15.0), hw4), SUB(MUL(12.f, mu2), hw2)), MUL(denom, denom)));
+  float r_var = SUB(ADD(DIV(mu2, 4.f), MUL((float)(5.0 / 12.0), hw2)), DIV(MUL((float)(4.0 / 15.0), hw4), denom));
+  r_var = MUL(r_var, MUL(radius, radius));
+  const float dms = fmaxf(1e-10f, ADD(ADD(MUL(d[0], d[0]), MUL(d[1], d[1])), MUL(d[2], d[2])));
   Gauss g;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    g.mean[i] = d[i] * t_mean + o[i];
+    g.mean[i] = ADD(MUL(d[i], t_mean), o[i]);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float d_outer = d[i] * d[j];
-      const float null_outer = (i == j ? 1.f : 0.f) - d[i] * (d[j] / dms);
-      g.cov[i][j] = t_var * d_outer + r_var * null_outer;
-    }
+    for (int j = 0; j < 3; ++j)
+      g.cov[i][j] = ADD(MUL(t_var, MUL(d[i], d[j])), MUL(r_var, SUB(i == j ? 1.f : 0.f, MUL(d[i], DIV(d[j], dms)))));
   }
   return g;
 }
 
 // coord.track_linearize(coord.contract, mean, cov) (coord.py:22-60): z = contract(x), cov' = J cov J^T with the Jacobian
-// J = scale I + 2 (1 - sqrt(s)) / s^2  x x^T  outside the unit ball (s = |x|^2, scale = (2 sqrt(s) - 1) / s), I inside
+// J = scale I + (k x) x^T outside the unit ball (s = |x|^2, scale = (2 sqrt(s) - 1) / s, k = 2 (1 - sqrt(s)) / s^2), I inside
 __device__ __forceinline__ void contract_linearize(Gauss& g) {
   const float* x = g.mean;
-  const float s = fmaxf(FLT_EPSILON, x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const float s = fmaxf(FLT_EPSILON, ADD(ADD(MUL(x[0], x[0]), MUL(x[1], x[1])), MUL(x[2], x[2])));
   if (s <= 1.f) return;
-  const float rs = sqrtf(s);
-  const float scale = (2.f * rs - 1.f) / s;
-  const float k = 2.f * (1.f - rs) / (s * s);
+  const float rs = __fsqrt_rn(s);
+  const float scale = DIV(SUB(MUL(2.f, rs), 1.f), s);
+  const float k = DIV(MUL(2.f, SUB(1.f, rs)), MUL(s, s));
   float J[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) J[i][j] = (i == j ? scale : 0.f) + k * x[i] * x[j];
+    for (int j = 0; j < 3; ++j) J[i][j] = ADD(i == j ? scale : 0.f, MUL(MUL(k, x[i]), x[j]));
   float t[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) t[i][j] = J[i][0] * g.cov[0][j] + J[i][1] * g.cov[1][j] + J[i][2] * g.cov[2][j];
+    for (int j = 0; j < 3; ++j) t[i][j] = ADD(ADD(MUL(J[i][0], g.cov[0][j]), MUL(J[i][1], g.cov[1][j])), MUL(J[i][2], g.cov[2][j]));
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) g.cov[i][j] = t[i][0] * J[j][0] + t[i][1] * J[j][1] + t[i][2] * J[j][2];
-  const float z0 = scale * x[0], z1 = scale * x[1], z2 = scale * x[2];
+    for (int j = 0; j < 3; ++j) g.cov[i][j] = ADD(ADD(MUL(t[i][0], J[j][0]), MUL(t[i][1], J[j][1])), MUL(t[i][2], J[j][2]));
+  const float z0 = MUL(scale, x[0]), z1 = MUL(scale, x[1]), z2 = MUL(scale, x[2]);
   g.mean[0] = z0; g.mean[1] = z1; g.mean[2] = z2;
 }
 
@@ -145,11 +151,11 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
 #pragma unroll 3
       for (int b = 0; b < NB; ++b) {
         const float b0 = c_basis[b][0], b1 = c_basis[b][1], b2 = c_basis[b][2];
-        lm[tid][b] = g.mean[0] * b0 + g.mean[1] * b1 + g.mean[2] * b2;
-        const float c0 = g.cov[0][0] * b0 + g.cov[0][1] * b1 + g.cov[0][2] * b2;
-        const float c1 = g.cov[1][0] * b0 + g.cov[1][1] * b1 + g.cov[1][2] * b2;
-        const float c2 = g.cov[2][0] * b0 + g.cov[2][1] * b1 + g.cov[2][2] * b2;
-        lv[tid][b] = b0 * c0 + b1 * c1 + b2 * c2;
+        lm[tid][b] = ADD(ADD(MUL(g.mean[0], b0), MUL(g.mean[1], b1)), MUL(g.mean[2], b2));
+        const float c0 = ADD(ADD(MUL(g.cov[0][0], b0), MUL(g.cov[0][1], b1)), MUL(g.cov[0][2], b2));
+        const float c1 = ADD(ADD(MUL(g.cov[1][0], b0), MUL(g.cov[1][1], b1)), MUL(g.cov[1][2], b2));
+        const float c2 = ADD(ADD(MUL(g.cov[2][0], b0), MUL(g.cov[2][1], b1)), MUL(g.cov[2][2], b2));
+        lv[tid][b] = ADD(ADD(MUL(b0, c0), MUL(b1, c1)), MUL(b2, c2));
       }
     }
   } else if (tid < 2 * SPB && dir != nullptr) {
@@ -199,13 +205,13 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
     for (int e = 0; e < 2; ++e) {
       const int p = 2 * t + e, j = p / NB, b = p - j * NB;
       const float sc = (float)(1 << j);
-      const float x = lm[smp][b] * sc;
-      const float hv = -0.5f * (lv[smp][b] * (sc * sc));
+      const float x = MUL(lm[smp][b], sc);
+      const float hv = MUL(-0.5f, MUL(lv[smp][b], sc * sc));
       // exp(hv) < 2^-25 rounds to zero in fp16 (and its low half too): skip the two sines
       if (hv < -17.4f) { sv[e] = 0.f; cv[e] = 0.f; continue; }
       const float ex = expf(hv);
-      sv[e] = ex * safe_sin(x);
-      cv[e] = ex * safe_sin(x + 1.5707964f);
+      sv[e] = MUL(ex, safe_sin(x));
+      cv[e] = MUL(ex, safe_sin(ADD(x, 1.5707964f)));
     }
     const uint32_t hs = pack_hi(sv[0], sv[1]), hc = pack_hi(cv[0], cv[1]);
     uint32_t* row = reinterpret_cast<uint32_t*>(enc + gi * ENC_LD);

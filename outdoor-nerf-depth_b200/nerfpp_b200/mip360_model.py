@@ -1,0 +1,212 @@
+"""Config 3 (BASELINE.json configs[2]): the mipnerf360 model loop -- host mirror of ``Model.__call__`` / ``MLP.__call__``
+(nerf-methods/mipnerf360/internal/models.py:75-330, 398-611) under ``configs/360.gin`` over the C ABI
+(``mip360_field_forward`` and the A16 entry points).  Names follow the reference: ``Model``, ``NerfMLP``, ``PropMLP``,
+``Rays`` (internal/utils.py), per-level ``renderings`` / ``ray_history`` dictionaries with the reference's keys.
+
+The reference is JAX/flax: its parameters are a tree ``params[<module>]['Dense_i']['kernel' | 'bias']`` with kernels
+stored [in, out].  ``MLP.load_flax`` takes exactly that tree (numpy arrays) so that a checkpoint of the reference can be
+dropped in; ``MLP.init`` draws flax's ``he_uniform`` default.  Inference only: the 1024-wide network has a forward here
+(render / evaluate / the proposal resampling cascade), no backward yet.
+
+All arithmetic is in libnerfpp_b200.so; torch owns memory, the stream and the RNG draw of the jitter."""
+import ctypes
+import math
+from collections import namedtuple
+
+import torch
+
+from . import _lib, mip360
+from ._lib import Mip360MlpParams, NerfppError, check
+from .ops import _c, _p, _stream
+
+Rays = namedtuple("Rays", ("origins", "directions", "viewdirs", "radii", "near", "far"))   # internal/utils.py:60-77 (the fields the path reads)
+
+NUM_FEATURES = 504          # 21 basis vectors x 12 degrees x (sin, cos): models.py:350-351, 379-380
+DIR_FEATURES = 27           # pos_enc(viewdirs, 0, 4, append_identity=True)
+BOTTLENECK, VIEW_WIDTH, SKIP = 256, 128, 4
+
+
+def dense_shapes(net_depth, net_width, has_rgb):
+    """(in, out) of Dense_0.. in flax's construction order (models.py:442-466, 508-597)."""
+    shapes, cur = [], NUM_FEATURES
+    for i in range(net_depth):
+        shapes.append((cur, net_width))
+        cur = net_width + (NUM_FEATURES if (i % SKIP == 0 and i > 0) else 0)
+    shapes.append((cur, 1))
+    if has_rgb:
+        shapes += [(cur, BOTTLENECK), (BOTTLENECK + DIR_FEATURES, VIEW_WIDTH), (VIEW_WIDTH, 3)]
+    return shapes
+
+
+class MLP(object):
+    """models.MLP as ``configs/360.gin`` configures it (warp_fn = contract, disable_density_normals = True, IPE degrees
+    0..12, icosahedron basis).  ``disable_rgb`` = PropMLP."""
+
+    def __init__(self, net_depth, net_width, disable_rgb, device, prec=False):
+        self.net_depth, self.net_width, self.disable_rgb = int(net_depth), int(net_width), bool(disable_rgb)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NerfppError("the mipnerf360 field only exists as CUDA kernels (no CPU fallback)")
+        self.prec = bool(prec)
+        self.shapes = dense_shapes(self.net_depth, self.net_width, not self.disable_rgb)
+        self.params = None          # list of (kernel [in,out], bias [out]) CUDA fp32 tensors
+        self._packed = None
+        self._ws = None
+
+    # -- parameters ------------------------------------------------------------------------------------------------
+    def init(self, seed=0):
+        """flax Dense under the config: kernel he_uniform = U(+-sqrt(6 / fan_in)), bias zeros (models.py:353, 428-429)."""
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        ps = []
+        for fan_in, fan_out in self.shapes:
+            lim = math.sqrt(6.0 / fan_in)
+            ps.append(((torch.rand(fan_in, fan_out, generator=g) * 2 - 1) * lim, torch.zeros(fan_out)))
+        return self.load(ps)
+
+    def load(self, params):
+        """params: sequence of (kernel [in, out], bias [out]) in Dense_0.. order (numpy arrays or tensors)."""
+        if len(params) != len(self.shapes):
+            raise ValueError("expected %d Dense layers, got %d" % (len(self.shapes), len(params)))
+        out = []
+        for (k, b), (fi, fo) in zip(params, self.shapes):
+            k = torch.as_tensor(k, dtype=torch.float32).to(self.device).contiguous()
+            b = torch.as_tensor(b, dtype=torch.float32).to(self.device).contiguous()
+            if tuple(k.shape) != (fi, fo) or tuple(b.shape) != (fo,):
+                raise ValueError("Dense kernel %s / bias %s do not match (%d, %d)" % (tuple(k.shape), tuple(b.shape), fi, fo))
+            out.append((k, b))
+        self.params = out
+        self._packed = None
+        return self
+
+    def load_flax(self, tree):
+        """tree: {'Dense_0': {'kernel': [in,out], 'bias': [out]}, ...} -- one module of the reference's checkpoint."""
+        return self.load([(tree["Dense_%d" % i]["kernel"], tree["Dense_%d" % i]["bias"]) for i in range(len(self.shapes))])
+
+    def packed(self):
+        if self.params is None:
+            raise NerfppError("MLP has no parameters: call init() or load()")
+        if self._packed is None:
+            L = _lib.lib()
+            has_rgb = int(not self.disable_rgb)
+            nbytes = L.mip360_mlp_packed_bytes(self.net_depth, self.net_width, has_rgb, int(self.prec))
+            if nbytes < 0:
+                check(-1, "mip360_mlp_packed_bytes")
+            buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+            st = Mip360MlpParams()
+            for i, (k, b) in enumerate(self.params):
+                st.kernel[i], st.bias[i] = k.data_ptr(), b.data_ptr()
+            with torch.cuda.device(self.device):
+                check(L.mip360_mlp_pack(ctypes.byref(st), self.net_depth, self.net_width, has_rgb, int(self.prec), _p(buf), _stream()),
+                      "mip360_mlp_pack")
+            self._packed = buf
+        return self._packed
+
+    def _workspace(self, n_samples):
+        L = _lib.lib()
+        need = int(L.mip360_field_workspace_bytes(int(n_samples), self.net_depth, self.net_width, int(not self.disable_rgb), int(self.prec)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- one level: s_to_t -> cast_rays -> MLP (models.py:203-231) ----------------------------------------------------------
+    def level(self, sdist, rays):
+        """sdist [n, S+1] -> tdist [n, S+1], density [n, S], rgb [n, S, 3] (None for a PropMLP)."""
+        sd = _c(sdist, "sdist", 2)
+        n, S = sd.shape[0], sd.shape[1] - 1
+        o, d, v = (_c(x, nm, 2) for x, nm in ((rays.origins, "origins"), (rays.directions, "directions"), (rays.viewdirs, "viewdirs")))
+        rad, near, far = (_c(x, nm).reshape(-1) for x, nm in ((rays.radii, "radii"), (rays.near, "near"), (rays.far, "far")))
+        if not (o.shape == d.shape == v.shape == (n, 3)) or not (rad.numel() == near.numel() == far.numel() == n):
+            raise ValueError("rays do not match sdist's %d rows" % n)
+        tdist = torch.empty(n, S + 1, device=sd.device, dtype=torch.float32)
+        density = torch.empty(n, S, device=sd.device, dtype=torch.float32)
+        rgb = None if self.disable_rgb else torch.empty(n, S, 3, device=sd.device, dtype=torch.float32)
+        ws = self._workspace(n * S)
+        with torch.cuda.device(sd.device):
+            check(_lib.lib().mip360_field_forward(_p(self.packed()), self.net_depth, self.net_width, int(not self.disable_rgb), int(self.prec),
+                                                  _p(sd), _p(near), _p(far), _p(o), _p(d), _p(v), _p(rad), n, S, _p(tdist), _p(density),
+                                                  _p(rgb), _p(ws), _stream()), "mip360_field_forward")
+        return tdist, density, rgb
+
+
+def NerfMLP(device, net_depth=8, net_width=1024, prec=False):      # configs/360.gin:16-19
+    return MLP(net_depth, net_width, False, device, prec)
+
+
+def PropMLP(device, net_depth=4, net_width=256, prec=False):       # configs/360.gin:10-14
+    return MLP(net_depth, net_width, True, device, prec)
+
+
+def resample_logits(sdist, weights, anneal, resample_padding=0.0):
+    """models.py:171-185: where(sdist[1:] > sdist[:-1], anneal * log(weights + padding), -inf)."""
+    sd, w = _c(sdist, "sdist", 2), _c(weights, "weights", 2)
+    n, M = w.shape
+    if sd.shape != (n, M + 1):
+        raise ValueError("sdist must be [n, M+1] for weights [n, M]")
+    out = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        check(_lib.lib().mip360_resample_logits(_p(sd), _p(w), n, M, float(anneal), float(resample_padding), _p(out), _stream()),
+              "mip360_resample_logits")
+    return out
+
+
+class Model(object):
+    """models.Model (models.py:47-330) with the gin bindings of configs/360.gin: raydist_fn = reciprocal,
+    opaque_background = True, three levels (64, 64 proposal intervals by one shared PropMLP, 32 by the NerfMLP), dilation
+    0.0025 + 0.5 / prod(samples so far), annealing slope 10, single_jitter, bg_intensity_range (1, 1)."""
+
+    num_prop_samples, num_nerf_samples, num_levels = 64, 32, 3
+    anneal_slope, dilation_multiplier, dilation_bias, resample_padding = 10.0, 0.5, 0.0025, 0.0
+    single_jitter, opaque_background, bg_intensity = True, True, 1.0
+
+    def __init__(self, device, nerf_mlp=None, prop_mlp=None, prec=False):
+        self.device = torch.device(device)
+        self.nerf_mlp = nerf_mlp if nerf_mlp is not None else NerfMLP(device, prec=prec)
+        self.prop_mlp = prop_mlp if prop_mlp is not None else PropMLP(device, prec=prec)
+
+    def init(self, seed=0):
+        self.nerf_mlp.init(seed)
+        self.prop_mlp.init(seed + 1)
+        return self
+
+    def load_flax(self, params):
+        """params: the reference checkpoint's ``params`` tree (keys 'NerfMLP_0', 'PropMLP_0')."""
+        self.nerf_mlp.load_flax(params["NerfMLP_0"])
+        self.prop_mlp.load_flax(params["PropMLP_0"])
+        return self
+
+    def __call__(self, rng, rays, train_frac=1.0, compute_extras=True, u_levels=None):
+        """-> (renderings, ray_history), one entry per level.  ``rng``: None (deterministic interval centres) or a
+        torch.Generator for the jitter; ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
+        near, far = _c(rays.near, "near").reshape(-1, 1), _c(rays.far, "far").reshape(-1, 1)
+        n = near.shape[0]
+        sdist = torch.cat([torch.zeros_like(near), torch.ones_like(far)], dim=-1)
+        weights = torch.ones_like(near)
+        prod_num_samples = 1
+        renderings, ray_history = [], []
+        for i_level in range(self.num_levels):
+            is_prop = i_level < self.num_levels - 1
+            num_samples = self.num_prop_samples if is_prop else self.num_nerf_samples
+            dilation = self.dilation_bias + self.dilation_multiplier * 1.0 / prod_num_samples
+            prod_num_samples *= num_samples
+            if i_level > 0:
+                sdist, weights = mip360.max_dilate_weights(sdist, weights, dilation, domain=(0.0, 1.0), renormalize=True)
+                sdist, weights = sdist[..., 1:-1].contiguous(), weights[..., 1:-1].contiguous()
+            s = self.anneal_slope
+            anneal = (s * train_frac) / ((s - 1) * train_frac + 1) if s > 0 else 1.0
+            logits = resample_logits(sdist, weights, anneal, self.resample_padding)
+            if u_levels is not None and u_levels[i_level] is not None:
+                u = u_levels[i_level]
+            elif rng is None:
+                u = None
+            else:
+                u = mip360.jittered_u((n,), num_samples, self.single_jitter, self.device, generator=rng)
+            sdist = mip360.sample_intervals(u, sdist, logits, num_samples, single_jitter=self.single_jitter, domain=(0.0, 1.0))
+            mlp = self.prop_mlp if is_prop else self.nerf_mlp
+            tdist, density, rgb = mlp.level(sdist, rays)
+            weights = mip360.compute_alpha_weights(density, tdist, rays.directions, opaque_background=self.opaque_background)[0]
+            if rgb is None:
+                rgb = torch.zeros(n, num_samples, 3, device=self.device)      # disable_rgb: zeros (models.py:511-512)
+            rendering = mip360.volumetric_rendering(rgb, weights, tdist, self.bg_intensity, far.reshape(-1), compute_extras)
+            renderings.append(rendering)
+            ray_history.append(dict(density=density, rgb=rgb, sdist=sdist, tdist=tdist, weights=weights))
+        return renderings, ray_history
