@@ -34,6 +34,9 @@ CONFIGS = {
     "c2": dict(global_rays=4096, quoted_gpus=1, losses=("mse",), what="NeRF++ configs[1]: KITTI Seq00 sample_every=8, depth_sup_type=gt, depth_loss=mse"),
     "c4": dict(global_rays=8192, quoted_gpus=4, losses=("l1",), what="NeRF++ configs[3]: Argoverse 2c07fcda, depth_sup_type=stereo_crop, depth_loss=l1, 8192 rays tile-sharded over 4 GPUs"),
     "c5": dict(global_rays=16384, quoted_gpus=8, losses=("mse", "l1", "kl"), what="NeRF++ configs[4]: KITTI sweep, {mse,l1,kl}, 16384 rays tile-sharded over 8 GPUs"),
+    # configs[2] is a different network: its own leg, run_c3()
+    "c3": dict(global_rays=4096, quoted_gpus=1, losses=("kl",), what="MipNeRF-360 configs[2]: KITTI Seq06, depth_sup_type=mono_crop, depth_loss=kl, 4096 rays, "
+               "PropMLP 4x256 (64 + 64 intervals) + NerfMLP 8x1024 (32 intervals), contract + IPE"),
 }
 LAMBDA_DEPTH = 0.1          # scripts/train.sh:5
 DEPTH_SIGMA, DEPTH_SCALE = 0.01, 0.05
@@ -670,6 +673,280 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# config 3: mipnerf360 (models.py:75-330 under configs/360.gin) -- forward of the three levels + the trainer's loss terms
+# ---------------------------------------------------------------------------------------------------------------------
+C3_PROP_MACS, C3_NERF_MACS = 325888, 8672000          # per sample (Dense stacks; tests/test_mip360_model_oracle.py)
+C3_SAMPLES = (64, 64, 32)
+C3_FLOPS_PER_RAY = 2.0 * (128 * C3_PROP_MACS + 32 * C3_NERF_MACS)      # 638.4 MFLOP
+
+
+def c3_batch(n, seed):
+    """A seeded 360-style batch (origins around the unit ball, unnormalised directions, pixel-footprint radii, near 0.2,
+    far 1e6 as configs/360.gin; rgb ~ U[0,1]^3, depth prior with every 5th ray invalid)."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * (0.2 + torch.rand(n, 1, generator=g))
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    dirs = d * (0.9 + 0.4 * torch.rand(n, 1, generator=g))
+    sup = 0.5 + 20 * torch.rand(n, 1, generator=g)
+    sup[::5] = 0
+    return dict(origins=o, directions=dirs, viewdirs=dirs / dirs.norm(dim=-1, keepdim=True), radii=5e-4 + 1.5e-3 * torch.rand(n, 1, generator=g),
+                near=torch.full((n, 1), 0.2), far=torch.full((n, 1), 1e6), rgb=torch.rand(n, 3, generator=g), disps_sup=sup)
+
+
+def c3_gemm_roofline(dev, n_rays, prec, reps=10):
+    """The Dense-layer GEMM kernel's launches of one step (gemm_tc_kernel: 2 x 4 PropMLP layers, 8 NerfMLP layers, bottleneck,
+    view layer), each shape timed alone with CUDA events through the C ABI's one-layer entry point."""
+    import ctypes
+    from nerfpp_b200 import _lib
+    burst, sustained, hbm, how = peaks()
+    L = _lib.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shapes = []
+    for S, (depth, width, rgb) in zip(C3_SAMPLES, ((4, 256, 0), (4, 256, 0), (8, 1024, 1))):
+        M = n_rays * S
+        shapes += [(M, width, 512)] + [(M, width, width + (512 if l == 5 else 0)) for l in range(1, depth)]
+        if rgb:
+            shapes += [(M, 256, width), (M, 128, 320)]
+    tot_ms = flops = 0.0
+    cache = {}
+    for M, N, K in shapes:
+        if (M, N, K) not in cache:
+            a = torch.randn(M, K, device=dev).half()
+            w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+            b = torch.zeros(N, device=dev)
+            out = torch.empty(M, N, device=dev, dtype=torch.float16)
+            call = lambda: _lib.check(L.mip360_dense_f16(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, 1, st), "dense")
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            cache[(M, N, K)] = e0.elapsed_time(e1) / reps
+            del a, w, b, out
+        tot_ms += cache[(M, N, K)]
+        flops += 2.0 * M * N * K
+    torch.cuda.empty_cache()
+    passes = 3 if prec else 1
+    achieved = flops / (tot_ms * passes * 1e-3) / 1e12
+    t = ncu_traffic("gemm_tc_kernel")
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+            "traffic": (t or {}).get("bytes_per_launch"), "traffic_source": t, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
+            "launches_per_step": len(shapes), "avg_launch_ms": tot_ms * passes / len(shapes), "algorithmic_flops_per_step": flops,
+            "note": ("K is padded to 64 (504 -> 512, 283 -> 320): padded FLOPs are in neither numerator; the one-pass rate of every shape timed alone"
+                     + ("; split precision issues three MMA passes per layer, which do not add to the numerator" if prec else ""))}
+
+
+def c3_oracle_step(prop, nerf, rays, u_levels, MM, mo):
+    rend, hist = MM.model_forward(prop, nerf, rays, train_frac=0.5, u_levels=u_levels)
+    losses = []
+    for r, h in zip(rend, hist):
+        losses.append(float(((r["rgb"] - rays["rgb"]) ** 2).mean()))
+        losses.append(float(mo.depth_loss_kl(h["weights"], h["tdist"], rays["disps_sup"].reshape(-1), DEPTH_SIGMA * 1.0, rays["directions"])))
+    return rend, hist, losses
+
+
+def c3_cpu_baseline(dev, n=256, reps=2):
+    """The CPU restatement of config 3's step (oracle/mip360_model_oracle.py: numpy fp32, BLAS threads = all host cores) on a
+    bounded sample, and -- same leg, as the checker -- the parity of the CUDA model against it in both precision modes."""
+    import numpy as np
+    import mip360_model_oracle as MM
+    import mip360_oracle as mo
+    from nerfpp_b200.mip360_model import Model, Rays
+    cores = os.cpu_count() or 1
+    b = c3_batch(n, 6)
+    rays = {k: v.numpy() for k, v in b.items()}
+    prop, nerf = MM.init_mlp_params(4, 256, False, seed=21), MM.init_mlp_params(8, 1024, True, seed=22)
+    g = np.random.default_rng(9)
+    u_levels = []
+    for ns in C3_SAMPLES:
+        base, mj = mo.jitter_base_u(ns)
+        u_levels.append((base[None, :] + g.random((n, 1)).astype(np.float32) * mj).astype(np.float32))
+    c3_oracle_step(prop, nerf, {k: v[:16] for k, v in rays.items()}, [u[:16] for u in u_levels], MM, mo)      # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rend_ref, hist_ref, _ = c3_oracle_step(prop, nerf, rays, u_levels, MM, mo)
+    dt = time.perf_counter() - t0
+    base = {"value": reps * n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d x %d rays of the same workload (oracle/mip360_model_oracle.py: numpy fp32 restatement of the JAX reference, which "
+                      "cannot run here -- no jax/flax in the image; BLAS on all host threads), %.1f s" % (reps, n, dt)}
+    parity = {"rays": n, "floors": {"rgb": 1e-2, "depth": 1e-3}, "norm": "per ray |a-b| / max(|b|, floor): max / p99 / p50"}
+    R = Rays(*(b[k].to(dev) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")))
+    for prec in (False, True):
+        model = Model(dev, prec=prec)
+        model.nerf_mlp.load(nerf)
+        model.prop_mlp.load(prop)
+        with torch.no_grad():
+            rend, hist = model(None, R, train_frac=0.5, u_levels=[torch.from_numpy(u).to(dev) for u in u_levels])
+        out = {}
+        for key, floor in (("rgb", 1e-2), ("depth", 1e-3)):
+            a, r = rend[-1][key].cpu().numpy(), rend_ref[-1][key]
+            err = np.abs(a - r)
+            den = np.maximum(np.abs(r), floor)
+            rel = (err / den).max(-1) if err.ndim > 1 else err / den
+            out[key] = [float(rel.max()), float(np.percentile(rel, 99)), float(np.median(rel))]
+        parity["split_precision" if prec else "fp16_operands"] = out
+        del model
+    torch.cuda.empty_cache()
+    return base, parity
+
+
+def run_c3(args):
+    """BASELINE.json configs[2]: one pass = Model.__call__ over 4096 rays per GPU (PropMLP 64 + 64 intervals, NerfMLP 32) +
+    the trainer's loss terms (per-level mse and kl depth prior, interlevel, distortion), forward only -- the 1024-wide network
+    has no backward in this repository yet.  Rays are independent: N ranks run N shards, no collective."""
+    from nerfpp_b200 import _lib, ops
+    from nerfpp_b200.mip360_model import GraphedModelStep, Model
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_rays = args.rays_per_gpu or N_RAYS
+    clk = ClockSampler(local)
+    _lib.lib()
+    prec = bool(args.c3_split)
+    model = Model(dev, prec=prec).init(rank)
+    host = c3_batch(n_rays, seed=rank)
+    dev_step = GraphedModelStep(model, n_rays, train_frac=0.5, depth_sigma=DEPTH_SIGMA, host_io=False)
+    for k, v in dev_step.dev_in.items():
+        v.copy_(host[k].to(dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    barrier()
+    ops.LAUNCHES[0] = 0
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with clk:
+        barrier()
+        t_wall = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            dev_step.launch()
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    launches = args.steps * dev_step.kernels_per_replay
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_rays * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: host batch -> pinned staging -> graph (H2D, kernels, D2H) -> host rgb / depth / losses; two steps in flight on
+    # one stream (step i+1 is staged and enqueued before step i's results are read) ----
+    slots = [GraphedModelStep(model, n_rays, train_frac=0.5, depth_sigma=DEPTH_SIGMA, host_io=True) for _ in range(2)]
+
+    def e2e_run(k):
+        t0 = time.perf_counter()
+        flush.zero_()
+        slots[0].launch(host)
+        for i in range(1, k):
+            flush.zero_()
+            slots[i & 1].launch(host)
+            slots[(i - 1) & 1].fetch()
+        slots[(k - 1) & 1].fetch()
+        return time.perf_counter() - t0
+
+    e2e_run(3)
+    barrier()
+    t_e2e = torch.tensor([e2e_run(args.steps)], device=dev, dtype=torch.float64)
+    barrier()
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n_rays * world * args.steps / float(t_e2e.item())
+    h2d = sum(v.numel() * 4 for v in host.values())
+    d2h = slots[0]._n_out * 4
+    last = slots[(args.steps - 1) & 1].fetch()
+    losses = dict(zip(("mse_0", "mse_1", "mse_2", "depth_0", "depth_1", "depth_2", "interlevel", "distortion"), [float(x) for x in last["losses"]]))
+    del slots
+    roof = c3_gemm_roofline(dev, n_rays, prec)
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, parity = c3_cpu_baseline(dev)
+        except Exception as e:   # noqa: BLE001
+            cpu = {"error": repr(e)[:500]}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (hi + lo fp16 tensor-core operands, three MMA passes, fp32 accumulate)" if prec else "f32 (fp16 tensor-core operands, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": CONFIGS["c3"]["what"] + "; forward of the three levels (resampling, ray warp, cast, contraction, IPE, Dense stacks, "
+                                                           "compositing) + per-level mse / kl depth prior + interlevel + distortion terms; no backward",
+                       "name": "c3", "rays_per_gpu": n_rays, "global_rays": n_rays * world, "depth_losses": ["kl"], "samples_per_level": list(C3_SAMPLES),
+                       "unit_of_work": "%.1f MFLOP per ray = %.3f TFLOP algorithmic per %d rays (Dense stacks only)" % (C3_FLOPS_PER_RAY / 1e6, C3_FLOPS_PER_RAY * n_rays / 1e12, n_rays),
+                       "l2": "flushed between timed steps (256 MiB write)", "field": "tcgen05 GEMM per Dense layer (gemm_tc_kernel)",
+                       "parallelism": ("rays sharded over %d ranks, no collective" % world) if world > 1 else "single GPU",
+                       "wall_s_timed_region": t_wall, "launch": "one CUDA graph per step (%d library kernels + torch rand/cat/fill nodes)" % dev_step.kernels_per_replay},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_in_flight": 2,
+                    "how": "GraphedModelStep(host_io=True): host batch -> pinned staging -> graph (H2D node, kernels, D2H node) -> host rgb / depth / 8 loss "
+                           "terms; step i+1 staged and enqueued before step i is read; wall clock over all steps, L2 flush included"},
+            "gpu_launches": launches, "roofline": roof, "losses_last_step": losses,
+            "algorithmic_tflops_per_s_whole_step": C3_FLOPS_PER_RAY * n_rays / (ms_per_step * 1e-3) / 1e12,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_c3(args):
+    """--impl reference --config c3: the JAX reference cannot run in this image (no jax / flax / gin); the CPU arm is the numpy
+    restatement oracle/mip360_model_oracle.py (kind "port"), a bounded sample of the same workload per step."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    import numpy as np
+    import mip360_model_oracle as MM
+    import mip360_oracle as mo
+    n = 256
+    b = c3_batch(n, 6)
+    rays = {k: v.numpy() for k, v in b.items()}
+    prop, nerf = MM.init_mlp_params(4, 256, False, seed=21), MM.init_mlp_params(8, 1024, True, seed=22)
+    g = np.random.default_rng(9)
+    u_levels = []
+    for ns in C3_SAMPLES:
+        base, mj = mo.jitter_base_u(ns)
+        u_levels.append((base[None, :] + g.random((n, 1)).astype(np.float32) * mj).astype(np.float32))
+    warm, steps = max(1, min(args.warmup, 2)), max(1, min(args.steps, 10))
+    for _ in range(warm):
+        c3_oracle_step(prop, nerf, rays, u_levels, MM, mo)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c3_oracle_step(prop, nerf, rays, u_levels, MM, mo)
+    dt = (time.perf_counter() - t0) / steps
+    v = n / dt
+    cores = os.cpu_count() or 1
+    emit({"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": warm,
+          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": CONFIGS["c3"]["what"], "name": "c3", "rays_per_step": n, "where": "host cores of the GPU box"},
+          "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                           "sample": "%d rays/step (oracle/mip360_model_oracle.py, numpy fp32, BLAS threads = host cores; the JAX reference cannot run here)" % n},
+          "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
 RESULT_OUT = [None]
 
 
@@ -698,7 +975,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host-to-host steps in flight in the e2e leg (PipelinedRenderStep)")
     ap.add_argument("--no-train", action="store_true", help="skip the trainer-step measurement")
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config: c2 = configs[1] (headline), c4 = configs[3], c5 = configs[4]")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2] (mipnerf360), c4 = configs[3], c5 = configs[4]")
+    ap.add_argument("--c3-split", type=int, default=0, help="config c3: 1 = split-precision operands (hi + lo fp16, three MMA passes per layer)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="c2 only: weak = 4096 rays per GPU (default, the driver's curve); strong = 4096 rays in total, sharded over the ranks")
     ap.add_argument("--rays-per-gpu", type=int, default=0, help="override the rays each rank processes")
@@ -706,7 +984,9 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference_c3(args) if args.config == "c3" else run_reference(args)
+    elif args.config == "c3":
+        run_c3(args)
     else:
         run_ours(args)
 

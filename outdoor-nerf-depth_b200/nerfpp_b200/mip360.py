@@ -7,16 +7,22 @@ import math
 import torch
 
 from . import _lib
-from ._lib import DEPTH_KL, DEPTH_L1, DEPTH_MSE, check
-from .ops import _c, _p, _stream
+from ._lib import DEPTH_KL, DEPTH_L1, DEPTH_MSE
+from .ops import _c, _p, _stream, check      # ops.check counts the library's kernel launches
 
 EPS = float(torch.finfo(torch.float32).eps)
 
 
+_CONST = {}       # (kind, num_samples, device) -> device tensor: built once on the host (no H2D copy inside a graph capture)
+
+
 def centers_u(num_samples, device):
     """stepfun.py:193-199 (rng=None, deterministic_center=True), built in float64 then rounded like jnp.linspace."""
-    pad = 1 / (2 * num_samples)
-    return torch.linspace(pad, 1. - pad - EPS, num_samples, dtype=torch.float64).float().to(device)
+    key = ("centers", int(num_samples), str(device))
+    if key not in _CONST:
+        pad = 1 / (2 * num_samples)
+        _CONST[key] = torch.linspace(pad, 1. - pad - EPS, num_samples, dtype=torch.float64).float().to(device)
+    return _CONST[key]
 
 
 def jittered_u(shape_prefix, num_samples, single_jitter, device, generator=None):
@@ -24,7 +30,10 @@ def jittered_u(shape_prefix, num_samples, single_jitter, device, generator=None)
     u_max = EPS + (1 - EPS) / num_samples
     max_jitter = (1 - u_max) / (num_samples - 1) - EPS
     d = 1 if single_jitter else num_samples
-    base = torch.linspace(0, 1 - u_max, num_samples, dtype=torch.float64).float().to(device)
+    key = ("jitter", int(num_samples), str(device))
+    if key not in _CONST:
+        _CONST[key] = torch.linspace(0, 1 - u_max, num_samples, dtype=torch.float64).float().to(device)
+    base = _CONST[key]
     return base + torch.rand(tuple(shape_prefix) + (d,), device=device, generator=generator) * max_jitter
 
 
@@ -82,8 +91,14 @@ def volumetric_rendering(rgbs, weights, tdist, bg_rgbs, t_far, compute_extras=Tr
     n = w.shape[0]
     c = _c(rgbs, "rgbs").reshape(n, S, 3)
     td = _c(tdist, "tdist").reshape(n, S + 1)
-    bg = torch.as_tensor(bg_rgbs, dtype=torch.float32, device=w.device)
-    bg = bg.expand(3).contiguous() if bg.dim() <= 1 else bg.reshape(n, 3).contiguous()
+    if isinstance(bg_rgbs, (int, float)):          # a constant background: built once per value (no H2D copy inside a graph capture)
+        key = ("bg", float(bg_rgbs), str(w.device))
+        if key not in _CONST:
+            _CONST[key] = torch.full((3,), float(bg_rgbs), dtype=torch.float32, device=w.device)
+        bg = _CONST[key]
+    else:
+        bg = torch.as_tensor(bg_rgbs, dtype=torch.float32, device=w.device)
+        bg = bg.expand(3).contiguous() if bg.dim() <= 1 else bg.reshape(n, 3).contiguous()
     tf = _c(t_far, "t_far").reshape(n)
     rgb = torch.empty(n, 3, device=w.device, dtype=torch.float32)
     sc = torch.empty(n, 6, device=w.device, dtype=torch.float32)

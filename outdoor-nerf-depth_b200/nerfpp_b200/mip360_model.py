@@ -16,8 +16,9 @@ from collections import namedtuple
 import torch
 
 from . import _lib, mip360
-from ._lib import Mip360MlpParams, NerfppError, check
-from .ops import _c, _p, _stream
+from . import ops
+from ._lib import Mip360MlpParams, NerfppError
+from .ops import _c, _p, _stream, check      # ops.check counts the library's kernel launches
 
 Rays = namedtuple("Rays", ("origins", "directions", "viewdirs", "radii", "near", "far"))   # internal/utils.py:60-77 (the fields the path reads)
 
@@ -125,6 +126,8 @@ class MLP(object):
             check(_lib.lib().mip360_field_forward(_p(self.packed()), self.net_depth, self.net_width, int(not self.disable_rgb), int(self.prec),
                                                   _p(sd), _p(near), _p(far), _p(o), _p(d), _p(v), _p(rad), n, S, _p(tdist), _p(density),
                                                   _p(rgb), _p(ws), _stream()), "mip360_field_forward")
+        # encode + one GEMM per Dense layer + density head (+ bottleneck, view layer, rgb head); check() counted one
+        ops.LAUNCHES[0] += self.net_depth + 1 + (0 if self.disable_rgb else 3)
         return tdist, density, rgb
 
 
@@ -176,7 +179,7 @@ class Model(object):
 
     def __call__(self, rng, rays, train_frac=1.0, compute_extras=True, u_levels=None):
         """-> (renderings, ray_history), one entry per level.  ``rng``: None (deterministic interval centres) or a
-        torch.Generator for the jitter; ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
+        torch.Generator / True (torch's default CUDA generator) for the jitter; ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
         near, far = _c(rays.near, "near").reshape(-1, 1), _c(rays.far, "far").reshape(-1, 1)
         n = near.shape[0]
         sdist = torch.cat([torch.zeros_like(near), torch.ones_like(far)], dim=-1)
@@ -199,7 +202,8 @@ class Model(object):
             elif rng is None:
                 u = None
             else:
-                u = mip360.jittered_u((n,), num_samples, self.single_jitter, self.device, generator=rng)
+                u = mip360.jittered_u((n,), num_samples, self.single_jitter, self.device,
+                                      generator=rng if isinstance(rng, torch.Generator) else None)      # True: torch's default CUDA generator
             sdist = mip360.sample_intervals(u, sdist, logits, num_samples, single_jitter=self.single_jitter, domain=(0.0, 1.0))
             mlp = self.prop_mlp if is_prop else self.nerf_mlp
             tdist, density, rgb = mlp.level(sdist, rays)
@@ -210,3 +214,104 @@ class Model(object):
             renderings.append(rendering)
             ray_history.append(dict(density=density, rgb=rgb, sdist=sdist, tdist=tdist, weights=weights))
         return renderings, ray_history
+
+
+IN_KEYS = (("origins", 3), ("directions", 3), ("viewdirs", 3), ("radii", 1), ("near", 1), ("far", 1), ("rgb", 3), ("disps_sup", 1))
+LOSS_KEYS = ("mse_0", "mse_1", "mse_2", "depth_0", "depth_1", "depth_2", "interlevel", "distortion")
+
+
+class GraphedModelStep(object):
+    """One evaluation of the mipnerf360 trainer's forward (train_utils.py:284-336: ``model.apply`` -> compute_data_loss with
+    the depth prior -> interlevel_loss -> distortion_loss) captured ONCE into a CUDA graph: ~45 library kernels, torch's
+    rand / cat nodes, and with ``host_io`` one H2D memcpy node in front (the batch: 16 floats per ray from a pinned staging
+    buffer) and one D2H node behind (rgb | depth | the eight loss terms).  ``step(batch)`` -> dict(rgb [n,3], depth [n],
+    losses [8] in LOSS_KEYS order); host tensors (views of a pinned buffer) when host_io, else device tensors."""
+
+    def __init__(self, model, n_rays, train_frac=1.0, jitter=True, depth_loss_type="kl", depth_sigma=0.01, depth_scale=1.0,
+                 host_io=True, warmup=2):
+        self.model, self.n, self.host_io = model, int(n_rays), bool(host_io)
+        dev, n = model.device, self.n
+        total = sum(w for _, w in IN_KEYS) * n
+        self._in_dev = torch.zeros(total, device=dev)
+        self._in_host = torch.zeros(total).pin_memory() if host_io else None
+
+        def views(flat):
+            out, off = {}, 0
+            for k, w in IN_KEYS:
+                out[k] = flat[off:off + n * w].view(n, w)
+                off += n * w
+            return out
+        self.dev_in = views(self._in_dev)
+        self.host_in = views(self._in_host) if host_io else None
+        self.dev_in["directions"][:, 2] = 1.0          # a valid batch for the warm-up passes
+        self.dev_in["viewdirs"][:, 2] = 1.0
+        self.dev_in["radii"].fill_(1e-3)
+        self.dev_in["near"].fill_(0.2)
+        self.dev_in["far"].fill_(1e6)
+        if host_io:
+            self._in_host.copy_(self._in_dev)
+        self._n_out = 4 * n + len(LOSS_KEYS)
+        self._out_host = torch.zeros(self._n_out).pin_memory() if host_io else None
+        sigma = float(depth_sigma) * float(depth_scale)                      # train_utils.py:125
+
+        def body():
+            if host_io:
+                self._in_dev.copy_(self._in_host, non_blocking=True)
+            d = self.dev_in
+            rays = Rays(d["origins"], d["directions"], d["viewdirs"], d["radii"], d["near"], d["far"])
+            renderings, history = model(True if jitter else None, rays, train_frac=train_frac, compute_extras=True)
+            mses, dls = [], []
+            for r, h in zip(renderings, history):
+                mses.append(ops.fused_loss(r["rgb"], d["rgb"], depth_loss_type=None)[0:1])          # lossmult = 1: mean squared residual
+                if depth_loss_type == "kl":
+                    dls.append(mip360.depth_loss(h["weights"], h["tdist"], d["disps_sup"].reshape(-1), r["distance_mean"], sigma,
+                                                 d["directions"], "kl").reshape(1))
+                else:
+                    dls.append(mip360.depth_point_loss(r["distance_mean"], d["disps_sup"].reshape(-1), depth_loss_type).reshape(1))
+            inter = mip360.interlevel_loss(history).reshape(1)
+            dist = mip360.distortion_loss(history).reshape(1)
+            packed = torch.cat([renderings[-1]["rgb"].reshape(-1), renderings[-1]["depth"].reshape(-1)] + mses + dls + [inter, dist])
+            if host_io:
+                self._out_host.copy_(packed, non_blocking=True)
+            return packed
+
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up off the capture: library init, weight packing, allocator
+                for _ in range(max(int(warmup), 1)):
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES[0]
+            with torch.cuda.graph(self.graph):
+                self._packed = body()
+            self.kernels_per_replay = ops.LAUNCHES[0] - before
+        self._done = torch.cuda.Event() if host_io else None
+
+    def _split(self, flat):
+        n = self.n
+        return dict(rgb=flat[:3 * n].view(n, 3), depth=flat[3 * n:4 * n], losses=flat[4 * n:4 * n + len(LOSS_KEYS)])
+
+    def launch(self, batch=None):
+        if batch is not None:
+            dst = self.host_in if self.host_io else self.dev_in
+            for k in dst:
+                if batch[k] is not dst[k]:
+                    dst[k].copy_(batch[k].reshape(dst[k].shape), non_blocking=True)
+        self.model.nerf_mlp.packed()
+        self.model.prop_mlp.packed()
+        self.graph.replay()
+        if self.host_io:
+            self._done.record()
+
+    def fetch(self):
+        if not self.host_io:
+            return self._split(self._packed)
+        self._done.synchronize()
+        return self._split(self._out_host)
+
+    def __call__(self, batch=None):
+        self.launch(batch)
+        return self.fetch()

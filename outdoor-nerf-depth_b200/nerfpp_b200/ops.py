@@ -20,7 +20,7 @@ RET_KEYS = ("rgb", "fg_weights", "bg_weights", "fg_dists", "fg_rgb", "fg_depth",
             "bg_lambda", "depth")
 LAUNCHES = [0]   # kernels of libnerfpp_b200.so launched through this module (bench.py reads it)
 _KERNELS_PER_CALL = {"backward": 16, "intersect_sphere": 1, "coarse_depths": 1, "perturb_samples": 1, "sample_pdf": 1, "sample_cdf": 1,
-                     "resample_merge": 1, "pack_weights": 1, "field_forward": 1, "forward": 3, "loss": 2}
+                     "resample_merge": 1, "pack_weights": 1, "field_forward": 1, "forward": 3, "loss": 2, "mip360_depth_loss": 2}
 
 
 def check(rc, what):   # noqa: F811  (wraps _lib.check to count launches)
