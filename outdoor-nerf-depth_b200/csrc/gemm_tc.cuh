@@ -24,7 +24,7 @@ struct Segment { int a_map, a_col, w_map, w_col, n_chunks; };
 struct GemmArgs {
   CUtensorMap a[4];                // A sources: dims {K_cols, M}, box {64, 128}
   CUtensorMap w[2];                // weights [N, K_pad] fp16 (hi, lo): box {64, BN}
-  CUtensorMap out[2];              // outputs [M, N] fp16 (hi, lo): box {64, 128}
+  CUtensorMap out[2];              // outputs [M, N] fp16 (hi, lo): box {64, 32} (one epilogue warp's rows)
   Segment seg[MAX_SEG];
   int n_seg;
   int M, N;
@@ -32,19 +32,29 @@ struct GemmArgs {
   const float* bias;               // [N] fp32, added in the epilogue
 };
 
-template <int BN, bool PREC> struct Cfg {
-  static constexpr int STAGES = PREC ? 3 : 4;
+// CTAS = 2: a CTA pair (cluster of two SMs of one TPC, tcgen05 cta_group::2) computes a 256 x BN tile -- each CTA stages its
+// own 128 rows of A and HALF of the weight tile, the leader issues M = 256 MMAs that read both halves, each CTA's TMEM
+// receives its 128 rows of the result.  Per SM that halves the weight stream (the L2 -> shared-memory traffic that bounds
+// the one-CTA form at 96 B/clk) and leaves room for six pipeline stages.
+template <int BN, bool PREC, int CTAS> struct Cfg {
+  static constexpr int B_ROWS = BN / CTAS;                    // weight rows each CTA loads per stage
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BUFS = PREC ? 4 : 2;
-  static constexpr int OUT_BYTES = BM * 64 * 2;
+  static constexpr int OUT_WARP_BYTES = (PREC ? 2 : 1) * 4096;   // per epilogue warp: [32 rows x 64 cols] fp16 (hi [, lo])
+  static constexpr int OUT_BYTES = 8 * OUT_WARP_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - OUT_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_OUT + OUT_BUFS * OUT_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;     // + alignment slack
+  static constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;     // + alignment slack
 };
 
-int launch_gemm(const GemmArgs& g, int bn, bool prec, cudaStream_t st);
+constexpr int OUT_BOX_ROWS = 32;
+void plan(int N, int K, int* bn, int* ctas);      // tile plan for an output width: column-block width, CTAs per tile (the W map's box has bn / ctas rows)
+int launch_gemm(const GemmArgs& g, int bn, int ctas, bool prec, cudaStream_t st);
+void set_pair_mode(int mode);      // debug / A-B: 0 = one-CTA tiles only, 1 = CTA pairs where the shape allows (default)
 // row-major fp16 matrix [outer, inner_valid] with a row pitch of `pitch_elems`; box = {64, box_outer}
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_outer);
 

@@ -32,12 +32,17 @@ __constant__ float c_basis[NB][3] = {
     {0.5f, (float)M360_P, (float)M360_Q},      {0.5f, (float)-M360_P, (float)M360_Q},   {0.f, 0.f, 1.f},
     {-0.5f, (float)M360_P, (float)M360_Q},     {(float)-M360_Q, 0.5f, (float)M360_P},   {(float)-M360_Q, 0.5f, (float)-M360_P}};
 
-// math.safe_sin (math.py:27-40): sin(where(|x| < 100 pi, x, x % (100 pi))), jnp's `%` being the floor modulus
+// math.safe_sin (math.py:27-40): sin(where(|x| < 100 pi, x, x % (100 pi))), jnp's `%` being the floor modulus.
+// The modulus is exact, as fmod is, but costs eight instructions instead of fmodf's loop: q = floor(x / T) from an IEEE
+// division can only be one too LARGE (rounding to nearest never crosses an integer downwards), so r = x - q T lies in
+// (-T, T); x and q T are multiples of ulp(T) = 2^-15 and |r| < 512, hence r is representable and the FMA returns it exactly,
+// and so is the correction r + T.
 __device__ __forceinline__ float safe_sin(float x) {
   const float T = 314.15927f;      // float32(100 * pi)
   if (!(fabsf(x) < T)) {
-    float r = fmodf(x, T);
-    if (r != 0.f && r < 0.f) r += T;
+    const float q = floorf(__fdiv_rn(x, T));
+    float r = __fmaf_rn(-q, T, x);
+    if (r < 0.f) r = __fadd_rn(r, T);
     x = r;
   }
   return sinf(x);
@@ -195,18 +200,29 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
   if (enc == nullptr) return;
   // coord.integrated_pos_enc (coord.py:107-126): feature j*21+b = exp(-0.5 var 4^j) safe_sin(mean 2^j), the second half the
   // same with the argument shifted by float32(pi/2)
+  // Thread t of a 128-thread half owns the two adjacent (degree, basis) pairs 2t and 2t+1 for every sample it visits
+  // (126 of 128 lanes active): the degree -- hence the slow modulus path of safe_sin -- is uniform over most of a warp,
+  // nothing is divided inside the loop, and a warp writes 128 contiguous bytes of a row per store.
   constexpr int ITEMS = NPAIR / 2;        // 126 items of two adjacent pairs per sample
-  for (int w = tid; w < SPB * ITEMS; w += 256) {
-    const int smp = w / ITEMS, t = w - smp * ITEMS;
+  const int t = tid & 127;
+  if (t >= ITEMS) return;
+  int jb[2];
+  float sc[2], sc2[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int p = 2 * t + e, j = p / NB;
+    jb[e] = p - j * NB;
+    sc[e] = (float)(1 << j);
+    sc2[e] = sc[e] * sc[e];
+  }
+  for (int smp = tid >> 7; smp < SPB; smp += 2) {
     const long long gi = g0 + smp;
     if (gi >= M) break;
     float sv[2], cv[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int p = 2 * t + e, j = p / NB, b = p - j * NB;
-      const float sc = (float)(1 << j);
-      const float x = MUL(lm[smp][b], sc);
-      const float hv = MUL(-0.5f, MUL(lv[smp][b], sc * sc));
+      const float x = MUL(lm[smp][jb[e]], sc[e]);
+      const float hv = MUL(-0.5f, MUL(lv[smp][jb[e]], sc2[e]));
       // exp(hv) < 2^-25 rounds to zero in fp16 (and its low half too): skip the two sines
       if (hv < -17.4f) { sv[e] = 0.f; cv[e] = 0.f; continue; }
       const float ex = expf(hv);
@@ -392,7 +408,8 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
                  cudaStream_t st) {
   using namespace gemm;
   GemmArgs g{};
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  int bn, ctas;
+  plan(N, k0 + (a1 ? k1 : 0), &bn, &ctas);
   const bool prec = L.prec != 0;
   if (make_map(&g.a[0], a0, (uint64_t)k0, (uint64_t)M, (uint64_t)ld0, BM)) return -1;
   g.a[1] = g.a[0]; g.a[2] = g.a[0]; g.a[3] = g.a[0];
@@ -403,12 +420,12 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
     if (prec && make_map(&g.a[3], a1_lo, (uint64_t)k1, (uint64_t)M, (uint64_t)ld1, BM)) return -1;
   }
   const int kp = L.k_pad[idx];
-  if (make_map(&g.w[0], packed + L.w_hi[idx], (uint64_t)kp, (uint64_t)N, (uint64_t)kp, (uint32_t)bn)) return -1;
+  if (make_map(&g.w[0], packed + L.w_hi[idx], (uint64_t)kp, (uint64_t)N, (uint64_t)kp, (uint32_t)(bn / ctas))) return -1;
   g.w[1] = g.w[0];
-  if (prec && make_map(&g.w[1], packed + L.w_lo[idx], (uint64_t)kp, (uint64_t)N, (uint64_t)kp, (uint32_t)bn)) return -1;
-  if (make_map(&g.out[0], out, (uint64_t)N, (uint64_t)M, (uint64_t)N, BM)) return -1;
+  if (prec && make_map(&g.w[1], packed + L.w_lo[idx], (uint64_t)kp, (uint64_t)N, (uint64_t)kp, (uint32_t)(bn / ctas))) return -1;
+  if (make_map(&g.out[0], out, (uint64_t)N, (uint64_t)M, (uint64_t)N, OUT_BOX_ROWS)) return -1;
   g.out[1] = g.out[0];
-  if (prec && make_map(&g.out[1], out_lo, (uint64_t)N, (uint64_t)M, (uint64_t)N, BM)) return -1;
+  if (prec && make_map(&g.out[1], out_lo, (uint64_t)N, (uint64_t)M, (uint64_t)N, OUT_BOX_ROWS)) return -1;
   const int c0 = (k0 + BK - 1) / BK, c1 = a1 ? (k1 + BK - 1) / BK : 0;
   const int w1 = c0 * BK;     // weight column where the second source starts
   int ns = 0;
@@ -421,7 +438,7 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
   }
   g.n_seg = ns; g.M = (int)M; g.N = N; g.relu = relu;
   g.bias = reinterpret_cast<const float*>(packed + L.bias[idx]);
-  return launch_gemm(g, bn, prec, st);
+  return launch_gemm(g, bn, ctas, prec, st);
 }
 
 }  // namespace m360

@@ -39,12 +39,17 @@ def run(M, N, K, relu, reps=0):
     return err, scale
 
 
-for shape in [(128, 128, 64, 0), (128, 256, 64, 1), (1000, 256, 512, 1), (333, 128, 320, 1), (4096, 1024, 1024, 1), (5000, 1024, 1536, 0)]:
+import ctypes
+for mode in (0, 1):
+  L.mip360_debug_set_pair_mode.argtypes = [ctypes.c_int]
+  L.mip360_debug_set_pair_mode(mode)
+  print("---- pair mode", mode, flush=True)
+  for shape in [(128, 128, 64, 0), (128, 256, 64, 1), (1000, 256, 512, 1), (333, 128, 320, 1), (4096, 1024, 1024, 1), (5000, 1024, 1536, 0)]:
     run(*shape)
-run(131072, 1024, 1024, 1, reps=10)
-run(131072, 1024, 1536, 1, reps=10)
-run(131072, 1024, 512, 1, reps=10)
-run(262144, 256, 256, 1, reps=10)
-run(262144, 256, 512, 1, reps=10)
-run(131072, 256, 1024, 0, reps=10)
-run(131072, 128, 320, 1, reps=10)
+  run(131072, 1024, 1024, 1, reps=10)
+  run(131072, 1024, 1536, 1, reps=10)
+  run(131072, 1024, 512, 1, reps=10)
+  run(262144, 256, 256, 1, reps=10)
+  run(262144, 256, 512, 1, reps=10)
+  run(131072, 256, 1024, 0, reps=10)
+  run(131072, 128, 320, 1, reps=10)
