@@ -37,6 +37,18 @@ __constant__ float c_basis[NB][3] = {
 // division can only be one too LARGE (rounding to nearest never crosses an integer downwards), so r = x - q T lies in
 // (-T, T); x and q T are multiples of ulp(T) = 2^-15 and |r| < 512, hence r is representable and the FMA returns it exactly,
 // and so is the correction r + T.
+// PRECISE (split-precision mode, whose features keep ~1e-7 through their low halves): libm's sinf.  Otherwise (features
+// rounded to fp16, 2.4e-4) a two-FMA Cody-Waite reduction to [-pi/4, pi/4] and the SFU's sin / cos (absolute error
+// 2^-21.4 = 3.6e-7): a third of the instructions.
+__device__ __forceinline__ float sin_sfu(float x) {          // |x| < 316
+  const float kf = rintf(x * 0.636619772367581f);
+  float r = __fmaf_rn(-kf, 1.5707963705062866f, x);          // exact: both are multiples of 2^-23 and |r| < 1
+  r = __fmaf_rn(-kf, -4.371138828673793e-8f, r);
+  const int k = (int)kf;
+  const float v = (k & 1) ? __cosf(r) : __sinf(r);
+  return (k & 2) ? -v : v;
+}
+template <bool PRECISE>
 __device__ __forceinline__ float safe_sin(float x) {
   const float T = 314.15927f;      // float32(100 * pi)
   if (!(fabsf(x) < T)) {
@@ -45,7 +57,7 @@ __device__ __forceinline__ float safe_sin(float x) {
     if (r < 0.f) r = __fadd_rn(r, T);
     x = r;
   }
-  return sinf(x);
+  return PRECISE ? sinf(x) : sin_sfu(x);
 }
 
 // coord.construct_ray_warps(reciprocal, near, far)[1] (coord.py:92-98): s_to_t(s) = 1 / (s / far + (1 - s) / near), every
@@ -126,6 +138,7 @@ __device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
 // One block = SPB consecutive samples.  Phase 1: a thread per sample casts the frustum, contracts it and projects onto
 // the basis (21 lifted means and variances -> shared memory); 64 more threads write the view-direction encoding rows.
 // Phase 2: all threads sweep (sample, feature-pair) items so that a warp writes 128 contiguous bytes of a row.
+template <bool PRECISE>
 __global__ void __launch_bounds__(256) cast_encode_kernel(
     const float* __restrict__ sdist, const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ origins,
     const float* __restrict__ directions, const float* __restrict__ viewdirs, const float* __restrict__ radii, int n, int S,
@@ -225,9 +238,9 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
       const float hv = MUL(-0.5f, MUL(lv[smp][jb[e]], sc2[e]));
       // exp(hv) < 2^-25 rounds to zero in fp16 (and its low half too): skip the two sines
       if (hv < -17.4f) { sv[e] = 0.f; cv[e] = 0.f; continue; }
-      const float ex = expf(hv);
-      sv[e] = MUL(ex, safe_sin(x));
-      cv[e] = MUL(ex, safe_sin(ADD(x, 1.5707964f)));
+      const float ex = PRECISE ? expf(hv) : __expf(hv);
+      sv[e] = MUL(ex, safe_sin<PRECISE>(x));
+      cv[e] = MUL(ex, safe_sin<PRECISE>(ADD(x, 1.5707964f)));
     }
     const uint32_t hs = pack_hi(sv[0], sv[1]), hc = pack_hi(cv[0], cv[1]);
     uint32_t* row = reinterpret_cast<uint32_t*>(enc + gi * ENC_LD);
@@ -446,6 +459,12 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
 
 using namespace npp::m360;
 
+// chain_tc.cu: the PropMLP's four layers + density head in one persistent kernel (activations stay on the SM)
+int npp_prop_chain(const void* enc, const void* const* w, const int* k_pad, const float* const* bias, const float* head, float* density,
+                   long long M, cudaStream_t st);
+static int g_chain = 1;
+extern "C" void mip360_debug_set_chain(int on) { g_chain = on; }      // A/B and tests: 0 = layer-by-layer GEMM launches
+
 extern "C" int64_t mip360_mlp_packed_bytes(int net_depth, int net_width, int has_rgb, int prec) {
   Layout L;
   if (!make_layout(net_depth, net_width, has_rgb, prec, L)) { npp_set_error("mip360_mlp: unsupported network %d x %d", net_depth, net_width); return -1; }
@@ -492,7 +511,9 @@ extern "C" int mip360_cast_encode(const float* sdist, const float* near, const f
   NPP_CHECK_ARG(n_rays > 0 && n_samples > 0, "empty batch");
   NPP_CHECK_ARG(!out_dir || viewdirs, "viewdirs needed for the direction encoding");
   const long long M = (long long)n_rays * n_samples;
-  cast_encode_kernel<<<(unsigned)((M + SPB - 1) / SPB), 256, 0, (cudaStream_t)stream>>>(
+  // the low halves are wanted: the split-precision mode, libm sin / exp; otherwise the SFU forms
+  auto kern = out_enc_lo ? cast_encode_kernel<true> : cast_encode_kernel<false>;
+  kern<<<(unsigned)((M + SPB - 1) / SPB), 256, 0, (cudaStream_t)stream>>>(
       sdist, near, far, origins, directions, viewdirs, radii, n_rays, n_samples, out_tdist, (__half*)out_enc, (__half*)out_enc_lo,
       (__half*)out_dir, (__half*)out_dir_lo, out_means, out_covs);
   NPP_CHECK_LAUNCH();
@@ -518,6 +539,13 @@ extern "C" int mip360_field_forward(const void* packed, int net_depth, int net_w
   int rc = mip360_cast_encode(sdist, near, far, origins, directions, viewdirs, radii, n_rays, n_samples, out_tdist, enc, enc_lo,
                               has_rgb ? ws + W.dir : nullptr, (has_rgb && prec) ? ws + W.dir_lo : nullptr, nullptr, nullptr, stream);
   if (rc) return rc;
+  if (g_chain && net_depth == 4 && net_width == 256 && !has_rgb && !prec) {
+    const void* wp[4];
+    const float* bp[4];
+    int kp[4];
+    for (int l = 0; l < 4; ++l) { wp[l] = pk + L.w_hi[l]; bp[l] = (const float*)(pk + L.bias[l]); kp[l] = L.k_pad[l]; }
+    return npp_prop_chain(enc, wp, kp, bp, (const float*)(pk + L.w_hi[net_depth]), out_density, M, st);
+  }
   auto hbuf = [&](int i) { return ws + W.h[i]; };
   auto hlo = [&](int i) { return prec ? ws + W.h_lo[i] : (uint8_t*)nullptr; };
   const int Wd = net_width;

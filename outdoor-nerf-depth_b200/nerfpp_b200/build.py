@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libnerfpp_b200.so")
-SOURCES = ["capi.cu", "sampling.cu", "composite.cu", "losses.cu", "field_simt.cu", "field_tc.cu", "field_bwd_tc.cu", "wgrad_tc.cu", "bwd_fused.cu", "mip360.cu", "backward.cu", "gemm_tc.cu", "mip360_field.cu"]
+SOURCES = ["capi.cu", "sampling.cu", "composite.cu", "losses.cu", "field_simt.cu", "field_tc.cu", "field_bwd_tc.cu", "wgrad_tc.cu", "bwd_fused.cu", "mip360.cu", "backward.cu", "gemm_tc.cu", "mip360_field.cu", "chain_tc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -156,6 +156,35 @@ def test_field_level_split_precision(depth, width, has_rgb):
         assert np.max(np.abs(c - c_same)) <= 4e-5 and np.max(np.abs(c - c_ref)) <= 4e-5
 
 
+def test_prop_chain_kernel_matches_layerwise_gemms():
+    """The PropMLP as one persistent kernel (activations in shared memory / TMEM, density head on the fp32 accumulators)
+    against the same network run layer by layer through the GEMM kernel: same fp16 operands, so only the last hidden layer's
+    rounding differs (the chain feeds the head from fp32).  Sizes: a single partial tile, an odd tile count, 2.3 waves."""
+    import ctypes as C
+    from nerfpp_b200 import _lib
+    from nerfpp_b200.mip360_model import MLP
+    dev = _dev()
+    L = _lib.lib()
+    L.mip360_debug_set_chain.argtypes = [C.c_int]
+    params = MM.init_mlp_params(4, 256, False, seed=31)
+    for n, S in ((3, 17), (5, 64), (700, 64)):
+        rays = MM.synthetic_rays(n, seed=n)
+        sd = torch.from_numpy(_sdist(n, S, n + 1)).to(dev)
+        R = _rays_t(rays, dev)
+        mlp = MLP(4, 256, True, dev).load(params)
+        try:
+            L.mip360_debug_set_chain(0)
+            _, d_gemm, _ = mlp.level(sd, R)
+            d_gemm = d_gemm.clone()
+        finally:
+            L.mip360_debug_set_chain(1)
+        _, d_chain, _ = mlp.level(sd, R)
+        torch.cuda.synchronize()
+        assert torch.isfinite(d_chain).all()
+        rel = float((d_chain - d_gemm).abs().max() / d_gemm.abs().max())
+        assert rel <= 1e-3, (n, S, rel)
+
+
 def test_ragged_sample_counts():
     """n*S not a multiple of the 128-row tile or of the encoder's 64-sample block: TMA clips the last tile."""
     (d, c), _, (d_same, c_same) = _field_case(4, 256, False, False, n=7, S=9)
