@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
       mbar_wait(bar(B::TFULL + buf), tph);
       tc_fence_after();
+      float hacc = 0.f;
 #pragma unroll 1
       for (int c = hh; c < BN / 64; c += 2) {
         uint32_t v0[32], v1[32];
@@ -201,6 +202,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             float x0 = __uint_as_float(v[4 * i]) + b4.x, x1 = __uint_as_float(v[4 * i + 1]) + b4.y;
             float x2 = __uint_as_float(v[4 * i + 2]) + b4.z, x3 = __uint_as_float(v[4 * i + 3]) + b4.w;
             if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+            if (g.head_w) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.head_w + n0 + c * 64) + half * 8 + i);
+              hacc += x0 * w4.x + x1 * w4.y + x2 * w4.z + x3 * w4.w;
+            }
             const uint32_t p0 = pack_f16x2<false>(__float_as_uint(x0), __float_as_uint(x1));
             const uint32_t p1 = pack_f16x2<false>(__float_as_uint(x2), __float_as_uint(x3));
             pk[half * 16 + 2 * i] = p0; pk[half * 16 + 2 * i + 1] = p1;
@@ -228,6 +233,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           if (PREC) tma_store_2d(&g.out[1], n0 + c * 64, m0 + q * 32, stg_s + 4096);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      }
+      if (g.head_w) {
+        const long long r = (long long)m0 + q * 32 + lane;
+        if (r < g.M) g.head_part[r * (2 * n_blks) + 2 * (n0 / BN) + hh] = hacc;
       }
     }
     if (lane == 0) stage_store_drain();

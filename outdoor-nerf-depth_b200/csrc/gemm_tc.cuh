@@ -30,6 +30,10 @@ struct GemmArgs {
   int M, N;
   int relu;
   const float* bias;               // [N] fp32, added in the epilogue
+  // optional fused head (the density head behind the last trunk layer): head_part[row][2 * (n0 / BN) + hh] = the dot product of
+  // the row's activated fp32 outputs in the warp's column chunks with head_w -- summed in a fixed order by a small kernel
+  const float* head_w;             // [N] fp32 or NULL
+  float* head_part;                // [M][2 * N / BN]
 };
 
 // CTAS = 2: a CTA pair (cluster of two SMs of one TPC, tcgen05 cta_group::2) computes a 256 x BN tile -- each CTA stages its

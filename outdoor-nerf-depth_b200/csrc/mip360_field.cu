@@ -15,7 +15,7 @@ constexpr int ENC_LD = 512;            // row pitch of the encoding (504 + 8 zer
 constexpr int DIR_LD = 64;             // row pitch of the view-direction encoding (27 + zeros)
 constexpr int DIR_DEG = 4;
 constexpr int BOTTLENECK = 256, VIEW_W = 128;
-constexpr int SPB = 64;                // samples per block of the encode kernel
+constexpr int SPB = 128;               // samples per block of the encode kernel
 
 // geopoly.generate_basis('icosahedron', 2) (geopoly.py:80-126), rows in the reference's order (golden table in
 // tests/geopoly_test.py:79-99): a = 1/sqrt(1+phi^2), c = phi a, p = (phi-1)/2, q = phi/2
@@ -37,27 +37,25 @@ __constant__ float c_basis[NB][3] = {
 // division can only be one too LARGE (rounding to nearest never crosses an integer downwards), so r = x - q T lies in
 // (-T, T); x and q T are multiples of ulp(T) = 2^-15 and |r| < 512, hence r is representable and the FMA returns it exactly,
 // and so is the correction r + T.
-// PRECISE (split-precision mode, whose features keep ~1e-7 through their low halves): libm's sinf.  Otherwise (features
-// rounded to fp16, 2.4e-4) a two-FMA Cody-Waite reduction to [-pi/4, pi/4] and the SFU's sin / cos (absolute error
-// 2^-21.4 = 3.6e-7): a third of the instructions.
-__device__ __forceinline__ float sin_sfu(float x) {          // |x| < 316
-  const float kf = rintf(x * 0.636619772367581f);
-  float r = __fmaf_rn(-kf, 1.5707963705062866f, x);          // exact: both are multiples of 2^-23 and |r| < 1
-  r = __fmaf_rn(-kf, -4.371138828673793e-8f, r);
-  const int k = (int)kf;
-  const float v = (k & 1) ? __cosf(r) : __sinf(r);
-  return (k & 2) ? -v : v;
-}
+// PRECISE (split-precision mode, whose features keep ~1e-7 through their low halves): the exact modulus and libm's sinf.
+// Otherwise (features rounded to fp16, half an ulp = 1.2e-4): six instructions -- the modulus with a reciprocal multiply
+// (a quotient off by one shifts the phase by T - 100 pi = 5.9e-6 only, T being 50 periods to that accuracy) and the SFU's
+// sin on the reduced argument (|x| < 2 T: 1 / 2 pi scaling error <= 4e-5 rad, SFU 4e-7).
+__device__ __forceinline__ float sin_sfu(float x) { return __sinf(x); }          // |x| < 8: view directions
 template <bool PRECISE>
 __device__ __forceinline__ float safe_sin(float x) {
   const float T = 314.15927f;      // float32(100 * pi)
-  if (!(fabsf(x) < T)) {
-    const float q = floorf(__fdiv_rn(x, T));
-    float r = __fmaf_rn(-q, T, x);
-    if (r < 0.f) r = __fadd_rn(r, T);
-    x = r;
+  if (PRECISE) {
+    if (!(fabsf(x) < T)) {
+      const float q = floorf(__fdiv_rn(x, T));
+      float r = __fmaf_rn(-q, T, x);
+      if (r < 0.f) r = __fadd_rn(r, T);
+      x = r;
+    }
+    return sinf(x);
   }
-  return PRECISE ? sinf(x) : sin_sfu(x);
+  if (fabsf(x) >= T) x = __fmaf_rn(-floorf(x * 0.0031830987f), T, x);
+  return __sinf(x);
 }
 
 // coord.construct_ray_warps(reciprocal, near, far)[1] (coord.py:92-98): s_to_t(s) = 1 / (s / far + (1 - s) / near), every
@@ -135,16 +133,18 @@ __device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
   return pack_hi(a - __low2float(h), b - __high2float(h));
 }
 
-// One block = SPB consecutive samples.  Phase 1: a thread per sample casts the frustum, contracts it and projects onto
-// the basis (21 lifted means and variances -> shared memory); 64 more threads write the view-direction encoding rows.
-// Phase 2: all threads sweep (sample, feature-pair) items so that a warp writes 128 contiguous bytes of a row.
+// One block = SPB consecutive samples, 256 threads.  Phase 1a: a thread per sample casts the frustum and contracts it
+// (means and covariances -> shared memory); the other half of the block writes the samples' view-direction rows (one
+// evaluation per sample of its ray's 24 sines -- a ray's samples share them, but the rows are what the view layer's TMA
+// loads read).  Phase 1b: all threads project onto the basis (21 lifted means / variances per sample).  Phase 2: all
+// threads sweep (sample, feature-pair) items so that a warp writes 128 contiguous bytes of a row.
 template <bool PRECISE>
 __global__ void __launch_bounds__(256) cast_encode_kernel(
     const float* __restrict__ sdist, const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ origins,
     const float* __restrict__ directions, const float* __restrict__ viewdirs, const float* __restrict__ radii, int n, int S,
     float* __restrict__ out_tdist, __half* __restrict__ enc, __half* __restrict__ enc_lo, __half* __restrict__ dir, __half* __restrict__ dir_lo,
     float* __restrict__ out_means, float* __restrict__ out_covs) {
-  __shared__ float lm[SPB][NB + 1], lv[SPB][NB + 1];
+  __shared__ float lm[SPB][NB + 1], lv[SPB][NB + 1], gs[SPB][13];       // gs: contracted mean (3) + covariance (9)
   const long long M = (long long)n * S;
   const long long g0 = (long long)blockIdx.x * SPB;
   const int tid = (int)threadIdx.x;
@@ -165,18 +165,12 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
       contract_linearize(g);
       if (out_means) { for (int k = 0; k < 3; ++k) out_means[gi * 3 + k] = g.mean[k]; }
       if (out_covs) { for (int k = 0; k < 9; ++k) out_covs[gi * 9 + k] = g.cov[k / 3][k % 3]; }
-      // coord.lift_and_diagonalize (coord.py:129-133): mean @ basis, diag(basis^T cov basis)
-#pragma unroll 3
-      for (int b = 0; b < NB; ++b) {
-        const float b0 = c_basis[b][0], b1 = c_basis[b][1], b2 = c_basis[b][2];
-        lm[tid][b] = ADD(ADD(MUL(g.mean[0], b0), MUL(g.mean[1], b1)), MUL(g.mean[2], b2));
-        const float c0 = ADD(ADD(MUL(g.cov[0][0], b0), MUL(g.cov[0][1], b1)), MUL(g.cov[0][2], b2));
-        const float c1 = ADD(ADD(MUL(g.cov[1][0], b0), MUL(g.cov[1][1], b1)), MUL(g.cov[1][2], b2));
-        const float c2 = ADD(ADD(MUL(g.cov[2][0], b0), MUL(g.cov[2][1], b1)), MUL(g.cov[2][2], b2));
-        lv[tid][b] = ADD(ADD(MUL(b0, c0), MUL(b1, c1)), MUL(b2, c2));
-      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gs[tid][k] = g.mean[k];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gs[tid][3 + k] = g.cov[k / 3][k % 3];
     }
-  } else if (tid < 2 * SPB && dir != nullptr) {
+  } else if (dir != nullptr) {
     // coord.pos_enc(viewdirs, 0, 4, append_identity=True) (coord.py:136-148): [d, sin(d 2^j), sin(d 2^j + pi/2)], 27 wide
     const long long gi = g0 + (tid - SPB);
     if (gi < M) {
@@ -192,8 +186,8 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float x = d[k] * (float)(1 << j);
-          f[3 + j * 3 + k] = sinf(x);
-          f[3 + 3 * DIR_DEG + j * 3 + k] = sinf(x + 1.5707964f);
+          f[3 + j * 3 + k] = PRECISE ? sinf(x) : sin_sfu(x);
+          f[3 + 3 * DIR_DEG + j * 3 + k] = PRECISE ? sinf(x + 1.5707964f) : sin_sfu(x + 1.5707964f);
         }
       uint4* rowp = reinterpret_cast<uint4*>(dir + gi * DIR_LD);
       uint4* rowl = dir_lo ? reinterpret_cast<uint4*>(dir_lo + gi * DIR_LD) : nullptr;
@@ -211,6 +205,20 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
   }
   __syncthreads();
   if (enc == nullptr) return;
+  // coord.lift_and_diagonalize (coord.py:129-133): mean @ basis, diag(basis^T cov basis); item = (sample, basis vector)
+  for (int w = tid; w < SPB * NB; w += 256) {
+    const int smp = w / NB, b = w - smp * NB;
+    if (g0 + smp >= M) break;
+    const float* m = gs[smp];
+    const float* c = gs[smp] + 3;
+    const float b0 = c_basis[b][0], b1 = c_basis[b][1], b2 = c_basis[b][2];
+    lm[smp][b] = ADD(ADD(MUL(m[0], b0), MUL(m[1], b1)), MUL(m[2], b2));
+    const float c0 = ADD(ADD(MUL(c[0], b0), MUL(c[1], b1)), MUL(c[2], b2));
+    const float c1 = ADD(ADD(MUL(c[3], b0), MUL(c[4], b1)), MUL(c[5], b2));
+    const float c2 = ADD(ADD(MUL(c[6], b0), MUL(c[7], b1)), MUL(c[8], b2));
+    lv[smp][b] = ADD(ADD(MUL(b0, c0), MUL(b1, c1)), MUL(b2, c2));
+  }
+  __syncthreads();
   // coord.integrated_pos_enc (coord.py:107-126): feature j*21+b = exp(-0.5 var 4^j) safe_sin(mean 2^j), the second half the
   // same with the argument shifted by float32(pi/2)
   // Thread t of a 128-thread half owns the two adjacent (degree, basis) pairs 2t and 2t+1 for every sample it visits
@@ -285,6 +293,17 @@ __global__ void __launch_bounds__(256) density_head_kernel(const __half* __restr
       out[r] = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));      // jax.nn.softplus = logaddexp(x, 0)
     }
   }
+}
+
+// density from the partial head sums the last trunk layer's GEMM epilogue left (fixed summation order: reproducible)
+__global__ void density_from_partials_kernel(const float* __restrict__ part, long long M, int P, const float* __restrict__ head_bias,
+                                             float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float acc = 0.f;
+  for (int i = 0; i < P; ++i) acc += part[r * P + i];
+  const float x = acc + head_bias[0] - 1.f;
+  out[r] = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
 }
 
 // rgb head (models.py:589-609): sigmoid(h_view . W + b) * (1 + 2 pad) - pad, pad = 0.001.  Eight lanes per row.
@@ -398,7 +417,7 @@ static int dense_in(const Layout& L, int idx) {
   return VIEW_W;
 }
 
-struct Workspace { size_t enc, enc_lo, h[2], h_lo[2], bott, bott_lo, dir, dir_lo, hv, hv_lo, total; };
+struct Workspace { size_t enc, enc_lo, h[2], h_lo[2], bott, bott_lo, dir, dir_lo, hv, hv_lo, hpart, total; };
 static Workspace make_ws(long long M, const Layout& L) {
   Workspace W{};
   size_t off = 0;
@@ -411,6 +430,7 @@ static Workspace make_ws(long long M, const Layout& L) {
     W.dir = take((size_t)M * DIR_LD * 2); W.dir_lo = L.prec ? take((size_t)M * DIR_LD * 2) : 0;
     W.hv = take((size_t)M * VIEW_W * 2); W.hv_lo = L.prec ? take((size_t)M * VIEW_W * 2) : 0;
   }
+  W.hpart = take((size_t)M * 2 * (L.width / 128 > 8 ? L.width / 128 : 8) * 4);
   W.total = off;
   return W;
 }
@@ -418,11 +438,11 @@ static Workspace make_ws(long long M, const Layout& L) {
 // one Dense layer: up to two A sources (a0 with k0 columns, a1 with k1 columns, lo images alongside in prec mode)
 static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t* a0, const uint8_t* a0_lo, int k0, int ld0,
                  const uint8_t* a1, const uint8_t* a1_lo, int k1, int ld1, uint8_t* out, uint8_t* out_lo, long long M, int N, int relu,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* head_w = nullptr, float* head_part = nullptr) {
   using namespace gemm;
   GemmArgs g{};
   int bn, ctas;
-  plan(N, k0 + (a1 ? k1 : 0), &bn, &ctas);
+  plan(N, (k0 + BK - 1) / BK * BK + (a1 ? (k1 + BK - 1) / BK * BK : 0), &bn, &ctas);
   const bool prec = L.prec != 0;
   if (make_map(&g.a[0], a0, (uint64_t)k0, (uint64_t)M, (uint64_t)ld0, BM)) return -1;
   g.a[1] = g.a[0]; g.a[2] = g.a[0]; g.a[3] = g.a[0];
@@ -451,6 +471,7 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
   }
   g.n_seg = ns; g.M = (int)M; g.N = N; g.relu = relu;
   g.bias = reinterpret_cast<const float*>(packed + L.bias[idx]);
+  g.head_w = head_w; g.head_part = head_part;
   return launch_gemm(g, bn, ctas, prec, st);
 }
 
@@ -462,7 +483,8 @@ using namespace npp::m360;
 // chain_tc.cu: the PropMLP's four layers + density head in one persistent kernel (activations stay on the SM)
 int npp_prop_chain(const void* enc, const void* const* w, const int* k_pad, const float* const* bias, const float* head, float* density,
                    long long M, cudaStream_t st);
-static int g_chain = 1;
+static int g_chain = 1, g_fuse_head = 1;
+extern "C" void mip360_debug_set_fused_head(int on) { g_fuse_head = on; }
 extern "C" void mip360_debug_set_chain(int on) { g_chain = on; }      // A/B and tests: 0 = layer-by-layer GEMM launches
 
 extern "C" int64_t mip360_mlp_packed_bytes(int net_depth, int net_width, int has_rgb, int prec) {
@@ -549,19 +571,28 @@ extern "C" int mip360_field_forward(const void* packed, int net_depth, int net_w
   auto hbuf = [&](int i) { return ws + W.h[i]; };
   auto hlo = [&](int i) { return prec ? ws + W.h_lo[i] : (uint8_t*)nullptr; };
   const int Wd = net_width;
+  const float* head_w = (const float*)(pk + L.w_hi[net_depth]);
   rc = dense(L, pk, 0, enc, enc_lo, 2 * NPAIR, ENC_LD, nullptr, nullptr, 0, 0, hbuf(0), hlo(0), M, Wd, 1, st);
   if (rc) return rc;
   int cur = 0;
   for (int l = 1; l < net_depth; ++l) {
     if (l == 5) rc = dense(L, pk, l, hbuf(cur), hlo(cur), Wd, Wd, enc, enc_lo, 2 * NPAIR, ENC_LD, hbuf(cur ^ 1), hlo(cur ^ 1), M, Wd, 1, st);
-    else rc = dense(L, pk, l, hbuf(cur), hlo(cur), Wd, Wd, nullptr, nullptr, 0, 0, hbuf(cur ^ 1), hlo(cur ^ 1), M, Wd, 1, st);
+    else {
+      // the last trunk layer's epilogue also evaluates the density head on its fp32 values (partials per column block)
+      const bool last = g_fuse_head && l == net_depth - 1;
+      rc = dense(L, pk, l, hbuf(cur), hlo(cur), Wd, Wd, nullptr, nullptr, 0, 0, hbuf(cur ^ 1), hlo(cur ^ 1), M, Wd, 1, st,
+                 last ? head_w : nullptr, last ? (float*)(ws + W.hpart) : nullptr);
+    }
     if (rc) return rc;
     cur ^= 1;
   }
-  {
+  if (g_fuse_head && net_depth - 1 != 5) {
+    int bn, ctas;
+    npp::gemm::plan(Wd, Wd, &bn, &ctas);
+    density_from_partials_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((const float*)(ws + W.hpart), M, 2 * (Wd / bn), head_w + Wd, out_density);
+  } else {
     const int blocks = (int)((M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8);
-    density_head_kernel<<<blocks, 256, (Wd + 1) * sizeof(float), st>>>((const __half*)hbuf(cur), (const __half*)hlo(cur), M, Wd,
-                                                                        (const float*)(pk + L.w_hi[net_depth]), out_density);
+    density_head_kernel<<<blocks, 256, (Wd + 1) * sizeof(float), st>>>((const __half*)hbuf(cur), (const __half*)hlo(cur), M, Wd, head_w, out_density);
   }
   if (has_rgb) {
     uint8_t* bott = ws + W.bott;
