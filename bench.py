@@ -696,29 +696,30 @@ def c3_batch(n, seed):
                 near=torch.full((n, 1), 0.2), far=torch.full((n, 1), 1e6), rgb=torch.rand(n, 3, generator=g), disps_sup=sup)
 
 
-def c3_gemm_roofline(dev, n_rays, prec, reps=10):
-    """The Dense-layer GEMM kernel's launches of one step (gemm_tc_kernel: 2 x 4 PropMLP layers, 8 NerfMLP layers, bottleneck,
-    view layer), each shape timed alone with CUDA events through the C ABI's one-layer entry point."""
+def c3_gemm_roofline(dev, n_rays, prec, model, reps=10):
+    """The dominant kernel of the step, gemm_tc_kernel: the NerfMLP's ten Dense-layer launches (8 trunk layers, bottleneck,
+    view layer; M = rays x 32), each shape timed alone with CUDA events through the C ABI's one-layer entry point;
+    achieved = algorithmic FLOPs (true in-features: 504, 1024, 1528, 283 -- padding excluded) / time.  Plus, as context, each
+    level's whole field call (encode + Dense stack + heads) timed the same way."""
     import ctypes
     from nerfpp_b200 import _lib
+    from nerfpp_b200.mip360_model import Rays, dense_shapes
     burst, sustained, hbm, how = peaks()
     L = _lib.lib()
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    shapes = []
-    for S, (depth, width, rgb) in zip(C3_SAMPLES, ((4, 256, 0), (4, 256, 0), (8, 1024, 1))):
-        M = n_rays * S
-        shapes += [(M, width, 512)] + [(M, width, width + (512 if l == 5 else 0)) for l in range(1, depth)]
-        if rgb:
-            shapes += [(M, 256, width), (M, 128, 320)]
+    M = n_rays * C3_SAMPLES[2]
+    true_shapes = dense_shapes(8, 1024, True)
+    gemm_layers = [true_shapes[i] for i in range(8)] + [true_shapes[9], true_shapes[10]]       # (in, out); the 1-wide heads are not GEMMs
     tot_ms = flops = 0.0
     cache = {}
-    for M, N, K in shapes:
-        if (M, N, K) not in cache:
+    for fin, fout in gemm_layers:
+        K = (fin + 63) // 64 * 64 if fin != 1528 else 1536
+        if (fout, K) not in cache:
             a = torch.randn(M, K, device=dev).half()
-            w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
-            b = torch.zeros(N, device=dev)
-            out = torch.empty(M, N, device=dev, dtype=torch.float16)
-            call = lambda: _lib.check(L.mip360_dense_f16(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, 1, st), "dense")
+            w = (torch.randn(fout, K, device=dev) / K ** 0.5).half()
+            b = torch.zeros(fout, device=dev)
+            out = torch.empty(M, fout, device=dev, dtype=torch.float16)
+            call = lambda: _lib.check(L.mip360_dense_f16(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, fout, K, 1, st), "dense")
             for _ in range(3):
                 call()
             torch.cuda.synchronize()
@@ -728,18 +729,38 @@ def c3_gemm_roofline(dev, n_rays, prec, reps=10):
                 call()
             e1.record()
             torch.cuda.synchronize()
-            cache[(M, N, K)] = e0.elapsed_time(e1) / reps
+            cache[(fout, K)] = e0.elapsed_time(e1) / reps
             del a, w, b, out
-        tot_ms += cache[(M, N, K)]
-        flops += 2.0 * M * N * K
+        tot_ms += cache[(fout, K)]
+        flops += 2.0 * M * fin * fout
     torch.cuda.empty_cache()
     passes = 3 if prec else 1
     achieved = flops / (tot_ms * passes * 1e-3) / 1e12
+    # per level: the whole field call
+    host = c3_batch(n_rays, 3)
+    R = Rays(*(host[k].to(dev) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")))
+    levels = {}
+    for name, mlp, S, macs in (("prop", model.prop_mlp, C3_SAMPLES[0], C3_PROP_MACS), ("nerf", model.nerf_mlp, C3_SAMPLES[2], C3_NERF_MACS)):
+        sd = torch.linspace(0, 1, S + 1, device=dev).repeat(n_rays, 1).contiguous()
+        for _ in range(3):
+            mlp.level(sd, R)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            mlp.level(sd, R)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        levels[name] = {"ms": ms, "samples": n_rays * S, "tflops": 2.0 * macs * n_rays * S / (ms * 1e-3) / 1e12,
+                        "what": "cast + contract + IPE encode, " + ("PropMLP chain kernel (4 layers + density head, one launch)" if name == "prop" else
+                                                                    "10 Dense-layer GEMM launches (CTA pairs), density / rgb heads")}
     t = ncu_traffic("gemm_tc_kernel")
     return {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
             "traffic": (t or {}).get("bytes_per_launch"), "traffic_source": t, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
-            "launches_per_step": len(shapes), "avg_launch_ms": tot_ms * passes / len(shapes), "algorithmic_flops_per_step": flops,
-            "note": ("K is padded to 64 (504 -> 512, 283 -> 320): padded FLOPs are in neither numerator; the one-pass rate of every shape timed alone"
+            "launches_per_step": len(gemm_layers), "avg_launch_ms": tot_ms * passes / len(gemm_layers), "algorithmic_flops_per_step": flops,
+            "levels": levels,
+            "note": ("the NerfMLP's Dense layers (87 %% of the step's FLOPs); K is padded to 64 (504 -> 512, 283 -> 320), padded FLOPs are not in the numerator"
                      + ("; split precision issues three MMA passes per layer, which do not add to the numerator" if prec else ""))}
 
 
@@ -877,7 +898,7 @@ def run_c3(args):
     last = slots[(args.steps - 1) & 1].fetch()
     losses = dict(zip(("mse_0", "mse_1", "mse_2", "depth_0", "depth_1", "depth_2", "interlevel", "distortion"), [float(x) for x in last["losses"]]))
     del slots
-    roof = c3_gemm_roofline(dev, n_rays, prec)
+    roof = c3_gemm_roofline(dev, n_rays, prec, model)
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

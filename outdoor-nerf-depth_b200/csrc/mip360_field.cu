@@ -67,7 +67,7 @@ __device__ __forceinline__ float s_to_t(float s, float s_near, float s_far) {
 struct Gauss { float mean[3]; float cov[3][3]; };
 
 // Every operation below is rounded on its own (__f*_rn intrinsics are never contracted into FMAs) and sums run left to
-// right: this is the evaluation order of oracle/mip360_model_oracle.py: lifted_gaussians_ordered, operation for operation.
+// right: the evaluation order of the test suite's CPU restatement (lifted_gaussians_ordered), operation for operation.
 // The path is badly conditioned -- feature sin(2^11 x) turns one ulp of a lifted mean into 5e-4, J cov J^T cancels ten
 // digits for distant samples -- so "the same arithmetic" has to mean the same order, not just the same formula.
 #define MUL(a, b) __fmul_rn((a), (b))
