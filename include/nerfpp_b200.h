@@ -298,7 +298,7 @@ int mip360_lossfun_distortion(const float* t, const float* w, int n_rays, int n_
 /* stepfun.max_dilate (weights_mode 0) / max_dilate_weights (weights_mode 1) (stepfun.py:99-128): max-pool the step
  * function (t [n,M+1], w [n,M]) over +-dilation; models.py:150-169 applies it to the proposal histogram between levels.
  * out_t [n,3M+1] = clip(sort(cat(t, t[:-1]-d, t[1:]+d)), domain), out_w [n,3M]; renormalize (weights_mode only) divides
- * by max(eps, sum).  M <= 85. */
+ * by max(eps, sum).  t must be sorted (non-decreasing), as the reference assumes.  M <= 85. */
 int mip360_max_dilate(const float* t, const float* w, int n_rays, int n_bins, float dilation, float domain_min,
                       float domain_max, int weights_mode, int renormalize, float eps, float* out_t, float* out_w,
                       void* stream);

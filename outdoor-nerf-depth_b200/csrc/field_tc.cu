@@ -43,7 +43,7 @@ constexpr int NUM_MMA_LAYERS = 10;          // base 0..7, remap, rgb0
 
 // barrier slots
 enum { B_WFULL = 0, B_WEMPTY = NSTAGE, B_AREADY = 2 * NSTAGE, B_EFULL = B_AREADY + 4, B_EEMPTY = B_EFULL + 2,
-       B_ACC = B_EEMPTY + 2, B_RGBREADY = B_ACC + 2, B_RGBFREE = B_RGBREADY + 1, B_COUNT = B_RGBFREE + 1 };
+       B_ACC = B_EEMPTY + 2, B_ACCH = B_ACC + 2, B_RGBREADY = B_ACCH + 2, B_RGBFREE = B_RGBREADY + 1, B_COUNT = B_RGBFREE + 1 };
 static_assert(8 * B_COUNT + 8 <= 256, "barrier area");
 
 // fp32 tail of the packed buffer (float offsets)
@@ -153,10 +153,13 @@ __device__ __forceinline__ void embed_vec(const float* x, int dim, int nfreq, ui
 //   KIND 0  hidden layer: ReLU + fp16 pack, written back over the fp32 columns just read = next layer's A operand
 //   KIND 1  base layer 7: the same, then the sigma head (nerf_network.py:133) on the fp32 values AFTER the arrive
 //   KIND 2  base_remap: fp16 pack without ReLU (nerf_network.py:135)
-template <int KIND, bool SAVE, bool PREC>
+//   NSPLIT  the layer's MMAs run as two N = 128 column halves (see the issuer): the caller has waited for columns [0,128)
+//           only; columns [128,256) are complete when `full_bar` reaches parity `full_par`, awaited here between chunks 1 and 2
+template <int KIND, bool SAVE, bool PREC, bool NSPLIT = false>
 __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
-                                               uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
+                                               uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0,
+                                               uint32_t full_bar = 0, uint32_t full_par = 0) {
   uint32_t v[2][32];
   uint32_t mbits[4];
   tmem_ld32(acc_addr, v[0]);
@@ -164,7 +167,7 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
   for (int j = 0; j < 4; ++j) {       // 64-column chunks of the layer output
     uint32_t (&cur)[32] = v[j & 1];
     tmem_ld_wait(cur);
-    if (j + 1 < 4) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
+    if (j + 1 < 4 && !(NSPLIT && j == 1)) tmem_ld32(acc_addr + 64u * (j + 1), v[(j + 1) & 1]);   // overlaps the work below
     uint32_t pk[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) pk[t] = pack_f16x2<KIND != 2>(cur[2 * t], cur[2 * t + 1]);
@@ -202,17 +205,23 @@ __device__ __forceinline__ void epilogue_layer(uint32_t acc_addr, uint32_t aread
       }
       sig_part += (s[0] + s[1]) + (s[2] + s[3]);
     }
+    if (NSPLIT && j == 1) {      // the second column half of the accumulator
+      mbar_wait(full_bar, full_par);
+      tc_fence_after();
+      tmem_ld32(acc_addr + 128u, v[0]);
+    }
   }
   if (SAVE && KIND != 2) *mask_dst = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
 }
 
-template <bool SAVE, bool PREC>
+template <bool SAVE, bool PREC, bool NSPLIT = false>
 __device__ __forceinline__ void epilogue_dispatch(int m, uint32_t acc_addr, uint32_t aready_bar, int lane, int row, int hh,
                                                   const float* __restrict__ tail, uint8_t* act_chunk0, uint4* mask_dst, uint8_t* stg,
-                                                  uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0) {
-  if (m < 7) epilogue_layer<0, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
-  else if (m == 7) epilogue_layer<1, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
-  else epilogue_layer<2, SAVE, PREC>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags);
+                                                  uint32_t& stg_flip, float& sig_part, long long* probe_slot, int xflags = 0,
+                                                  uint32_t full_bar = 0, uint32_t full_par = 0) {
+  if (m < 7) epilogue_layer<0, SAVE, PREC, NSPLIT>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags, full_bar, full_par);
+  else if (m == 7) epilogue_layer<1, SAVE, PREC, NSPLIT>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags, full_bar, full_par);
+  else epilogue_layer<2, SAVE, PREC, NSPLIT>(acc_addr, aready_bar, lane, row, hh, tail, act_chunk0, mask_dst, stg, stg_flip, sig_part, probe_slot, xflags, full_bar, full_par);
 }
 
 // Colour head for one row: rgb.2 (nerf_network.py:114-117) as fp32 dot products over the 128 rgb.0 accumulators
@@ -269,13 +278,19 @@ __device__ __forceinline__ void rgb_head(uint32_t acc_addr, uint32_t free_bar, i
 // that the inference kernel's register allocation never sees the save code.
 // PREC: split-precision ("3-pass") inference variant, see make_table().  The E operand is then single-buffered: its two
 // 32 KB buffers hold the high and the low halves of one tile's encoding.
-template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false>
+// NSPLIT (fast inference kernel only): hidden layers issue their A-chunk MMAs as N = 128 column halves in the order
+// [h0: K0 K1] [h1: K0 K1] [h0: K2 K3] [h1: K2 K3].  The epilogue converts columns [0,128) of a layer -- the next layer's
+// K-chunks 0 and 1 -- while that layer's last eight MMAs (h1: K2 K3) still run, and columns [128,256) while the NEXT
+// layer's first sixteen MMAs (both halves of K0, K1) run: the tensor pipe no longer idles for the conversion chain at
+// every layer boundary.  Each weight stage serves both halves (rows 0-127, then 128-255) before it is released.
+template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false, bool NSPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
 field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tail, const float* __restrict__ ray_o,
                 const float* __restrict__ ray_d, const float* __restrict__ z, int n, int S, float* __restrict__ out_sigma,
                 float* __restrict__ out_rgb, float* __restrict__ out_depth_real, int num_tiles, TrainSave save, long long* __restrict__ dbg, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   static_assert(!PREC || (!TRAIN && CLUSTER == 1), "the split-precision variant is inference-only");
+  static_assert(!NSPLIT || (!TRAIN && !PREC && CLUSTER == 1), "column-half issue order: fast inference kernel only");
   constexpr int D = BG ? 4 : 3;
   constexpr uint32_t NEB = PREC ? 1 : 2;       // E buffers in rotation
   const StepTable& tab = c_tab[(PREC ? 2 : 0) + (BG ? 1 : 0)];
@@ -303,7 +318,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_AREADY + i), NUM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(B_EFULL + i), NUM_EMB_WARPS); mbar_init(bar(B_EEMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(bar(B_ACC + i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_ACC + i), 1); mbar_init(bar(B_ACCH + i), 1); }
     mbar_init(bar(B_RGBREADY), 1);
     mbar_init(bar(B_RGBFREE), NUM_EMB_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -411,7 +426,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                     for (int k = 0; k < (c == 1 ? 2 : 4); ++k) mma_ss<1>(d_tmem, allo + 2u * k, SW128_HI, blo + 2u * k, SW128_HI, idesc);
                   }
                   release(wempty);
-                  if (!PREC && m == 0 && c == E_CHUNKS - 1) tc_commit(bar(B_ACC));
+                  if (!PREC && m == 0 && c == E_CHUNKS - 1) { if (NSPLIT) tc_commit(bar(B_ACCH)); tc_commit(bar(B_ACC)); }
                 }
                 __syncwarp();
                 advance();
@@ -460,7 +475,41 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                 advance();
               }
             }
-            if (m != 0) {
+            if (NSPLIT && m != 0 && m != 9) {
+              // ---- column-half issue order (see the kernel's header comment) ----
+              wait_stage();                                   // chunk 0's stage; its head holds the layer's bias tile (not layer 5's)
+              if (m == 1 && tile_i > 0) { mbar_wait(bar(B_RGBFREE), (tile_i - 1) & 1); tc_fence_after(); }   // previous tile's rgb.0 accumulators have been read
+              if (m != 5) {
+                // the bias MMA (N = 256, overwrites the whole accumulator) goes out right behind the previous layer's last MMA:
+                // the tensor pipe executes in issue order, so it cannot overtake that layer's reads of this buffer
+                if (elect_one()) mma_ss<0>(d_tmem, one_lo, SW128_HI, bias_lo(slot, 256), NOSW_HI, ID256);
+                __syncwarp();
+              }
+              uint32_t hslot[2], hwempty[2];
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {          // K-chunk pairs (0, 1) and (2, 3)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                  const int c = 2 * half + cc;
+                  mbar_wait2(bar(B_AREADY + c), a_par, wfull, ph);
+                  tc_fence_after();
+                  if (elect_one()) ts4(d_tmem, a_tmem + 64u * c, sw128_lo(slot + AUX_BYTES), ID128);              // columns [0,128)
+                  __syncwarp();
+                  hslot[cc] = slot; hwempty[cc] = wempty;
+                  advance();
+                }
+                if (elect_one()) {
+                  if (half == 1) tc_commit(bar(B_ACCH + (m & 1)));                                                  // columns [0,128) complete
+                  ts4(d_tmem + 128u, a_tmem + 64u * (2 * half), sw128_lo(hslot[0] + AUX_BYTES + 16384u), ID128);   // columns [128,256): weight rows 128..255
+                  release(hwempty[0]);
+                  ts4(d_tmem + 128u, a_tmem + 64u * (2 * half + 1), sw128_lo(hslot[1] + AUX_BYTES + 16384u), ID128);
+                  release(hwempty[1]);
+                  if (half == 1) tc_commit(bar(B_ACC + (m & 1)));
+                }
+                __syncwarp();
+              }
+              a_par ^= 1;
+            } else if (m != 0) {
               const bool early_bias = (m != 1 && m != 5 && m != 9);
               if (early_bias) {
                 // The bias MMA does not depend on the epilogue, so it runs under the epilogue's latency chain -- once the
@@ -484,6 +533,7 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
                   if (PREC) ts4(d_tmem, a_tmem + 64u * c + 16u, sw128_lo(slot + AUX_BYTES), idesc);     // + A_lo W_hi
                   release(wempty);
                   if (!PREC && c == 3) {
+                    if (NSPLIT) tc_commit(bar(B_ACCH + (m & 1)));   // (only layer 9 comes here then: keeps the two barriers' phases in step)
                     tc_commit(bar(B_ACC + (m & 1)));
                     if (m == 9) tc_commit(bar(B_RGBREADY));   // the colour head (embedding warps) has its own barrier: one phase per tile
                   }
@@ -602,7 +652,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
       for (int m = 0; m < NUM_MMA_LAYERS - 1; ++m) {       // rgb.0 (layer 9) is read by the colour head, not here
         const int ab = m & 1;
         if (timing) ett = clock64();
-        mbar_wait(bar(B_ACC + ab), (acc_par >> ab) & 1u);
+        const uint32_t acc_ph = (acc_par >> ab) & 1u;
+        mbar_wait(bar((NSPLIT ? B_ACCH : B_ACC) + ab), acc_ph);      // NSPLIT: columns [0,128) first; the rest is awaited inside
         if (timing) e_wait += clock64() - ett;
         acc_par ^= 1u << ab;
         tc_fence_after();
@@ -613,7 +664,8 @@ field_tc_kernel(const uint8_t* __restrict__ blobs, const float* __restrict__ tai
         if (TRAIN) epilogue_dispatch<true, false>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, act_tile + m * act_layer_stride,
                                               reinterpret_cast<uint4*>(save.mask + mask_off(m & 7, (size_t)num_tiles, (size_t)tile, hh, row)),
                                               smem + OFF_STG_TRAIN, stg_flip, sig_part, probe, flags);
-        else epilogue_dispatch<false, PREC>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe);
+        else epilogue_dispatch<false, PREC, NSPLIT>(m, acc_addr, bar(B_AREADY), lane, row, hh, tail_s, nullptr, nullptr, nullptr, stg_flip, sig_part, probe,
+                                                    0, bar(B_ACC + ab), acc_ph);
         if (probe_base) dbg[32 * 148 + 40 * (int)cta_pinned + 20 + m] = clock64();
         if (m == 0) flush_pending();
       }
@@ -721,6 +773,7 @@ using namespace npp;
 static int g_cluster = -1;      // weight-sharing cluster size; NERFPP_TC_CLUSTER overrides (1 or 2)
 static long long* g_dbg = nullptr;
 static int g_flags = 0;          // experiment switches (diagnostics only)
+static int g_nsplit = 0;         // column-half issue order of the fast inference kernel (A/B: nerfpp_debug_set_tc_nsplit)
 
 static void tc_config() {
   static bool done = false;
@@ -744,10 +797,10 @@ int npp_pack_tc(const NerfppNetParams* p, bool bg, bool prec, void* out, cudaStr
   return 0;
 }
 
-template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false>
+template <bool BG, int CLUSTER, bool TRAIN, bool PREC = false, bool NSPLIT = false>
 static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, const float* ray_o, const float* ray_d, const float* z,
                      int n, int S, float* out_sigma, float* out_rgb, float* out_dr, int num_tiles, tc::TrainSave save, cudaStream_t st) {
-  auto kern = tc::field_tc_kernel<BG, CLUSTER, TRAIN, PREC>;
+  auto kern = tc::field_tc_kernel<BG, CLUSTER, TRAIN, PREC, NSPLIT>;
   static bool configured_dev[64] = {false};       // the shared-memory opt-in is per device
   static int max_clusters = 0;
   int dev = 0;
@@ -780,6 +833,7 @@ static int launch_tc(int max_ctas, const uint8_t* blobs, const float* tail, cons
 extern "C" void nerfpp_debug_set_tc_timers(long long* dev_buf) { g_dbg = dev_buf; }
 extern "C" void nerfpp_debug_set_tc_cluster(int c) { g_cluster = (c == 2) ? 2 : 1; }
 extern "C" void nerfpp_debug_set_tc_flags(int f) { g_flags = f; }
+extern "C" void nerfpp_debug_set_tc_nsplit(int on) { g_nsplit = on; }
 
 size_t npp_tc_train_ws_bytes(long long n_samples) { return tc::train_ws_bytes((size_t)((n_samples + tc::TILE - 1) / tc::TILE)); }
 
@@ -811,6 +865,9 @@ int npp_field_tc(const void* packed, bool bg, bool prec, const float* ray_o, con
     if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, true) : NPP_TC_LAUNCH(true, 2, true);
     return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, true) : NPP_TC_LAUNCH(false, 2, true);
   }
+  if (g_nsplit && g_cluster == 1)      // the fast inference kernel with the column-half issue order
+    return bg ? launch_tc<true, 1, false, false, true>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st)
+              : launch_tc<false, 1, false, false, true>(num_sms, blobs, tail, ray_o, ray_d, z, n, S, out_sigma, out_rgb, out_depth_real, num_tiles, save, st);
   if (bg) return g_cluster == 1 ? NPP_TC_LAUNCH(true, 1, false) : NPP_TC_LAUNCH(true, 2, false);
   return g_cluster == 1 ? NPP_TC_LAUNCH(false, 1, false) : NPP_TC_LAUNCH(false, 2, false);
 #undef NPP_TC_LAUNCH

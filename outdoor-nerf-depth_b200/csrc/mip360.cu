@@ -370,7 +370,14 @@ max_dilate_kernel(const float* __restrict__ t, const float* __restrict__ w, int 
   for (int k = lane; k < n_out - 1; k += 32) {
     const float tk = all[k];
     float m = 0.f;
-    for (int j = 0; j < M; ++j) if (t0[j] <= tk && t1[j] > tk) m = fmaxf(m, v[j]);
+    // t is sorted, hence so are t0 = t[:-1] - d and t1 = t[1:] + d: the intervals with t0[j] <= tk < t1[j] are the contiguous
+    // range [first j with t1[j] > tk, last j with t0[j] <= tk] -- two binary searches instead of a sweep over all M
+    int lo = 0, hi = M;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t1[mid] > tk) hi = mid; else lo = mid + 1; }
+    const int jl = lo;
+    lo = 0; hi = M;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t0[mid] <= tk) lo = mid + 1; else hi = mid; }
+    for (int j = jl; j < lo; ++j) m = fmaxf(m, v[j]);
     if (weights_mode) m = __fmul_rn(m, __fsub_rn(all[k + 1], tk));
     wd[k] = m;
     part += m;

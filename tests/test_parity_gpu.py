@@ -510,3 +510,30 @@ def test_pipelined_step_is_fifo_and_matches_eager():
     pipe.submit(batches[0]); pipe.submit(batches[1])
     with pytest.raises(NerfppError):
         pipe.submit(batches[2])
+
+
+def test_column_half_issue_order_is_bit_equal():
+    """The fast field kernel's experimental N = 128 column-half issue order (field_tc.cu: NSPLIT; measured no faster, off by
+    default) performs the same accumulations in the same order: outputs bit-equal, fg and bg, ragged sizes."""
+    import ctypes
+    from nerfpp_b200 import FIELD_TC, _lib, ops
+    L = _lib.lib()
+    L.nerfpp_debug_set_tc_nsplit.argtypes = [ctypes.c_int]
+    net = make_models([O.densify(O.make_params(), 5.0)])[0].nerf_net
+    rays = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in O.synthetic_rays(300, seed=3).items()}
+    far = ops.intersect_sphere(rays["ray_o"], rays["ray_d"])
+    try:
+        for S in (192, 5):
+            for is_bg, sub in ((0, net.fg_net), (1, net.bg_net)):
+                z = torch.sort(torch.rand(300, S, device="cuda"), -1)[0]
+                if not is_bg:
+                    z = z * far[:, None]
+                pk = net._packed[is_bg].get(sub.tensors(), FIELD_TC)
+                outs = []
+                for mode in (0, 1):
+                    L.nerfpp_debug_set_tc_nsplit(mode)
+                    outs.append([t.clone() for t in ops.field_forward(pk, is_bg, rays["ray_o"], rays["ray_d"], z, FIELD_TC) if torch.is_tensor(t)])
+                torch.cuda.synchronize()
+                assert all(torch.equal(a, b) for a, b in zip(*outs)), (S, is_bg)
+    finally:
+        L.nerfpp_debug_set_tc_nsplit(0)
