@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const uint32_t buf = tcount & 1, tph = (tcount >> 1) & 1;
       mbar_wait(bar(B::TFULL + buf), tph);
       tc_fence_after();
-      float hacc = 0.f;
+      float hacc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = hh; c < BN / 64; c += 2) {
         uint32_t v0[32], v1[32];
@@ -203,8 +203,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             float x2 = __uint_as_float(v[4 * i + 2]) + b4.z, x3 = __uint_as_float(v[4 * i + 3]) + b4.w;
             if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
             if (g.head_w) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.head_w + n0 + c * 64) + half * 8 + i);
-              hacc += x0 * w4.x + x1 * w4.y + x2 * w4.z + x3 * w4.w;
+              const float4* hw = reinterpret_cast<const float4*>(g.head_w + n0 + c * 64) + half * 8 + i;
+              const float4 w4 = __ldg(hw);
+              hacc[0] += x0 * w4.x + x1 * w4.y + x2 * w4.z + x3 * w4.w;
+              if (g.head_n > 1) {
+                const float4 w5 = __ldg(hw + g.N / 4), w6 = __ldg(hw + g.N / 2);
+                hacc[1] += x0 * w5.x + x1 * w5.y + x2 * w5.z + x3 * w5.w;
+                hacc[2] += x0 * w6.x + x1 * w6.y + x2 * w6.z + x3 * w6.w;
+              }
             }
             const uint32_t p0 = pack_f16x2<false>(__float_as_uint(x0), __float_as_uint(x1));
             const uint32_t p1 = pack_f16x2<false>(__float_as_uint(x2), __float_as_uint(x3));
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             }
           }
         }
+        if (g.no_store) continue;                  // only the fused head's result is wanted
         if (lane == 0) bulk_s2g_wait_read();       // the warp's previous store has read the staging buffer
         __syncwarp();
         uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 128);
@@ -236,7 +243,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       }
       if (g.head_w) {
         const long long r = (long long)m0 + q * 32 + lane;
-        if (r < g.M) g.head_part[r * (2 * n_blks) + 2 * (n0 / BN) + hh] = hacc;
+        if (r < g.M) {
+          float* hp = g.head_part + (r * (2 * n_blks) + 2 * (n0 / BN) + hh) * g.head_n;
+          hp[0] = hacc[0];
+          if (g.head_n > 1) { hp[1] = hacc[1]; hp[2] = hacc[2]; }
+        }
       }
     }
     if (lane == 0) stage_store_drain();

@@ -30,10 +30,13 @@ struct GemmArgs {
   int M, N;
   int relu;
   const float* bias;               // [N] fp32, added in the epilogue
-  // optional fused head (the density head behind the last trunk layer): head_part[row][2 * (n0 / BN) + hh] = the dot product of
-  // the row's activated fp32 outputs in the warp's column chunks with head_w -- summed in a fixed order by a small kernel
-  const float* head_w;             // [N] fp32 or NULL
-  float* head_part;                // [M][2 * N / BN]
+  // optional fused head (the density head behind the last trunk layer, the rgb head behind the view layer): head_part[row][p][k],
+  // p = 2 * (n0 / BN) + hh, = the dot product of the row's activated fp32 outputs in the warp's column chunks with head_w[k] --
+  // summed over p in a fixed order by a small kernel.  no_store: the layer's own output is not needed (nothing is written).
+  const float* head_w;             // [head_n][N] fp32 or NULL
+  float* head_part;                // [M][2 * N / BN][head_n]
+  int head_n;                      // 1 or 3
+  int no_store;
 };
 
 // CTAS = 2: a CTA pair (cluster of two SMs of one TPC, tcgen05 cta_group::2) computes a 256 x BN tile -- each CTA stages its

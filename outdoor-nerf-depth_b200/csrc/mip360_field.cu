@@ -306,6 +306,18 @@ __global__ void density_from_partials_kernel(const float* __restrict__ part, lon
   out[r] = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
 }
 
+// colour from the partial head sums the view layer's GEMM epilogue left: sigmoid(sum + b) * (1 + 2 pad) - pad (models.py:589-609)
+__global__ void rgb_from_partials_kernel(const float* __restrict__ part, long long M, int P, const float* __restrict__ head_bias, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * 3) return;
+  const long long r = i / 3;
+  const int k = (int)(i - r * 3);
+  float acc = 0.f;
+  for (int p = 0; p < P; ++p) acc += part[(r * P + p) * 3 + k];
+  const float sg = 1.f / (1.f + expf(-(acc + head_bias[k])));
+  out[i] = sg * (1.f + 2.f * 0.001f) - 0.001f;
+}
+
 // rgb head (models.py:589-609): sigmoid(h_view . W + b) * (1 + 2 pad) - pad, pad = 0.001.  Eight lanes per row.
 __global__ void __launch_bounds__(256) rgb_head_kernel(const __half* __restrict__ h, const __half* __restrict__ h_lo, long long M,
                                                        const float* __restrict__ wb, float* __restrict__ out) {
@@ -438,7 +450,7 @@ static Workspace make_ws(long long M, const Layout& L) {
 // one Dense layer: up to two A sources (a0 with k0 columns, a1 with k1 columns, lo images alongside in prec mode)
 static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t* a0, const uint8_t* a0_lo, int k0, int ld0,
                  const uint8_t* a1, const uint8_t* a1_lo, int k1, int ld1, uint8_t* out, uint8_t* out_lo, long long M, int N, int relu,
-                 cudaStream_t st, const float* head_w = nullptr, float* head_part = nullptr) {
+                 cudaStream_t st, const float* head_w = nullptr, float* head_part = nullptr, int head_n = 1, int no_store = 0) {
   using namespace gemm;
   GemmArgs g{};
   int bn, ctas;
@@ -471,7 +483,7 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
   }
   g.n_seg = ns; g.M = (int)M; g.N = N; g.relu = relu;
   g.bias = reinterpret_cast<const float*>(packed + L.bias[idx]);
-  g.head_w = head_w; g.head_part = head_part;
+  g.head_w = head_w; g.head_part = head_part; g.head_n = head_n; g.no_store = no_store;
   return launch_gemm(g, bn, ctas, prec, st);
 }
 
@@ -599,11 +611,17 @@ extern "C" int mip360_field_forward(const void* packed, int net_depth, int net_w
     uint8_t* bott_lo = prec ? ws + W.bott_lo : nullptr;
     rc = dense(L, pk, net_depth + 1, hbuf(cur), hlo(cur), Wd, Wd, nullptr, nullptr, 0, 0, bott, bott_lo, M, BOTTLENECK, 0, st);
     if (rc) return rc;
+    // the view layer; its epilogue also evaluates the rgb head on the fp32 activated values (partials per column chunk), so the
+    // 128-wide hidden layer is never written out
+    const float* rgb_w = (const float*)(pk + L.w_hi[net_depth + 3]);
+    float* rpart = (float*)(ws + W.hpart);
     rc = dense(L, pk, net_depth + 2, bott, bott_lo, BOTTLENECK, BOTTLENECK, ws + W.dir, prec ? ws + W.dir_lo : nullptr, DIR_LD, DIR_LD,
-               ws + W.hv, prec ? ws + W.hv_lo : nullptr, M, VIEW_W, 1, st);
+               ws + W.hv, prec ? ws + W.hv_lo : nullptr, M, VIEW_W, 1, st, g_fuse_head ? rgb_w : nullptr, g_fuse_head ? rpart : nullptr, 3, g_fuse_head);
     if (rc) return rc;
-    rgb_head_kernel<<<(unsigned)((M * 8 + 255) / 256), 256, 0, st>>>((const __half*)(ws + W.hv), prec ? (const __half*)(ws + W.hv_lo) : nullptr, M,
-                                                                      (const float*)(pk + L.w_hi[net_depth + 3]), out_rgb);
+    if (g_fuse_head)
+      rgb_from_partials_kernel<<<(unsigned)((M * 3 + 255) / 256), 256, 0, st>>>(rpart, M, 2, rgb_w + 3 * VIEW_W, out_rgb);
+    else
+      rgb_head_kernel<<<(unsigned)((M * 8 + 255) / 256), 256, 0, st>>>((const __half*)(ws + W.hv), prec ? (const __half*)(ws + W.hv_lo) : nullptr, M, rgb_w, out_rgb);
   }
   NPP_CHECK_LAUNCH();
   return 0;

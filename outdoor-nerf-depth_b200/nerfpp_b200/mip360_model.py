@@ -51,7 +51,8 @@ class MLP(object):
         self.prec = bool(prec)
         self.shapes = dense_shapes(self.net_depth, self.net_width, not self.disable_rgb)
         self.params = None          # list of (kernel [in,out], bias [out]) CUDA fp32 tensors
-        self._packed = None
+        self._packed = None         # the fp16 operand images; ONE allocation for the object's lifetime (captured graphs hold its address)
+        self._dirty = True
         self._ws = None
 
     # -- parameters ------------------------------------------------------------------------------------------------
@@ -76,7 +77,7 @@ class MLP(object):
                 raise ValueError("Dense kernel %s / bias %s do not match (%d, %d)" % (tuple(k.shape), tuple(b.shape), fi, fo))
             out.append((k, b))
         self.params = out
-        self._packed = None
+        self._dirty = True          # re-packed into the same buffer on the next use
         return self
 
     def load_flax(self, tree):
@@ -86,20 +87,22 @@ class MLP(object):
     def packed(self):
         if self.params is None:
             raise NerfppError("MLP has no parameters: call init() or load()")
-        if self._packed is None:
+        if self._dirty:
             L = _lib.lib()
             has_rgb = int(not self.disable_rgb)
-            nbytes = L.mip360_mlp_packed_bytes(self.net_depth, self.net_width, has_rgb, int(self.prec))
-            if nbytes < 0:
-                check(-1, "mip360_mlp_packed_bytes")
-            buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+            if self._packed is None:
+                nbytes = L.mip360_mlp_packed_bytes(self.net_depth, self.net_width, has_rgb, int(self.prec))
+                if nbytes < 0:
+                    check(-1, "mip360_mlp_packed_bytes")
+                self._packed = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+            buf = self._packed
             st = Mip360MlpParams()
             for i, (k, b) in enumerate(self.params):
                 st.kernel[i], st.bias[i] = k.data_ptr(), b.data_ptr()
             with torch.cuda.device(self.device):
                 check(L.mip360_mlp_pack(ctypes.byref(st), self.net_depth, self.net_width, has_rgb, int(self.prec), _p(buf), _stream()),
                       "mip360_mlp_pack")
-            self._packed = buf
+            self._dirty = False
         return self._packed
 
     def _workspace(self, n_samples):
@@ -121,6 +124,8 @@ class MLP(object):
         tdist = torch.empty(n, S + 1, device=sd.device, dtype=torch.float32)
         density = torch.empty(n, S, device=sd.device, dtype=torch.float32)
         rgb = None if self.disable_rgb else torch.empty(n, S, 3, device=sd.device, dtype=torch.float32)
+        if n == 0 or S == 0:        # an empty batch is a no-op (the reference returns empty arrays)
+            return tdist, density, rgb
         ws = self._workspace(n * S)
         with torch.cuda.device(sd.device):
             check(_lib.lib().mip360_field_forward(_p(self.packed()), self.net_depth, self.net_width, int(not self.disable_rgb), int(self.prec),
@@ -185,8 +190,14 @@ class Model(object):
         torch.Generator / True (torch's default CUDA generator) for the jitter; ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
         near, far = _c(rays.near, "near").reshape(-1, 1), _c(rays.far, "far").reshape(-1, 1)
         n = near.shape[0]
-        sdist = torch.cat([torch.zeros_like(near), torch.ones_like(far)], dim=-1)
-        weights = torch.ones_like(near)
+        # the initial interval [0, 1] with weight 1 (models.py:129-136) and the proposal levels' all-zero colours are constants
+        # of the batch size: built once, not once per call (five fills and a cat fewer per step)
+        key = (n, str(near.device))
+        if getattr(self, "_const_key", None) != key:
+            self._const = (torch.tensor([0.0, 1.0], device=near.device).repeat(n, 1).contiguous(), torch.ones(n, 1, device=near.device),
+                           torch.zeros(n, self.num_prop_samples, 3, device=near.device))
+            self._const_key = key
+        sdist, weights, zero_rgb = self._const
         prod_num_samples = 1
         renderings, ray_history = [], []
         for i_level in range(self.num_levels):
@@ -212,7 +223,7 @@ class Model(object):
             tdist, density, rgb = mlp.level(sdist, rays)
             weights = mip360.compute_alpha_weights(density, tdist, rays.directions, opaque_background=self.opaque_background)[0]
             if rgb is None:
-                rgb = torch.zeros(n, num_samples, 3, device=self.device)      # disable_rgb: zeros (models.py:511-512)
+                rgb = zero_rgb                                                 # disable_rgb: zeros (models.py:511-512)
             rendering = mip360.volumetric_rendering(rgb, weights, tdist, self.bg_intensity, far.reshape(-1), compute_extras)
             renderings.append(rendering)
             ray_history.append(dict(density=density, rgb=rgb, sdist=sdist, tdist=tdist, weights=weights))

@@ -227,6 +227,28 @@ def test_model_three_levels_matches_oracle(prec):
     np.testing.assert_allclose(hist[0]["sdist"].cpu().numpy(), hist_ref[0]["sdist"], atol=1e-6)
 
 
+def test_empty_batch_and_reloaded_weights():
+    """An empty batch returns empty tensors; weights loaded a second time are re-packed into the SAME buffer (a captured CUDA
+    graph holds its address) and take effect."""
+    from nerfpp_b200.mip360_model import MLP
+    dev = _dev()
+    rays = MM.synthetic_rays(8, seed=2)
+    R = _rays_t(rays, dev)
+    mlp = MLP(4, 256, True, dev).load(MM.init_mlp_params(4, 256, False, seed=1))
+    empty = type(R)(*(t[:0] for t in R))
+    t, d, c = mlp.level(torch.zeros(0, 17, device=dev), empty)
+    assert t.shape == (0, 17) and d.shape == (0, 16) and c is None
+    sd = torch.from_numpy(_sdist(8, 16, 3)).to(dev)
+    _, d1, _ = mlp.level(sd, R)
+    ptr = mlp.packed().data_ptr()
+    p2 = MM.init_mlp_params(4, 256, False, seed=2)
+    mlp.load(p2)
+    _, d2, _ = mlp.level(sd, R)
+    assert mlp.packed().data_ptr() == ptr and not torch.equal(d1, d2)
+    ref = MM.field_level(p2, 4, False, sd.cpu().numpy(), rays["near"], rays["far"], rays["origins"], rays["directions"], rays["viewdirs"], rays["radii"])[1]
+    assert _rel(d2.cpu().numpy(), ref) <= 2e-3
+
+
 def test_cpu_tensors_raise():
     from nerfpp_b200 import NerfppError
     from nerfpp_b200.mip360_model import MLP
