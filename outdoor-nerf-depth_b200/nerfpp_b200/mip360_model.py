@@ -230,6 +230,45 @@ class Model(object):
         return renderings, ray_history
 
 
+def render_image(model, rays, render_chunk_size=16384, train_frac=1.0, process_group=None):
+    """models.render_image (models.py:625-703) in test mode: every pixel of an image through ``model`` in chunks of
+    ``render_chunk_size`` rays (configs.py: render_chunk_size = 16384), the LAST level's 2-D buffers reshaped to
+    [height, width, ...].  ``rays``: a ``Rays`` of [height, width, C] CUDA tensors.  With a ``process_group`` (one process per
+    GPU) every rank renders its contiguous band of each chunk -- the reference shards a chunk over its devices the same way
+    (models.py:665-669) -- and ONE all-gather of the packed keys per image collects the bands on every rank."""
+    height, width = rays.origins.shape[:2]
+    num_rays = height * width
+    flat = Rays(*(_c(r, "rays").reshape(num_rays, -1) for r in rays))
+    if process_group is not None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    else:
+        world, rank = 1, 0
+    keys = ("rgb", "acc", "distance_mean", "depth", "distance_percentile_5", "distance_median", "distance_percentile_95")
+    widths = (3, 1, 1, 1, 1, 1, 1)
+    per = (num_rays + world - 1) // world                 # rays per rank (the last band may be short)
+    lo, hi = min(rank * per, num_rays), min((rank + 1) * per, num_rays)
+    packed = torch.zeros(per, sum(widths), device=model.device)
+    with torch.no_grad():
+        for idx0 in range(lo, hi, render_chunk_size):
+            idx1 = min(idx0 + render_chunk_size, hi)
+            chunk = Rays(*(r[idx0:idx1] for r in flat))
+            renderings, _ = model(None, chunk, train_frac=train_frac, compute_extras=True)
+            last = renderings[-1]
+            packed[idx0 - lo:idx1 - lo] = torch.cat([last[k].reshape(idx1 - idx0, -1) for k in keys], dim=-1)
+    if world > 1:
+        import torch.distributed as dist
+        gathered = torch.empty(world * per, sum(widths), device=model.device)
+        dist.all_gather_into_tensor(gathered, packed, group=process_group)
+        packed = gathered
+    packed = packed[:num_rays]
+    out, off = {}, 0
+    for k, w in zip(keys, widths):
+        out[k] = packed[:, off:off + w].reshape((height, width) + ((w,) if w > 1 else ()))
+        off += w
+    return out
+
+
 IN_KEYS = (("origins", 3), ("directions", 3), ("viewdirs", 3), ("radii", 1), ("near", 1), ("far", 1), ("rgb", 3), ("disps_sup", 1))
 LOSS_KEYS = ("mse_0", "mse_1", "mse_2", "depth_0", "depth_1", "depth_2", "interlevel", "distortion")
 
