@@ -493,8 +493,8 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
 using namespace npp::m360;
 
 // chain_tc.cu: the PropMLP's four layers + density head in one persistent kernel (activations stay on the SM)
-int npp_prop_chain(const void* enc, const void* const* w, const int* k_pad, const float* const* bias, const float* head, float* density,
-                   long long M, cudaStream_t st);
+int npp_prop_chain(const void* enc, const void* enc_lo, const void* const* w, const void* const* w_lo, const int* k_pad,
+                   const float* const* bias, const float* head, float* density, long long M, cudaStream_t st);
 static int g_chain = 1, g_fuse_head = 1;
 extern "C" void mip360_debug_set_fused_head(int on) { g_fuse_head = on; }
 extern "C" void mip360_debug_set_chain(int on) { g_chain = on; }      // A/B and tests: 0 = layer-by-layer GEMM launches
@@ -573,12 +573,13 @@ extern "C" int mip360_field_forward(const void* packed, int net_depth, int net_w
   int rc = mip360_cast_encode(sdist, near, far, origins, directions, viewdirs, radii, n_rays, n_samples, out_tdist, enc, enc_lo,
                               has_rgb ? ws + W.dir : nullptr, (has_rgb && prec) ? ws + W.dir_lo : nullptr, nullptr, nullptr, stream);
   if (rc) return rc;
-  if (g_chain && net_depth == 4 && net_width == 256 && !has_rgb && !prec) {
+  if (g_chain && net_depth == 4 && net_width == 256 && !has_rgb) {
     const void* wp[4];
+    const void* wl[4];
     const float* bp[4];
     int kp[4];
-    for (int l = 0; l < 4; ++l) { wp[l] = pk + L.w_hi[l]; bp[l] = (const float*)(pk + L.bias[l]); kp[l] = L.k_pad[l]; }
-    return npp_prop_chain(enc, wp, kp, bp, (const float*)(pk + L.w_hi[net_depth]), out_density, M, st);
+    for (int l = 0; l < 4; ++l) { wp[l] = pk + L.w_hi[l]; wl[l] = pk + L.w_lo[l]; bp[l] = (const float*)(pk + L.bias[l]); kp[l] = L.k_pad[l]; }
+    return npp_prop_chain(enc, enc_lo, wp, prec ? wl : nullptr, kp, bp, (const float*)(pk + L.w_hi[net_depth]), out_density, M, st);
   }
   auto hbuf = [&](int i) { return ws + W.h[i]; };
   auto hlo = [&](int i) { return prec ? ws + W.h_lo[i] : (uint8_t*)nullptr; };

@@ -132,7 +132,7 @@ class MLP(object):
                                                   _p(sd), _p(near), _p(far), _p(o), _p(d), _p(v), _p(rad), n, S, _p(tdist), _p(density),
                                                   _p(rgb), _p(ws), _stream()), "mip360_field_forward")
         # encode + one GEMM per Dense layer + density head (+ bottleneck, view layer, rgb head); check() counted one
-        if self.net_depth == 4 and self.net_width == 256 and self.disable_rgb and not self.prec:
+        if self.net_depth == 4 and self.net_width == 256 and self.disable_rgb:
             ops.LAUNCHES[0] += 1          # encode + the fused PropMLP chain kernel
         else:
             ops.LAUNCHES[0] += self.net_depth + 1 + (0 if self.disable_rgb else 3)

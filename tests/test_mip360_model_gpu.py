@@ -156,10 +156,12 @@ def test_field_level_split_precision(depth, width, has_rgb):
         assert np.max(np.abs(c - c_same)) <= 4e-5 and np.max(np.abs(c - c_ref)) <= 4e-5
 
 
-def test_prop_chain_kernel_matches_layerwise_gemms():
+@pytest.mark.parametrize("prec", [False, True])
+def test_prop_chain_kernel_matches_layerwise_gemms(prec):
     """The PropMLP as one persistent kernel (activations in shared memory / TMEM, density head on the fp32 accumulators)
     against the same network run layer by layer through the GEMM kernel: same fp16 operands, so only the last hidden layer's
-    rounding differs (the chain feeds the head from fp32).  Sizes: a single partial tile, an odd tile count, 2.3 waves."""
+    rounding differs (the chain feeds the head from fp32).  Sizes: a single partial tile, an odd tile count, 2.3 waves.
+    prec: the split-precision variant of the chain (one tile in flight, hi + lo activations, chunk-wise hand-over)."""
     import ctypes as C
     from nerfpp_b200 import _lib
     from nerfpp_b200.mip360_model import MLP
@@ -171,7 +173,7 @@ def test_prop_chain_kernel_matches_layerwise_gemms():
         rays = MM.synthetic_rays(n, seed=n)
         sd = torch.from_numpy(_sdist(n, S, n + 1)).to(dev)
         R = _rays_t(rays, dev)
-        mlp = MLP(4, 256, True, dev).load(params)
+        mlp = MLP(4, 256, True, dev, prec=prec).load(params)
         try:
             L.mip360_debug_set_chain(0)
             _, d_gemm, _ = mlp.level(sd, R)
@@ -182,7 +184,7 @@ def test_prop_chain_kernel_matches_layerwise_gemms():
         torch.cuda.synchronize()
         assert torch.isfinite(d_chain).all()
         rel = float((d_chain - d_gemm).abs().max() / d_gemm.abs().max())
-        assert rel <= 1e-3, (n, S, rel)
+        assert rel <= (2e-5 if prec else 1e-3), (n, S, rel)
 
 
 def test_ragged_sample_counts():
