@@ -37,11 +37,30 @@ __constant__ float c_basis[NB][3] = {
 // division can only be one too LARGE (rounding to nearest never crosses an integer downwards), so r = x - q T lies in
 // (-T, T); x and q T are multiples of ulp(T) = 2^-15 and |r| < 512, hence r is representable and the FMA returns it exactly,
 // and so is the correction r + T.
-// PRECISE (split-precision mode, whose features keep ~1e-7 through their low halves): the exact modulus and libm's sinf.
+// PRECISE (split-precision mode, whose features keep ~1e-7 through their low halves): the exact modulus and sin_cw (~1 ulp).
 // Otherwise (features rounded to fp16, half an ulp = 1.2e-4): six instructions -- the modulus with a reciprocal multiply
 // (a quotient off by one shifts the phase by T - 100 pi = 5.9e-6 only, T being 50 periods to that accuracy) and the SFU's
 // sin on the reduced argument (|x| < 2 T: 1 / 2 pi scaling error <= 4e-5 rad, SFU 4e-7).
 __device__ __forceinline__ float sin_sfu(float x) { return __sinf(x); }          // |x| < 8: view directions
+// |x| < 2 * 100 pi: two-FMA Cody-Waite reduction by pi/2 (the first FMA is exact: both terms are multiples of 2^-23 and the
+// difference is below 1) and the single-precision minimax polynomials for sin / cos on [-pi/4, pi/4] (~1 ulp): libm's sinf
+// without its large-argument path, less than half the instructions
+__device__ __forceinline__ float sin_cw(float x) {
+  const float kf = rintf(x * 0.636619772367581f);
+  float r = __fmaf_rn(-kf, 1.5707963705062866f, x);
+  r = __fmaf_rn(-kf, -4.371138828673793e-8f, r);
+  const int k = (int)kf;
+  const float s = r * r;
+  float v;
+  if (k & 1) {
+    v = fmaf(s, fmaf(s, fmaf(s, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), -0.5f);
+    v = fmaf(v, s, 1.f);
+  } else {
+    v = fmaf(s, fmaf(s, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f);
+    v = fmaf(v * s, r, r);
+  }
+  return (k & 2) ? -v : v;
+}
 template <bool PRECISE>
 __device__ __forceinline__ float safe_sin(float x) {
   const float T = 314.15927f;      // float32(100 * pi)
@@ -52,7 +71,7 @@ __device__ __forceinline__ float safe_sin(float x) {
       if (r < 0.f) r = __fadd_rn(r, T);
       x = r;
     }
-    return sinf(x);
+    return sin_cw(x);
   }
   if (fabsf(x) >= T) x = __fmaf_rn(-floorf(x * 0.0031830987f), T, x);
   return __sinf(x);
@@ -186,8 +205,8 @@ __global__ void __launch_bounds__(256) cast_encode_kernel(
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float x = d[k] * (float)(1 << j);
-          f[3 + j * 3 + k] = PRECISE ? sinf(x) : sin_sfu(x);
-          f[3 + 3 * DIR_DEG + j * 3 + k] = PRECISE ? sinf(x + 1.5707964f) : sin_sfu(x + 1.5707964f);
+          f[3 + j * 3 + k] = PRECISE ? sin_cw(x) : sin_sfu(x);
+          f[3 + 3 * DIR_DEG + j * 3 + k] = PRECISE ? sin_cw(x + 1.5707964f) : sin_sfu(x + 1.5707964f);
         }
       uint4* rowp = reinterpret_cast<uint4*>(dir + gi * DIR_LD);
       uint4* rowl = dir_lo ? reinterpret_cast<uint4*>(dir_lo + gi * DIR_LD) : nullptr;
