@@ -57,9 +57,10 @@ template <int STAGES> struct Bars {
   static constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, COUNT = 2 * STAGES + 4;
 };
 
-template <int BN, bool PREC, int CTAS>
+template <int BN, bool PREC, int CTAS, bool F3 = false>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs g) {
-  using C = Cfg<BN, PREC, CTAS>;
+  static_assert(!F3 || (PREC && CTAS == 2), "the fused three-group stage is the split-precision CTA-pair form");
+  using C = Cfg<BN, PREC, CTAS, F3>;
   using B = Bars<C::STAGES>;
   static_assert(8 * B::COUNT + 8 <= C::BAR_BYTES, "barrier area");
   extern __shared__ uint8_t smem_raw[];
@@ -122,8 +123,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             } else {
               if (leader) mbar_expect_tx(bar(B::FULL + st), C::STAGE_BYTES * CTAS);     // both CTAs' bytes land on the leader's barrier
               const uint32_t fb = map_to_cta(bar(B::FULL + st), 0);
-              tma_load_2d_pair(dst, &g.a[sg.a_map], sg.a_col + c * BK, m0, fb);
-              tma_load_2d_pair(dst + C::A_BYTES, &g.w[sg.w_map], sg.w_col + c * BK, n0, fb);
+              if (!F3) {
+                tma_load_2d_pair(dst, &g.a[sg.a_map], sg.a_col + c * BK, m0, fb);
+                tma_load_2d_pair(dst + C::A_BYTES, &g.w[sg.w_map], sg.w_col + c * BK, n0, fb);
+              } else {            // A_hi | A_lo | W_hi | W_lo
+                tma_load_2d_pair(dst, &g.a[sg.a_map], sg.a_col + c * BK, m0, fb);
+                tma_load_2d_pair(dst + C::A_BYTES, &g.a[sg.a_map + 1], sg.a_col + c * BK, m0, fb);
+                tma_load_2d_pair(dst + 2 * C::A_BYTES, &g.w[0], sg.w_col + c * BK, n0, fb);
+                tma_load_2d_pair(dst + 2 * C::A_BYTES + C::B_BYTES, &g.w[1], sg.w_col + c * BK, n0, fb);
+              }
             }
           }
         }
@@ -145,11 +153,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           tc_fence_after();
           if (elect_one()) {
             const uint32_t alo = sw128_lo(s_base + st * C::STAGE_BYTES);
-            const uint32_t blo = sw128_lo(s_base + st * C::STAGE_BYTES + C::A_BYTES);
+            const uint32_t blo = sw128_lo(s_base + st * C::STAGE_BYTES + (F3 ? 2 : 1) * C::A_BYTES);
             mma_ss_rt<CTAS>(d, alo, blo, idesc, c > 0 ? 1u : 0u);
             mma_ss_rt<CTAS>(d, alo + 2, blo + 2, idesc, 1u);
             mma_ss_rt<CTAS>(d, alo + 4, blo + 4, idesc, 1u);
             mma_ss_rt<CTAS>(d, alo + 6, blo + 6, idesc, 1u);
+            if (F3) {
+              const uint32_t al2 = sw128_lo(s_base + st * C::STAGE_BYTES + C::A_BYTES);                       // A_lo
+              const uint32_t bl2 = sw128_lo(s_base + st * C::STAGE_BYTES + 2 * C::A_BYTES + C::B_BYTES);      // W_lo
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma_ss_rt<CTAS>(d, al2 + 2 * k, blo + 2 * k, idesc, 1u);            // A_lo W_hi
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma_ss_rt<CTAS>(d, alo + 2 * k, bl2 + 2 * k, idesc, 1u);            // A_hi W_lo
+            }
             if (CTAS == 1) {
               tc_commit(bar(B::EMPTY + st));                  // stage free once these MMAs have read it
               if (c == chunks_per_tile - 1) tc_commit(bar(B::TFULL + buf));
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         uint4* rowp = reinterpret_cast<uint4*>(stg + lane * 128);
 #pragma unroll
         for (int u = 0; u < 8; ++u) rowp[u ^ (lane & 7)] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        if (PREC) {
+        if (PREC && !F3) {
           uint4* rowl = reinterpret_cast<uint4*>(stg + 4096 + lane * 128);
 #pragma unroll
           for (int u = 0; u < 8; ++u) rowl[u ^ (lane & 7)] = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
@@ -237,8 +253,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&g.out[0], n0 + c * 64, m0 + q * 32, stg_s);
-          if (PREC) tma_store_2d(&g.out[1], n0 + c * 64, m0 + q * 32, stg_s + 4096);
+          if (PREC && !F3) tma_store_2d(&g.out[1], n0 + c * 64, m0 + q * 32, stg_s + 4096);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (F3) {                                  // the low halves through the same 4 KB buffer, once the hi store has read it
+          if (lane == 0) bulk_s2g_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rowp[u ^ (lane & 7)] = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&g.out[1], n0 + c * 64, m0 + q * 32, stg_s);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
       if (g.head_w) {
@@ -302,10 +330,10 @@ void plan(int N, int K, int* bn, int* ctas) {
   *ctas = (*bn == 256 && (g_pair_mode == 2 || (g_pair_mode == 1 && K >= 512))) ? 2 : 1;
 }
 
-template <int BN, bool PREC, int CTAS>
+template <int BN, bool PREC, int CTAS, bool F3 = false>
 static int launch_t(const GemmArgs& g, cudaStream_t st) {
-  using C = Cfg<BN, PREC, CTAS>;
-  auto kern = gemm_tc_kernel<BN, PREC, CTAS>;
+  using C = Cfg<BN, PREC, CTAS, F3>;
+  auto kern = gemm_tc_kernel<BN, PREC, CTAS, F3>;
   static bool configured_dev[64] = {false};
   static int max_ctas_dev[64] = {0};
   int dev = 0;
@@ -343,7 +371,7 @@ static int launch_t(const GemmArgs& g, cudaStream_t st) {
 
 int launch_gemm(const GemmArgs& g, int bn, int ctas, bool prec, cudaStream_t st) {
   if (g.N % bn != 0 || (bn != 256 && bn != 128) || (ctas == 2 && bn != 256)) { npp_set_error("gemm_tc: N %d / tile width %d / %d CTAs per tile", g.N, bn, ctas); return -1; }
-  if (bn == 256 && ctas == 2) return prec ? launch_t<256, true, 2>(g, st) : launch_t<256, false, 2>(g, st);
+  if (bn == 256 && ctas == 2) return prec ? (g.fused3 ? launch_t<256, true, 2, true>(g, st) : launch_t<256, true, 2>(g, st)) : launch_t<256, false, 2>(g, st);
   if (bn == 256) return prec ? launch_t<256, true, 1>(g, st) : launch_t<256, false, 1>(g, st);
   return prec ? launch_t<128, true, 1>(g, st) : launch_t<128, false, 1>(g, st);
 }

@@ -37,18 +37,23 @@ struct GemmArgs {
   float* head_part;                // [M][2 * N / BN][head_n]
   int head_n;                      // 1 or 3
   int no_store;
+  int fused3;                      // split precision, F3 kernel: `seg` lists the hi x hi pass only; A lo map = a_map + 1, W lo map = 1
 };
 
 // CTAS = 2: a CTA pair (cluster of two SMs of one TPC, tcgen05 cta_group::2) computes a 256 x BN tile -- each CTA stages its
 // own 128 rows of A and HALF of the weight tile, the leader issues M = 256 MMAs that read both halves, each CTA's TMEM
 // receives its 128 rows of the result.  Per SM that halves the weight stream (the L2 -> shared-memory traffic that bounds
 // the one-CTA form at 96 B/clk) and leaves room for six pipeline stages.
-template <int BN, bool PREC, int CTAS> struct Cfg {
+// F3 (split precision, CTA pairs): a stage holds the hi AND lo tiles of both operands for one K-chunk and feeds three MMA
+// groups (A_hi W_hi, A_lo W_hi, A_hi W_lo): four tiles staged per three groups instead of six -- per 128 MMA-cycles the SM then
+// moves 107 B/clk through shared memory instead of the 128 B/clk it has.  The epilogue stages its hi and lo images one after
+// the other through one 4 KB buffer per warp to make room for three 64 KB stages.
+template <int BN, bool PREC, int CTAS, bool F3 = false> struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;                    // weight rows each CTA loads per stage
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_WARP_BYTES = (PREC ? 2 : 1) * 4096;   // per epilogue warp: [32 rows x 64 cols] fp16 (hi [, lo])
+  static constexpr int STAGE_BYTES = (F3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int OUT_WARP_BYTES = ((PREC && !F3) ? 2 : 1) * 4096;   // per epilogue warp: [32 rows x 64 cols] fp16 (hi [, lo])
   static constexpr int OUT_BYTES = 8 * OUT_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - OUT_BYTES;

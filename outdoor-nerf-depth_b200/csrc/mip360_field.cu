@@ -466,6 +466,7 @@ static Workspace make_ws(long long M, const Layout& L) {
   return W;
 }
 
+static int g_fused3 = 1;      // A/B: mip360_debug_set_fused3
 // one Dense layer: up to two A sources (a0 with k0 columns, a1 with k1 columns, lo images alongside in prec mode)
 static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t* a0, const uint8_t* a0_lo, int k0, int ld0,
                  const uint8_t* a1, const uint8_t* a1_lo, int k1, int ld1, uint8_t* out, uint8_t* out_lo, long long M, int N, int relu,
@@ -494,7 +495,10 @@ static int dense(const Layout& L, const uint8_t* packed, int idx, const uint8_t*
   const int w1 = c0 * BK;     // weight column where the second source starts
   int ns = 0;
   // (A half, W half): hi x hi, then the two cross terms of the split-precision mode (lo x lo is below fp32 resolution)
-  const int passes = prec ? 3 : 1;
+  // CTA pairs in split precision: ONE pass whose stages carry hi and lo tiles of both operands (gemm_tc.cuh: F3)
+  const bool fused3 = prec && ctas == 2 && g_fused3;
+  g.fused3 = fused3;
+  const int passes = (prec && !fused3) ? 3 : 1;
   for (int p = 0; p < passes; ++p) {
     const int ah = (p == 1) ? 1 : 0, wh = (p == 2) ? 1 : 0;
     g.seg[ns++] = Segment{0 + ah, 0, wh, 0, c0};
@@ -516,6 +520,7 @@ int npp_prop_chain(const void* enc, const void* enc_lo, const void* const* w, co
                    const float* const* bias, const float* head, float* density, long long M, cudaStream_t st);
 static int g_chain = 1, g_fuse_head = 1;
 extern "C" void mip360_debug_set_fused_head(int on) { g_fuse_head = on; }
+extern "C" void mip360_debug_set_fused3(int on) { npp::m360::g_fused3 = on; }
 extern "C" void mip360_debug_set_chain(int on) { g_chain = on; }      // A/B and tests: 0 = layer-by-layer GEMM launches
 
 extern "C" int64_t mip360_mlp_packed_bytes(int net_depth, int net_width, int has_rgb, int prec) {

@@ -33,10 +33,13 @@ def _sdist(n, S, seed):
     return s.astype(F32)
 
 
-@pytest.mark.parametrize("M,N,K,relu", [(128, 128, 64, 0), (1000, 256, 512, 1), (333, 128, 320, 1), (4096, 1024, 1024, 1), (777, 1024, 1536, 0)])
+@pytest.mark.parametrize("M,N,K,relu", [(128, 128, 64, 0), (1000, 256, 512, 1), (333, 128, 320, 1), (4096, 1024, 1024, 1), (777, 1024, 1536, 0),
+                                        (1, 128, 8, 1), (31, 256, 72, 0), (129, 1024, 504, 1), (257, 256, 1528, 1), (300, 1024, 256, 0)])
 def test_dense_layer_matches_torch(M, N, K, relu):
     """The tcgen05 Dense layer (tensor-map TMA operands, fp32 accumulation in TMEM, fused bias / ReLU, fp16 output through a
-    TMA store) against torch fp32 on the same fp16 operands: only the output's fp16 rounding may differ (half an ulp)."""
+    TMA store) against torch fp32 on the same fp16 operands: only the output's fp16 rounding may differ (half an ulp).
+    Ragged shapes: rows that do not fill a tile or a 32-row store box, K that is not a multiple of the 64-column stage (the
+    TMA unit zero-fills the rest), one-CTA tiles (K < 512 or N = 128) and CTA pairs."""
     from nerfpp_b200 import _lib
     dev = _dev()
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
