@@ -230,40 +230,53 @@ class Model(object):
         return renderings, ray_history
 
 
-def render_image(model, rays, render_chunk_size=16384, train_frac=1.0, process_group=None):
+RENDER_KEYS = ("rgb", "acc", "distance_mean", "depth", "distance_percentile_5", "distance_median", "distance_percentile_95")
+RENDER_WIDTHS = (3, 1, 1, 1, 1, 1, 1)
+
+
+def band(num_rays, world, rank):
+    """Rank ``rank``'s contiguous band [lo, hi) of ``num_rays`` rays and the common band length (the last may be short)."""
+    per = (num_rays + world - 1) // world
+    return min(rank * per, num_rays), min((rank + 1) * per, num_rays), per
+
+
+def render_image(model, rays, render_chunk_size=16384, train_frac=1.0, process_group=None, render_chunk=None, device=None):
     """models.render_image (models.py:625-703) in test mode: every pixel of an image through ``model`` in chunks of
     ``render_chunk_size`` rays (configs.py: render_chunk_size = 16384), the LAST level's 2-D buffers reshaped to
     [height, width, ...].  ``rays``: a ``Rays`` of [height, width, C] CUDA tensors.  With a ``process_group`` (one process per
-    GPU) every rank renders its contiguous band of each chunk -- the reference shards a chunk over its devices the same way
-    (models.py:665-669) -- and ONE all-gather of the packed keys per image collects the bands on every rank."""
+    GPU) every rank renders its contiguous band of the image -- the reference shards its chunks over its devices
+    (models.py:665-669) -- and ONE all-gather of the packed keys per image collects the bands on every rank.
+    ``render_chunk(chunk_rays) -> last level's rendering dict`` replaces the model call (tests of the host logic on CPU)."""
     height, width = rays.origins.shape[:2]
     num_rays = height * width
-    flat = Rays(*(_c(r, "rays").reshape(num_rays, -1) for r in rays))
+    if render_chunk is None:
+        flat = Rays(*(_c(r, "rays").reshape(num_rays, -1) for r in rays))
+        device = model.device
+
+        def render_chunk(chunk):
+            renderings, _ = model(None, chunk, train_frac=train_frac, compute_extras=True)
+            return renderings[-1]
+    else:
+        flat = Rays(*(r.reshape(num_rays, -1) for r in rays))
+    world, rank = 1, 0
     if process_group is not None:
         import torch.distributed as dist
         world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
-    else:
-        world, rank = 1, 0
-    keys = ("rgb", "acc", "distance_mean", "depth", "distance_percentile_5", "distance_median", "distance_percentile_95")
-    widths = (3, 1, 1, 1, 1, 1, 1)
-    per = (num_rays + world - 1) // world                 # rays per rank (the last band may be short)
-    lo, hi = min(rank * per, num_rays), min((rank + 1) * per, num_rays)
-    packed = torch.zeros(per, sum(widths), device=model.device)
+    lo, hi, per = band(num_rays, world, rank)
+    packed = torch.zeros(per, sum(RENDER_WIDTHS), device=device)
     with torch.no_grad():
         for idx0 in range(lo, hi, render_chunk_size):
             idx1 = min(idx0 + render_chunk_size, hi)
-            chunk = Rays(*(r[idx0:idx1] for r in flat))
-            renderings, _ = model(None, chunk, train_frac=train_frac, compute_extras=True)
-            last = renderings[-1]
-            packed[idx0 - lo:idx1 - lo] = torch.cat([last[k].reshape(idx1 - idx0, -1) for k in keys], dim=-1)
+            last = render_chunk(Rays(*(r[idx0:idx1] for r in flat)))
+            packed[idx0 - lo:idx1 - lo] = torch.cat([last[k].reshape(idx1 - idx0, -1) for k in RENDER_KEYS], dim=-1)
     if world > 1:
         import torch.distributed as dist
-        gathered = torch.empty(world * per, sum(widths), device=model.device)
+        gathered = torch.empty(world * per, sum(RENDER_WIDTHS), device=device)
         dist.all_gather_into_tensor(gathered, packed, group=process_group)
         packed = gathered
     packed = packed[:num_rays]
     out, off = {}, 0
-    for k, w in zip(keys, widths):
+    for k, w in zip(RENDER_KEYS, RENDER_WIDTHS):
         out[k] = packed[:, off:off + w].reshape((height, width) + ((w,) if w > 1 else ()))
         off += w
     return out

@@ -112,3 +112,55 @@ def test_lazy_render_dict_behaves_like_the_plain_dict():
     d4 = _LazyRenderDict([("fg_dists", None), ("b", torch.zeros(1))], {"fg_dists": fetch})
     c = d4.copy()
     assert isinstance(c, OrderedDict) and c["fg_dists"].shape == (2, 3) and d4.pop("fg_dists").shape == (2, 3)
+
+
+# ---- config 3: mip360_model.render_image's banding / chunking / single all-gather, world size 2 over gloo -----------------
+def _stub_chunk(chunk):
+    """Per-ray outputs with the last level's keys (models.py:270-305), deterministic functions of the ray origin."""
+    o = chunk.origins[:, :1]
+    from nerfpp_b200.mip360_model import RENDER_KEYS
+    out = {k: o[:, 0] + 10.0 * i for i, k in enumerate(RENDER_KEYS)}
+    out["rgb"] = o + torch.arange(3.)
+    return out
+
+
+def _rays_c3(h, w):
+    from nerfpp_b200.mip360_model import Rays
+    idx = torch.arange(h * w, dtype=torch.float32).reshape(h, w, 1)
+    return Rays(idx.repeat(1, 1, 3), torch.ones(h, w, 3), torch.ones(h, w, 3), torch.ones(h, w, 1), torch.ones(h, w, 1), torch.ones(h, w, 1))
+
+
+def _worker_c3(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nerfpp_b200.mip360_model import render_image
+        out = render_image(None, _rays_c3(5, 7), render_chunk_size=4, process_group=dist.group.WORLD, render_chunk=_stub_chunk,
+                           device=torch.device("cpu"))
+        q.put((rank, {k: v.numpy().copy() for k, v in out.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mip360_render_image_bands_over_gloo():
+    from nerfpp_b200.mip360_model import band, render_image
+    assert band(35, 2, 0) == (0, 18, 18) and band(35, 2, 1) == (18, 35, 18) and band(3, 8, 7) == (3, 3, 1)
+    single = render_image(None, _rays_c3(5, 7), render_chunk_size=4, render_chunk=_stub_chunk, device=torch.device("cpu"))
+    assert single["rgb"].shape == (5, 7, 3) and single["depth"].shape == (5, 7)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [ctx.Process(target=_worker_c3, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for r in (0, 1):                      # every rank ends up with the whole image (35 rays: ragged bands of 18 + 17)
+        for k, v in single.items():
+            assert (got[r][k] == v.numpy()).all(), (r, k)
