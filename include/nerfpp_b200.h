@@ -341,6 +341,14 @@ int mip360_cast_encode(const float* sdist, const float* near, const float* far, 
  * and output, fp32 accumulation; K % 8 == 0, N % 128 == 0. */
 int mip360_dense_f16(const void* a, const void* w, const float* bias, void* out, int M, int N, int K, int relu,
                      void* stream);
+/* The whole resampling step between two levels of Model.__call__ (models.py:171-200) in one launch: the logits above built
+ * inline from the weights, then stepfun.sample_intervals.  t / weights are read with row strides t_ld / w_ld (pass
+ * dilated_t + 1 and dilated_w + 1 with the dilated histogram's strides: its [1:-1] slices need no copy; n_bins = the sliced
+ * bin count).  u: with jitter == NULL the ordinates [n, Ns] (u_ld = Ns) or one shared row (u_ld 0); with jitter [n] (the
+ * single_jitter draw in [0,1)) u is the shared base row (stepfun.py:203-209) and the ordinates are base + jitter * max_jitter. */
+int mip360_resample_level(const float* t, int t_ld, const float* weights, int w_ld, int n_rays, int n_bins, float anneal,
+                          float resample_padding, const float* u, int u_ld, const float* jitter, float max_jitter,
+                          int n_samples, float domain_min, float domain_max, float* out_t, void* stream);
 /* Model.__call__'s logits for the next resampling (models.py:171-185): where(sdist[1:] > sdist[:-1],
  * anneal * log(weights + padding), -inf).  sdist [n, M+1], weights [n, M] -> out_logits [n, M]. */
 int mip360_resample_logits(const float* sdist, const float* weights, int n_rays, int n_bins, float anneal,

@@ -44,16 +44,30 @@ __device__ __forceinline__ float sorted_interp1(float x, const float* xp, const 
 }
 
 // stepfun.sample_intervals (stepfun.py:214-263): t [B,M+1], w_logits [B,M], u [B,Ns] (u_ld 0 = one shared row)
+// FUSED: the whole resampling step of Model.__call__ between two levels (models.py:171-200) in one launch -- the logits
+// where(t[1:] > t[:-1], anneal * log(w + padding), -inf) are built here from the WEIGHTS (`logits` then points at them), rows
+// of t / w are read with strides t_ld / w_ld (the dilated histogram's [1:-1] slices need no copy), and with `jitter` the
+// ordinates are u[k] = base[k] + jitter[r] * max_jitter (stepfun.py:203-209, single_jitter) instead of a materialised [B,Ns].
+template <bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32)
-sample_intervals_kernel(const float* __restrict__ t, const float* __restrict__ logits, const float* __restrict__ u, int u_ld,
+sample_intervals_kernel(const float* __restrict__ t, int t_ld, const float* __restrict__ logits, int w_ld, const float* __restrict__ u, int u_ld,
+                        const float* __restrict__ jitter, float max_jitter, float anneal, float padding,
                         int B, int M, int Ns, float dmin, float dmax, float* __restrict__ out) {
   __shared__ float s_t[WARPS][MAX_BINS + 1], s_cw[WARPS][MAX_BINS + 1], s_c[WARPS][MAX_BINS + 1];
+  __shared__ float s_lg[FUSED ? WARPS : 1][FUSED ? MAX_BINS : 1];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const int r = blockIdx.x * WARPS + wl;
   if (r >= B) return;
-  const float* tr = t + (size_t)r * (M + 1);
-  const float* lr = logits + (size_t)r * M;
+  const float* tr = t + (size_t)r * t_ld;
+  const float* lr = logits + (size_t)r * w_ld;
   float* st = s_t[wl]; float* cw = s_cw[wl]; float* cen = s_c[wl];
+  if (FUSED) {
+    float* lg = s_lg[wl];
+    for (int i = lane; i < M; i += 32)
+      lg[i] = (tr[i + 1] > tr[i]) ? __fmul_rn(anneal, logf(__fadd_rn(lr[i], padding))) : -INFINITY;
+    __syncwarp();
+    lr = lg;
+  }
   // softmax (jax.nn.softmax, stepfun.py:156)
   float mx = -INFINITY;
   for (int i = lane; i < M; i += 32) mx = fmaxf(mx, lr[i]);
@@ -75,7 +89,8 @@ sample_intervals_kernel(const float* __restrict__ t, const float* __restrict__ l
   __syncwarp();
   // invert_cdf -> centres (stepfun.py:153-161)
   const float* ur = u + (size_t)r * u_ld;
-  for (int k = lane; k < Ns; k += 32) cen[k] = sorted_interp1(ur[k], cw, st, M + 1);
+  const float jit = (FUSED && jitter) ? __fmul_rn(jitter[r], max_jitter) : 0.f;
+  for (int k = lane; k < Ns; k += 32) cen[k] = sorted_interp1((FUSED && jitter) ? __fadd_rn(ur[k], jit) : ur[k], cw, st, M + 1);
   __syncwarp();
   // fenceposts: midpoints, reflected and clamped ends (stepfun.py:250-262)
   float* o = out + (size_t)r * (Ns + 1);
@@ -399,8 +414,21 @@ extern "C" int mip360_sample_intervals(const float* t, const float* w_logits, co
   NPP_CHECK_ARG(t && w_logits && u && out_t, "null argument");
   NPP_CHECK_ARG(n_rays >= 0 && n_bins >= 1 && n_bins <= mip::MAX_BINS && n_samples >= 2 && n_samples <= mip::MAX_BINS, "bad shape");
   if (n_rays == 0) return 0;
-  mip::sample_intervals_kernel<<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
-      t, w_logits, u, u_ld, n_rays, n_bins, n_samples, domain_min, domain_max, out_t);
+  mip::sample_intervals_kernel<false><<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, n_bins + 1, w_logits, n_bins, u, u_ld, nullptr, 0.f, 1.f, 0.f, n_rays, n_bins, n_samples, domain_min, domain_max, out_t);
+  NPP_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mip360_resample_level(const float* t, int t_ld, const float* weights, int w_ld, int n_rays, int n_bins, float anneal,
+                                     float resample_padding, const float* u, int u_ld, const float* jitter, float max_jitter, int n_samples,
+                                     float domain_min, float domain_max, float* out_t, void* stream) {
+  NPP_CHECK_ARG(t && weights && u && out_t, "null argument");
+  NPP_CHECK_ARG(n_rays >= 0 && n_bins >= 1 && n_bins <= mip::MAX_BINS && n_samples >= 2 && n_samples <= mip::MAX_BINS, "bad shape");
+  NPP_CHECK_ARG(t_ld >= n_bins + 1 && w_ld >= n_bins, "row strides shorter than the rows");
+  if (n_rays == 0) return 0;
+  mip::sample_intervals_kernel<true><<<(n_rays + mip::WARPS - 1) / mip::WARPS, mip::WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, t_ld, weights, w_ld, u, u_ld, jitter, max_jitter, anneal, resample_padding, n_rays, n_bins, n_samples, domain_min, domain_max, out_t);
   NPP_CHECK_LAUNCH();
   return 0;
 }

@@ -88,6 +88,7 @@ SIGNATURES = {
     "mip360_cast_encode": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
     "mip360_dense_f16": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "mip360_resample_logits": (c_int, [P, P, c_int, c_int, c_float, c_float, P, P]),
+    "mip360_resample_level": (c_int, [P, c_int, P, c_int, c_int, c_int, c_float, c_float, P, c_int, P, c_float, c_int, c_float, c_float, P, P]),
 }
 OPTIONAL = {}
 _lib = None

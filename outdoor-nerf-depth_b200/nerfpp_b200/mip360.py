@@ -25,6 +25,21 @@ def centers_u(num_samples, device):
     return _CONST[key]
 
 
+def max_jitter(num_samples):
+    """stepfun.py:203-206."""
+    u_max = EPS + (1 - EPS) / num_samples
+    return (1 - u_max) / (num_samples - 1) - EPS
+
+
+def jitter_base(num_samples, device):
+    """stepfun.py:207: linspace(0, 1 - u_max, Ns), built in float64 then rounded like jnp.linspace (cached per device)."""
+    key = ("jitter", int(num_samples), str(device))
+    if key not in _CONST:
+        u_max = EPS + (1 - EPS) / num_samples
+        _CONST[key] = torch.linspace(0, 1 - u_max, num_samples, dtype=torch.float64).float().to(device)
+    return _CONST[key]
+
+
 def jittered_u(shape_prefix, num_samples, single_jitter, device, generator=None):
     """stepfun.py:203-209: linspace(0, 1-u_max, Ns) + U[0, max_jitter).  The draw is torch's, not jax.random's."""
     u_max = EPS + (1 - EPS) / num_samples

@@ -160,6 +160,34 @@ def resample_logits(sdist, weights, anneal, resample_padding=0.0):
     return out
 
 
+def resample_level(t, weights, anneal, resample_padding, num_samples, u=None, jitter=None, domain=(0.0, 1.0)):
+    """models.py:171-200 in one launch: logits from the weights, then stepfun.sample_intervals.  ``t`` [n, M+1] / ``weights``
+    [n, M] may be row-strided VIEWS (the dilated histogram's [..., 1:-1] slices).  ``u`` [n, Ns]: explicit ordinates; else
+    ``jitter`` [n] in [0,1) (single_jitter) or None (the deterministic centres)."""
+    for x, nm in ((t, "t"), (weights, "weights")):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1):
+            raise NerfppError("%s must be a float32 CUDA matrix with unit column stride" % nm)
+    n, M = weights.shape
+    if t.shape != (n, M + 1):
+        raise ValueError("t must be [n, M+1] for weights [n, M]")
+    dev = t.device
+    jit, mj = None, 0.0
+    if u is not None:
+        uu, u_ld = _c(u, "u", 2), num_samples
+    elif jitter is not None:
+        uu, u_ld = mip360.jitter_base(num_samples, dev), 0
+        jit = _c(jitter, "jitter").reshape(-1)
+        mj = mip360.max_jitter(num_samples)
+    else:
+        uu, u_ld = mip360.centers_u(num_samples, dev), 0
+    out = torch.empty(n, num_samples + 1, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(_lib.lib().mip360_resample_level(_p(t), t.stride(0), _p(weights), weights.stride(0), n, M, float(anneal), float(resample_padding),
+                                               _p(uu), u_ld, _p(jit), float(mj), num_samples, float(domain[0]), float(domain[1]), _p(out),
+                                               _stream()), "mip360_resample_level")
+    return out
+
+
 class Model(object):
     """models.Model (models.py:47-330) with the gin bindings of configs/360.gin: raydist_fn = reciprocal,
     opaque_background = True, three levels (64, 64 proposal intervals by one shared PropMLP, 32 by the NerfMLP), dilation
@@ -207,18 +235,20 @@ class Model(object):
             prod_num_samples *= num_samples
             if i_level > 0:
                 sdist, weights = mip360.max_dilate_weights(sdist, weights, dilation, domain=(0.0, 1.0), renormalize=True)
-                sdist, weights = sdist[..., 1:-1].contiguous(), weights[..., 1:-1].contiguous()
+                sdist, weights = sdist[..., 1:-1], weights[..., 1:-1]          # views: the resampling kernel reads them strided
             s = self.anneal_slope
             anneal = (s * train_frac) / ((s - 1) * train_frac + 1) if s > 0 else 1.0
-            logits = resample_logits(sdist, weights, anneal, self.resample_padding)
+            # logits + ordinates + sample_intervals in one launch (models.py:171-200)
             if u_levels is not None and u_levels[i_level] is not None:
-                u = u_levels[i_level]
+                sdist = resample_level(sdist, weights, anneal, self.resample_padding, num_samples, u=u_levels[i_level])
             elif rng is None:
-                u = None
+                sdist = resample_level(sdist, weights, anneal, self.resample_padding, num_samples)
             else:
-                u = mip360.jittered_u((n,), num_samples, self.single_jitter, self.device,
-                                      generator=rng if isinstance(rng, torch.Generator) else None)      # True: torch's default CUDA generator
-            sdist = mip360.sample_intervals(u, sdist, logits, num_samples, single_jitter=self.single_jitter, domain=(0.0, 1.0))
+                d = 1 if self.single_jitter else num_samples
+                if not self.single_jitter:
+                    raise NotImplementedError("per-sample jitter: pass u_levels (configs/360.gin uses single_jitter)")
+                jit = torch.rand(n, d, device=self.device, generator=rng if isinstance(rng, torch.Generator) else None)
+                sdist = resample_level(sdist, weights, anneal, self.resample_padding, num_samples, jitter=jit)
             mlp = self.prop_mlp if is_prop else self.nerf_mlp
             tdist, density, rgb = mlp.level(sdist, rays)
             weights = mip360.compute_alpha_weights(density, tdist, rays.directions, opaque_background=self.opaque_background)[0]

@@ -254,6 +254,31 @@ def test_empty_batch_and_reloaded_weights():
     assert _rel(d2.cpu().numpy(), ref) <= 2e-3
 
 
+def test_fused_resample_level_is_bit_equal_to_the_separate_calls():
+    """mip360_resample_level (logits from the weights + jittered ordinates + sample_intervals in one launch, strided views of
+    the dilated histogram) against resample_logits -> jittered u -> sample_intervals on contiguous copies: the same operations,
+    bit-equal fenceposts."""
+    from nerfpp_b200 import mip360
+    from nerfpp_b200.mip360_model import resample_level, resample_logits
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n, M = 300, 64
+    t = torch.sort(torch.rand(n, M + 1, generator=g), -1)[0].to(dev)
+    t[::7, 3] = t[::7, 2]                                              # an empty interval now and then: logit -inf
+    w = torch.softmax(2 * torch.randn(n, M, generator=g), -1).to(dev)
+    td, wd = mip360.max_dilate_weights(t, w, 0.0125, domain=(0.0, 1.0), renormalize=True)
+    tv, wv = td[..., 1:-1], wd[..., 1:-1]                              # strided views
+    jit = torch.rand(n, 1, generator=g).to(dev)
+    for ns in (64, 32):
+        fused = resample_level(tv, wv, 0.7, 0.0, ns, jitter=jit)
+        logits = resample_logits(tv.contiguous(), wv.contiguous(), 0.7, 0.0)
+        u = mip360.jitter_base(ns, dev) + jit * mip360.max_jitter(ns)
+        sep = mip360.sample_intervals(u, tv.contiguous(), logits, ns, single_jitter=True, domain=(0.0, 1.0))
+        assert torch.equal(fused, sep)
+        det = resample_level(tv, wv, 0.7, 0.0, ns)                     # rng=None: the deterministic centres
+        assert torch.equal(det, mip360.sample_intervals(None, tv.contiguous(), logits, ns, domain=(0.0, 1.0)))
+
+
 def test_render_image_chunks_equal_one_pass():
     """models.render_image's chunk loop: an image rendered in ragged chunks equals the one-pass render (rays are independent);
     keys and shapes as the reference's last-level rendering."""
