@@ -213,9 +213,10 @@ class Model(object):
         self.prop_mlp.load_flax(params["PropMLP_0"])
         return self
 
-    def __call__(self, rng, rays, train_frac=1.0, compute_extras=True, u_levels=None):
+    def __call__(self, rng, rays, train_frac=1.0, compute_extras=True, u_levels=None, on_level=None):
         """-> (renderings, ray_history), one entry per level.  ``rng``: None (deterministic interval centres) or a
-        torch.Generator / True (torch's default CUDA generator) for the jitter; ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
+        torch.Generator / True (torch's default CUDA generator) for the jitter; ``on_level(i, rendering, history_entry)`` is
+        called as soon as a level is rendered (GraphedModelStep forks that level's loss kernels from it); ``u_levels`` overrides the per-level inverse-CDF ordinates (tests)."""
         near, far = _c(rays.near, "near").reshape(-1, 1), _c(rays.far, "far").reshape(-1, 1)
         n = near.shape[0]
         # the initial interval [0, 1] with weight 1 (models.py:129-136) and the proposal levels' all-zero colours are constants
@@ -257,6 +258,8 @@ class Model(object):
             rendering = mip360.volumetric_rendering(rgb, weights, tdist, self.bg_intensity, far.reshape(-1), compute_extras)
             renderings.append(rendering)
             ray_history.append(dict(density=density, rgb=rgb, sdist=sdist, tdist=tdist, weights=weights))
+            if on_level is not None:
+                on_level(i_level, rendering, ray_history[-1])
         return renderings, ray_history
 
 
@@ -347,6 +350,7 @@ class GraphedModelStep(object):
         if host_io:
             self._in_host.copy_(self._in_dev)
         self._n_out = 4 * n + len(LOSS_KEYS)
+        self._side = torch.cuda.Stream(device=dev)
         self._out_host = torch.zeros(self._n_out).pin_memory() if host_io else None
         sigma = float(depth_sigma) * float(depth_scale)                      # train_utils.py:125
 
@@ -355,17 +359,28 @@ class GraphedModelStep(object):
                 self._in_dev.copy_(self._in_host, non_blocking=True)
             d = self.dev_in
             rays = Rays(d["origins"], d["directions"], d["viewdirs"], d["radii"], d["near"], d["far"])
-            renderings, history = model(True if jitter else None, rays, train_frac=train_frac, compute_extras=True)
-            mses, dls = [], []
-            for r, h in zip(renderings, history):
-                mses.append(ops.fused_loss(r["rgb"], d["rgb"], depth_loss_type=None)[0:1])          # lossmult = 1: mean squared residual
-                if depth_loss_type == "kl":
-                    dls.append(mip360.depth_loss(h["weights"], h["tdist"], d["disps_sup"].reshape(-1), r["distance_mean"], sigma,
-                                                 d["directions"], "kl").reshape(1))
-                else:
-                    dls.append(mip360.depth_point_loss(r["distance_mean"], d["disps_sup"].reshape(-1), depth_loss_type).reshape(1))
+            # each level's data terms are forked onto a side stream as soon as the level is rendered: they run beside the
+            # next level's field kernels (and the last level's beside the interlevel / distortion terms) instead of in a
+            # serial tail of ~20 small launches
+            main = torch.cuda.current_stream(dev)
+            mses, dls = [None] * 3, [None] * 3
+
+            def level_losses(i, r, h):
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(ev)
+                    mses[i] = ops.fused_loss(r["rgb"], d["rgb"], depth_loss_type=None)[0:1]          # lossmult = 1: mean squared residual
+                    if depth_loss_type == "kl":
+                        dls[i] = mip360.depth_loss(h["weights"], h["tdist"], d["disps_sup"].reshape(-1), r["distance_mean"], sigma,
+                                                   d["directions"], "kl").reshape(1)
+                    else:
+                        dls[i] = mip360.depth_point_loss(r["distance_mean"], d["disps_sup"].reshape(-1), depth_loss_type).reshape(1)
+
+            renderings, history = model(True if jitter else None, rays, train_frac=train_frac, compute_extras=True, on_level=level_losses)
             inter = mip360.interlevel_loss(history).reshape(1)
             dist = mip360.distortion_loss(history).reshape(1)
+            main.wait_stream(self._side)
             packed = torch.cat([renderings[-1]["rgb"].reshape(-1), renderings[-1]["depth"].reshape(-1)] + mses + dls + [inter, dist])
             if host_io:
                 self._out_host.copy_(packed, non_blocking=True)

@@ -279,6 +279,37 @@ def test_fused_resample_level_is_bit_equal_to_the_separate_calls():
         assert torch.equal(det, mip360.sample_intervals(None, tv.contiguous(), logits, ns, domain=(0.0, 1.0)))
 
 
+def test_graphed_model_step_matches_eager():
+    """GraphedModelStep (forward + the trainer's loss terms as ONE CUDA graph with an H2D and a D2H node; per-level loss kernels
+    forked onto a side stream) replays to the same rgb / depth / loss terms as the eager calls -- twice, with new inputs."""
+    from nerfpp_b200 import mip360, ops
+    from nerfpp_b200.mip360_model import GraphedModelStep, LOSS_KEYS, Model, Rays
+    dev = _dev()
+    n = 64
+    model = Model(dev)
+    model.nerf_mlp.load(MM.init_mlp_params(8, 1024, True, seed=5))
+    model.prop_mlp.load(MM.init_mlp_params(4, 256, False, seed=6))
+    step = GraphedModelStep(model, n, train_frac=0.5, jitter=False, depth_sigma=0.01, host_io=True)
+    for seed in (1, 2):
+        rays = MM.synthetic_rays(n, seed=seed)
+        g = np.random.default_rng(seed)
+        batch = {k: torch.from_numpy(rays[k]) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")}
+        batch["rgb"] = torch.from_numpy(g.random((n, 3)).astype(F32))
+        batch["disps_sup"] = torch.from_numpy((g.random((n, 1)) * 5).astype(F32))
+        out = step(batch)
+        got = {k: v.clone() for k, v in out.items()}
+        R = Rays(*(batch[k].to(dev) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")))
+        with torch.no_grad():
+            rend, hist = model(None, R, train_frac=0.5)
+            want = [float(ops.fused_loss(r["rgb"], batch["rgb"].to(dev), depth_loss_type=None)[0]) for r in rend]
+            want += [float(mip360.depth_loss(h["weights"], h["tdist"], batch["disps_sup"].to(dev).reshape(-1), r["distance_mean"], 0.01,
+                                             R.directions, "kl")) for r, h in zip(rend, hist)]
+            want += [float(mip360.interlevel_loss(hist)), float(mip360.distortion_loss(hist))]
+        assert torch.equal(got["rgb"], rend[-1]["rgb"].cpu()) and torch.equal(got["depth"], rend[-1]["depth"].cpu())
+        np.testing.assert_allclose(got["losses"].numpy(), np.array(want, F32), rtol=1e-6, atol=1e-9)
+        assert len(LOSS_KEYS) == 8
+
+
 def test_render_image_chunks_equal_one_pass():
     """models.render_image's chunk loop: an image rendered in ragged chunks equals the one-pass render (rays are independent);
     keys and shapes as the reference's last-level rendering."""
