@@ -351,6 +351,28 @@ def test_scaled_weights_split_precision_holds(scale):
     assert errs[False][0] <= 1e-2
 
 
+def test_model_matches_committed_fixture(golden_dir):
+    """The committed fixture tests/golden/mip360_model.npz (the oracle's output on a seeded 16-ray case, with the script that
+    wrote it) as the target: split-precision model within 1e-4 per ray on colour, first-level fenceposts to 1e-6."""
+    import os
+    import gen_golden_mip360_model as G
+    from nerfpp_b200.mip360_model import Model, Rays
+    dev = _dev()
+    gold = np.load(os.path.join(golden_dir, "mip360_model.npz"))
+    prop = MM.init_mlp_params(4, 256, False, seed=G.SEEDS["prop"])
+    nerf = MM.init_mlp_params(8, 1024, True, seed=G.SEEDS["nerf"])
+    R = Rays(*(torch.from_numpy(gold["ray_" + k]).to(dev) for k in ("origins", "directions", "viewdirs", "radii", "near", "far")))
+    model = Model(dev, prec=True)
+    model.nerf_mlp.load(nerf)
+    model.prop_mlp.load(prop)
+    rend, hist = model(None, R, train_frac=0.5, u_levels=[torch.from_numpy(gold["u_%d" % i]).to(dev) for i in range(3)])
+    np.testing.assert_allclose(hist[0]["sdist"].cpu().numpy(), gold["sdist_0"], atol=1e-6)
+    rgb, ref = rend[-1]["rgb"].cpu().numpy(), gold["rgb_2"]
+    rel = np.abs(rgb - ref).max(-1) / np.maximum(np.abs(ref).max(-1), 1e-2)
+    assert rel.max() <= 1e-4, rel.max()
+    np.testing.assert_allclose(rend[-1]["acc"].cpu().numpy(), gold["acc_2"], atol=1e-5)
+
+
 def test_cpu_tensors_raise():
     from nerfpp_b200 import NerfppError
     from nerfpp_b200.mip360_model import MLP

@@ -259,3 +259,21 @@ def test_model_forward_three_levels():
     assert rend[-1]["rgb"].shape == (16, 3) and np.all(np.isfinite(rend[-1]["rgb"]))
     assert np.all(rend[0]["rgb"] < 1e-6)                   # the proposal levels have no colour (disable_rgb)
     assert np.all(rend[-1]["depth"] >= hist[-1]["tdist"][:, 0]) and np.all(rend[-1]["depth"] <= hist[-1]["tdist"][:, -1])
+
+
+def test_oracle_reproduces_its_committed_fixture():
+    """tests/golden/mip360_model.npz (oracle/gen_golden_mip360_model.py): the restatement has not drifted.  Fenceposts to 1e-6,
+    densities / colours to 1e-5 relative (BLAS summation order may differ between machines)."""
+    import os
+    import gen_golden_mip360_model as G
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mip360_model.npz")
+    gold = np.load(path)
+    out, _ = G.build()
+    assert set(gold.files) == set(out)
+    for k in gold.files:
+        if k.startswith(("ray_", "u_")):
+            assert np.array_equal(gold[k], out[k]), k
+        elif k.startswith(("sdist", "tdist")):
+            np.testing.assert_allclose(out[k], gold[k], rtol=1e-5, atol=1e-6, err_msg=k)
+        else:
+            np.testing.assert_allclose(out[k], gold[k], rtol=2e-4, atol=2e-5, err_msg=k)
