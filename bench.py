@@ -763,6 +763,7 @@ def c3_gemm_roofline(dev, n_rays, prec, model, reps=10):
     return {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
             "traffic": (t or {}).get("bytes_per_launch"), "traffic_source": t, "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % how,
             "launches_per_step": len(gemm_layers), "avg_launch_ms": tot_ms * passes / len(gemm_layers), "algorithmic_flops_per_step": flops,
+            "peak_sustained": sustained, "frac_sustained": achieved / sustained,      # the leg runs after the timed steps, on a box already at its power cap
             "levels": levels,
             "note": ("the NerfMLP's Dense layers (87 %% of the step's FLOPs); K is padded to 64 (504 -> 512, 283 -> 320), padded FLOPs are not in the numerator"
                      + ("; split precision: timed through the NerfMLP level's whole field call (the one-layer entry point is fp16 only); its three MMA "
