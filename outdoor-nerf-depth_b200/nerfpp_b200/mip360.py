@@ -78,8 +78,9 @@ def sample_intervals(u, t, w_logits, num_samples, single_jitter=False, domain=(-
     return out.reshape(lead + (num_samples + 1,))
 
 
-def compute_alpha_weights(density, tdist, dirs, opaque_background=False):
-    """render.compute_alpha_weights (render.py:130-151) -> (weights, alpha, trans)."""
+def compute_alpha_weights(density, tdist, dirs, opaque_background=False, weights_only=False):
+    """render.compute_alpha_weights (render.py:130-151) -> (weights, alpha, trans); ``weights_only``: alpha and trans are not
+    materialised (None) -- Model.__call__ keeps only the weights (models.py:233-238)."""
     dn = _c(density, "density")
     lead = tuple(dn.shape[:-1])
     S = dn.shape[-1]
@@ -87,11 +88,12 @@ def compute_alpha_weights(density, tdist, dirs, opaque_background=False):
     td = _c(tdist, "tdist").reshape(-1, S + 1)
     dr = _c(dirs, "dirs").reshape(-1, 3)
     n = dn.shape[0]
-    w, a, tr = (torch.empty(n, S, device=dn.device, dtype=torch.float32) for _ in range(3))
+    w = torch.empty(n, S, device=dn.device, dtype=torch.float32)
+    a, tr = (None, None) if weights_only else (torch.empty_like(w), torch.empty_like(w))
     with torch.cuda.device(dn.device):
         check(_lib.lib().mip360_compute_alpha_weights(_p(dn), _p(td), _p(dr), n, S, int(bool(opaque_background)), _p(w), _p(a),
                                                       _p(tr), _stream()), "mip360_compute_alpha_weights")
-    return tuple(x.reshape(lead + (S,)) for x in (w, a, tr))
+    return tuple((x.reshape(lead + (S,)) if x is not None else None) for x in (w, a, tr))
 
 
 def volumetric_rendering(rgbs, weights, tdist, bg_rgbs, t_far, compute_extras=True, extras=None):

@@ -252,7 +252,7 @@ class Model(object):
                 sdist = resample_level(sdist, weights, anneal, self.resample_padding, num_samples, jitter=jit)
             mlp = self.prop_mlp if is_prop else self.nerf_mlp
             tdist, density, rgb = mlp.level(sdist, rays)
-            weights = mip360.compute_alpha_weights(density, tdist, rays.directions, opaque_background=self.opaque_background)[0]
+            weights = mip360.compute_alpha_weights(density, tdist, rays.directions, opaque_background=self.opaque_background, weights_only=True)[0]
             if rgb is None:
                 rgb = zero_rgb                                                 # disable_rgb: zeros (models.py:511-512)
             rendering = mip360.volumetric_rendering(rgb, weights, tdist, self.bg_intensity, far.reshape(-1), compute_extras)
