@@ -373,6 +373,38 @@ def test_model_matches_committed_fixture(golden_dir):
     np.testing.assert_allclose(rend[-1]["acc"].cpu().numpy(), gold["acc_2"], atol=1e-5)
 
 
+def test_full_size_properties():
+    """BASELINE.json's full size for config 3 (4096 rays x 64 / 64 / 32 intervals), where the oracle takes minutes: the
+    size-independent properties instead -- sorted fenceposts inside the warp's range, non-negative weights that sum to one
+    (opaque background), colours inside the padded sigmoid range, depth inside the ray's extent, and bit-reproducibility
+    (no atomics on the path)."""
+    from nerfpp_b200.mip360_model import Model
+    dev = _dev()
+    n = 4096
+    rays = MM.synthetic_rays(n, seed=123)
+    R = _rays_t(rays, dev)
+    model = Model(dev).init(7)
+    g = torch.Generator(device=dev)
+    outs = []
+    for _ in range(2):
+        g.manual_seed(5)
+        rend, hist = model(g, R, train_frac=0.3)
+        outs.append((rend[-1]["rgb"].clone(), rend[-1]["depth"].clone(), hist[-1]["sdist"].clone()))
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+    assert [tuple(h["sdist"].shape) for h in hist] == [(n, 65), (n, 65), (n, 33)]
+    for r, h in zip(rend, hist):
+        sd, td, w = h["sdist"], h["tdist"], h["weights"]
+        assert bool((sd[:, 1:] >= sd[:, :-1]).all()) and float(sd.min()) >= 0 and float(sd.max()) <= 1
+        assert bool((td[:, 1:] >= td[:, :-1]).all()) and bool(torch.isfinite(td).all())
+        assert float(w.min()) >= 0 and float((w.sum(-1) - 1).abs().max()) <= 2e-5
+        assert float((r["acc"] - 1).abs().max()) <= 2e-5
+        assert bool((r["depth"] >= td[:, 0] - 1e-6).all()) and bool((r["depth"] <= td[:, -1]).all())
+    c = hist[-1]["rgb"]
+    assert float(c.min()) >= -0.001 - 1e-6 and float(c.max()) <= 1.001 + 1e-6
+    assert float(rend[0]["rgb"].abs().max()) <= 3e-5           # the proposal levels carry no colour: (1 - acc) * background only
+
+
 def test_cpu_tensors_raise():
     from nerfpp_b200 import NerfppError
     from nerfpp_b200.mip360_model import MLP
